@@ -1,0 +1,242 @@
+"""ctypes binding of the closed-form C++ CPU oracle (oracle/c).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this.
+Arrays are NumPy fp64, chains as rows ([n_chain, dim], C-contiguous).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+
+MODEL_TOY, MODEL_HIER, MODEL_FN, MODEL_HH = 0, 1, 2, 3
+PARAM_UNBOUNDED, PARAM_NORMAL = 0, 1
+(SOLVER_QUASI_NEWTON, SOLVER_NEWTON, SOLVER_NEWTON_LS, SOLVER_MICI_NEWTON,
+ SOLVER_MICI_QUASI_NEWTON) = range(5)  # fmt: skip
+ST_OK, ST_DIVERGED, ST_NOT_CONVERGED, ST_NON_REVERSIBLE, ST_H_DIVERGED, ST_LINALG = range(6)
+NORM_MAX, NORM_EUCLID = 0, 1
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "c")
+    if force or not os.path.exists(LIB_PATH):
+        subprocess.check_call(["make", "-C", src] + (["-B"] if force else []))
+    return LIB_PATH
+
+
+class SolverOpts(C.Structure):
+    _fields_ = [
+        ("solver", C.c_int), ("max_iters", C.c_int), ("max_ls", C.c_int),
+        ("norm", C.c_int), ("ctol", C.c_double), ("ptol", C.c_double),
+        ("dtol", C.c_double), ("rev_tol", C.c_double), ("rev_norm", C.c_int),
+        ("_pad", C.c_int),
+    ]  # fmt: skip
+
+
+def solver_opts(solver=SOLVER_NEWTON, constraint_tol=1e-9, position_tol=1e-8,
+                divergence_tol=1e10, max_iters=50, max_line_search_iters=10,
+                norm=NORM_MAX, reverse_check_tol=None, reverse_check_norm=NORM_MAX):  # fmt: skip
+    if reverse_check_tol is None:
+        reverse_check_tol = 2 * position_tol
+    return SolverOpts(solver, max_iters, max_line_search_iters, norm, constraint_tol,
+                      position_tol, divergence_tol, reverse_check_tol,
+                      reverse_check_norm, 0)  # fmt: skip
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB_PATH)
+        _lib.orc_model_create.restype = C.c_void_p
+        _lib.orc_model_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        _lib.orc_philox_uniform.restype = C.c_double
+        _lib.orc_philox_uniform.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
+        _lib.orc_philox_normals.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int,
+                                            C.c_void_p]  # fmt: skip
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class OracleModel:
+    def __init__(self, model_id, dim_y, param, data):
+        data = _f(data).ravel()
+        self.h = C.c_void_p(lib().orc_model_create(model_id, dim_y, param, _p(data),
+                                                   data.size))  # fmt: skip
+        if not self.h:
+            raise ValueError("oracle model could not be created")
+        L = lib()
+        self.U, self.Y, self.Q = (L.orc_dim_u(self.h), L.orc_dim_y(self.h),
+                                  L.orc_dim_q(self.h))  # fmt: skip
+        self.dense = bool(L.orc_is_dense(self.h))
+        self.K = self.Y if self.dense else self.U
+        self.hier = model_id == MODEL_HIER
+        self.model_id = model_id
+
+    @classmethod
+    def toy(cls, sigma, y=1.0, coeff=2.0):
+        return cls(MODEL_TOY, 1, 0, [sigma, y, coeff])
+
+    @classmethod
+    def hier(cls, y_obs, sigma, parametrization="unbounded"):
+        y_obs, sigma = _f(y_obs), _f(sigma)
+        par = PARAM_NORMAL if parametrization == "normal" else PARAM_UNBOUNDED
+        return cls(MODEL_HIER, y_obs.size, par, np.concatenate([y_obs, sigma]))
+
+    def __del__(self):
+        try:
+            lib().orc_model_destroy(self.h)
+        except Exception:
+            pass
+
+    # ---- individual operations (one per row of SURVEY 2b)
+    def constr(self, q):
+        q = _f(q)
+        c = np.empty((q.shape[0], self.Y))
+        lib().orc_constr(self.h, C.c_int64(q.shape[0]), _p(q), _p(c))
+        return c
+
+    def jacob_constr_blocks(self, q):
+        q = _f(q)
+        n = q.shape[0]
+        dy_du = np.empty((n, self.Y, self.U))
+        dy_dv = np.empty((n, self.Y)) if self.hier else None
+        dy_dn, c = np.empty((n, self.Y)), np.empty((n, self.Y))
+        lib().orc_jacob_constr_blocks(self.h, C.c_int64(n), _p(q), _p(dy_du), _p(dy_dv),
+                                      _p(dy_dn), _p(c))  # fmt: skip
+        return (dy_du, dy_dv, dy_dn), c
+
+    def decompose_gram(self, jac):
+        dy_du, dy_dv, dy_dn = jac
+        n = dy_du.shape[0]
+        chol, d = np.empty((n, self.K, self.K)), np.empty((n, self.Y))
+        lib().orc_decompose_gram(self.h, C.c_int64(n), _p(dy_du), _p(dy_dv), _p(dy_dn),
+                                 _p(chol), _p(d))  # fmt: skip
+        return chol, d
+
+    def log_det_sqrt_gram(self, q):
+        q = _f(q)
+        val = np.empty(q.shape[0])
+        lib().orc_log_det_sqrt_gram(self.h, C.c_int64(q.shape[0]), _p(q), _p(val))
+        return val
+
+    def grad_log_det_sqrt_gram(self, q):
+        q = _f(q)
+        val, g = np.empty(q.shape[0]), np.empty_like(q)
+        lib().orc_grad_log_det_sqrt_gram(self.h, C.c_int64(q.shape[0]), _p(q), _p(g),
+                                         _p(val))  # fmt: skip
+        return g, val
+
+    def neg_log_dens(self, q, with_grad=True):
+        q = _f(q)
+        val = np.empty(q.shape[0])
+        g = np.empty_like(q) if with_grad else None
+        lib().orc_neg_log_dens(self.h, C.c_int64(q.shape[0]), _p(q), _p(val), _p(g))
+        return (val, g) if with_grad else val
+
+    def lmult_by_jacob_constr(self, jac, v):
+        v = _f(v)
+        out = np.empty((v.shape[0], self.Y))
+        lib().orc_lmult_by_jacob_constr(self.h, C.c_int64(v.shape[0]), _p(jac[0]),
+                                        _p(jac[1]), _p(jac[2]), _p(v), _p(out))  # fmt: skip
+        return out
+
+    def rmult_by_jacob_constr(self, jac, w):
+        w = _f(w)
+        out = np.empty((w.shape[0], self.Q))
+        lib().orc_rmult_by_jacob_constr(self.h, C.c_int64(w.shape[0]), _p(jac[0]),
+                                        _p(jac[1]), _p(jac[2]), _p(w), _p(out))  # fmt: skip
+        return out
+
+    def lmult_by_pinv_jacob_constr(self, jac, gram, w):
+        w = _f(w)
+        out = np.empty((w.shape[0], self.Q))
+        lib().orc_lmult_by_pinv_jacob_constr(
+            self.h, C.c_int64(w.shape[0]), _p(jac[0]), _p(jac[1]), _p(jac[2]),
+            _p(gram[0]), _p(gram[1]), _p(w), _p(out))  # fmt: skip
+        return out
+
+    def normal_space_component(self, jac, gram, v):
+        v = _f(v)
+        out = np.empty((v.shape[0], self.Q))
+        lib().orc_normal_space_component(
+            self.h, C.c_int64(v.shape[0]), _p(jac[0]), _p(jac[1]), _p(jac[2]),
+            _p(gram[0]), _p(gram[1]), _p(v), _p(out))  # fmt: skip
+        return out
+
+    def lmult_by_inv_jacob_product(self, jac_l, jac_r, w):
+        w = _f(w)
+        out = np.empty((w.shape[0], self.Y))
+        lib().orc_lmult_by_inv_jacob_product(
+            self.h, C.c_int64(w.shape[0]), _p(jac_l[0]), _p(jac_l[1]), _p(jac_l[2]),
+            _p(jac_r[0]), _p(jac_r[1]), _p(jac_r[2]), _p(w), _p(out))  # fmt: skip
+        return out
+
+    # ---- projection / step / transition drivers
+    def solve_projection(self, q, q_prev, dt, opts):
+        q, q_prev = _f(q), _f(q_prev)
+        n = q.shape[0]
+        q_out, mu = np.empty_like(q), np.empty_like(q)
+        iters, n_constr, status = (np.empty(n, np.int32) for _ in range(3))
+        ndq, err = np.empty(n), np.empty(n)
+        lib().orc_solve_projection(
+            self.h, C.c_int64(n), _p(q), _p(q_prev), C.c_double(dt), C.byref(opts),
+            _p(q_out), _p(mu), _p(iters), _p(ndq), _p(err), _p(n_constr), _p(status))  # fmt: skip
+        return dict(q=q_out, mu=mu, iters=iters, norm_dq=ndq, err=err,
+                    n_constr=n_constr, status=status)  # fmt: skip
+
+    def leapfrog_steps(self, q, p, dt, n_step, opts, dt_per_chain=None):
+        q, p = _f(q).copy(), _f(p).copy()
+        n = q.shape[0]
+        status, n_done, itf, itr = (np.empty(n, np.int32) for _ in range(4))
+        h0, h1 = np.empty(n), np.empty(n)
+        dpc = None if dt_per_chain is None else _f(dt_per_chain)
+        lib().orc_leapfrog_steps(
+            self.h, C.c_int64(n), _p(q), _p(p), C.c_double(dt), _p(dpc), C.c_int(n_step),
+            C.byref(opts), _p(status), _p(n_done), _p(itf), _p(itr), _p(h0), _p(h1))  # fmt: skip
+        return dict(q=q, p=p, status=status, n_done=n_done, iters_fwd=itf, iters_rev=itr,
+                    h_init=h0, h_final=h1)  # fmt: skip
+
+    def hmc_transition(self, q, dt, n_step, opts, mom_noise=None, unif=None, seed=0,
+                       chain0=0, iteration=0, max_delta_h=1000.0, dt_per_chain=None):  # fmt: skip
+        q = _f(q).copy()
+        n = q.shape[0]
+        status, acc, n_done, its = (np.empty(n, np.int32) for _ in range(4))
+        a_stat, h = np.empty(n), np.empty(n)
+        mom_noise = None if mom_noise is None else _f(mom_noise)
+        unif = None if unif is None else _f(unif)
+        dpc = None if dt_per_chain is None else _f(dt_per_chain)
+        lib().orc_hmc_transition(
+            self.h, C.c_int64(n), _p(q), C.c_double(dt), _p(dpc), C.c_int(n_step),
+            C.byref(opts), C.c_double(max_delta_h), _p(mom_noise), _p(unif),
+            C.c_uint64(seed), C.c_uint64(chain0), C.c_uint32(iteration), _p(status),
+            _p(acc), _p(a_stat), _p(n_done), _p(its), _p(h))  # fmt: skip
+        return dict(q=q, status=status, accepted=acc, accept_stat=a_stat, n_done=n_done,
+                    iters_total=its, h=h)  # fmt: skip
+
+
+def philox_normals(seed, chain, iteration, n):
+    out = np.empty(n + (n & 1))
+    lib().orc_philox_normals(seed, chain, iteration, n, _p(out))
+    return out[:n]
+
+
+def philox_uniform(seed, chain, iteration):
+    return lib().orc_philox_uniform(seed, chain, iteration)
+
+
+def max_threads():
+    return lib().orc_max_threads()

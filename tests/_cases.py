@@ -1,0 +1,74 @@
+"""Shared model / state builders for the tests (oracle side)."""
+import numpy as np
+
+import c_oracle
+import mlift_oracle  # noqa: F401  (sets torch default dtype)
+from mlift_oracle.mici import ChainState, DenseConstrainedEuclideanMetricSystem
+from mlift_oracle.models import EightSchools, Toy2D
+from mlift_oracle.systems import HierarchicalLatentVariableModelSystem
+
+EIGHT_SCHOOLS_Y = np.array([28.0, 8.0, -3.0, 7.0, -1.0, 1.0, 18.0, 12.0])
+EIGHT_SCHOOLS_SIGMA = np.array([15.0, 10.0, 16.0, 11.0, 9.0, 11.0, 10.0, 18.0])
+
+
+def synthetic_schools(n_school, seed=202101):
+    """sigma_j~U(9,18), y_j = 4.4 + 3.6 N(0,1) + sigma_j N(0,1)."""
+    rng = np.random.default_rng(seed)
+    sigma = rng.uniform(9.0, 18.0, n_school)
+    y = 4.4 + 3.6 * rng.standard_normal(n_school) + sigma * rng.standard_normal(n_school)
+    return y, sigma
+
+
+def hier_case(parametrization="unbounded", y=EIGHT_SCHOOLS_Y, sigma=EIGHT_SCHOOLS_SIGMA):
+    model = EightSchools(y, sigma, parametrization)
+    system = HierarchicalLatentVariableModelSystem(
+        model.generate_y, model.data, model.dim_u, model.extended_prior_neg_log_dens
+    )
+    cm = c_oracle.OracleModel.hier(y, sigma, parametrization)
+    return model, system, cm
+
+
+def hier_states(model, n, seed=7, scale=1.0):
+    """On-manifold positions with moderate u (prior draws can be extreme)."""
+    rng = np.random.default_rng(seed)
+    Y = model.dim_y
+    u = np.stack([rng.normal(0.0, 1.0, n) * scale, rng.normal(0.5, 0.7, n) * scale], 1)
+    v = rng.standard_normal((n, Y))
+    if model.data["parametrization"] == "normal":
+        mu, tau = 5.0 * u[:, 0], None
+        import torch
+
+        tau = model.generate_params(torch.as_tensor(u.T), model.data)["tau"].numpy()
+    else:
+        mu, tau = u[:, 0], np.exp(u[:, 1])
+    x = mu[:, None] + tau[:, None] * v
+    nn = (model.data["y_obs"].numpy()[None] - x) / model.data["sigma"].numpy()[None]
+    return np.concatenate([u, v, nn], 1)
+
+
+def toy_case(sigma=0.1, y=1.0, coeff=2.0):
+    model = Toy2D(sigma, y, coeff)
+    system = DenseConstrainedEuclideanMetricSystem(Toy2D.neg_log_dens, model.constr)
+    cm = c_oracle.OracleModel.toy(sigma, y, coeff)
+    return model, system, cm
+
+
+def toy_states(model, n, seed=3):
+    rng = np.random.default_rng(seed)
+    return model.lift(rng.standard_normal((n, 2)))
+
+
+def tangent_momentum(cm, q, seed=11):
+    rng = np.random.default_rng(seed)
+    p = rng.standard_normal(q.shape)
+    jac, _ = cm.jacob_constr_blocks(q)
+    gram = cm.decompose_gram(jac)
+    return p - cm.normal_space_component(jac, gram, p)
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / (1e-300 + np.maximum(np.abs(b), 1.0))))
+
+
+__all__ = [n for n in dir() if not n.startswith("__")]
