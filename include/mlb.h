@@ -1,0 +1,264 @@
+/* mlb.h - C ABI of the B200-native constrained-HMC hot path (libmlb.so).
+ *
+ * Drop-in boundary for the hot path of thiery-lab/manifold_lifting (`mlift`): each entry
+ * point replaces one of the reference's XLA:CPU-jitted callables (the jit table at
+ * mlift/systems.py:328-346) or the Mici-driven loop around them, batched over
+ * independent chains.  All file:line citations are relative to the reference tree.
+ *
+ * Conventions
+ *   - All array arguments are DEVICE pointers unless the function name ends in `_host`.
+ *   - Numeric type is fp64 (`double`) everywhere (systems.py:8); counters and status
+ *     codes are `int32_t`.
+ *   - Chain-state arrays are component-major ("SoA"): element (k, chain) of a
+ *     [dim][n_chain] array lives at `ptr[k * ld + chain]`, ld >= n_chain.  A torch
+ *     tensor of shape [n_chain, dim] with strides (1, ld) is a view of it.
+ *   - The library never allocates or frees caller memory; outputs are written into
+ *     caller-provided buffers.  No global mutable state; every call is re-entrant given
+ *     distinct buffers; `stream` is a `cudaStream_t` passed as `void*` (NULL = default).
+ *   - Return value: 0 on success, negative `MLB_ERR_*` for argument / CUDA errors.
+ *     Per-chain numerical failures are NOT errors: they are reported in `status[chain]`
+ *     (the reference raises `ConvergenceError` / Mici raises `NonReversibleStepError`,
+ *     solvers.py:86-95; a batched kernel reports a mask instead).
+ *   - `generate_y` is an arbitrary Python closure in the reference (systems.py:520-527);
+ *     it cannot cross a C ABI, so a model is described by `mlb_model_desc`.
+ */
+#ifndef MLB_H_
+#define MLB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLB_VERSION 100
+
+/* ---- process-level error codes */
+enum {
+  MLB_OK = 0,
+  MLB_ERR_ARG = -1,       /* bad argument (null pointer, unsupported dims, ...) */
+  MLB_ERR_CUDA = -2,      /* CUDA runtime error; see mlb_last_error() */
+  MLB_ERR_UNSUPPORTED = -3 /* model / shape combination not compiled in */
+};
+
+/* ---- per-chain status codes (written to `status[chain]`) */
+enum {
+  MLB_ST_OK = 0,
+  MLB_ST_DIVERGED = 1,       /* |c| > divergence_tol or NaN  (solvers.py:86-90)  */
+  MLB_ST_NOT_CONVERGED = 2,  /* max_iters reached            (solvers.py:91-95)  */
+  MLB_ST_NON_REVERSIBLE = 3, /* Mici reversibility check failed                  */
+  MLB_ST_H_DIVERGED = 4,     /* |h - h_init| > max_delta_h   (notebook cell 44)  */
+  MLB_ST_LINALG = 5          /* singular / non-PD factorisation                  */
+};
+
+/* ---- models */
+enum {
+  MLB_MODEL_TOY = 0,  /* toy_2d_model.py:43-87 / notebook; additive noise, dense Gram */
+  MLB_MODEL_HIER = 1, /* eight_schools.py:28-53; hierarchical, Woodbury Gram          */
+  MLB_MODEL_FN = 2,   /* fitzhugh_nagumo.py:20-64; additive noise, RK4                */
+  MLB_MODEL_HH = 3    /* hh_current_stimulus.py:19-203; additive noise, exp-Euler     */
+};
+
+enum { MLB_PARAM_UNBOUNDED = 0, MLB_PARAM_NORMAL = 1 }; /* utils.py:37-46 */
+
+/* ---- projection solvers */
+enum {
+  MLB_SOLVER_QUASI_NEWTON = 0,     /* systems.py:190-228 / solvers.py:16-95        */
+  MLB_SOLVER_NEWTON = 1,           /* systems.py:230-270 / solvers.py:98-169       */
+  MLB_SOLVER_NEWTON_LS = 2,        /* systems.py:272-326 / solvers.py:172-256      */
+  MLB_SOLVER_MICI_NEWTON = 3,      /* mici.solvers.solve_projection_onto_manifold_newton
+                                      (toy configs, toy_2d_model.py:170-174)       */
+  MLB_SOLVER_MICI_QUASI_NEWTON = 4 /* mici...quasi_newton (same call site)         */
+};
+
+enum { MLB_NORM_MAX = 0, MLB_NORM_EUCLIDEAN = 1 }; /* solvers.py:6-13 */
+
+/* Model description.  `data` is a HOST array, copied at creation:
+ *   TOY : {sigma, y, coeff}                        (n_data = 3)
+ *   HIER: {y_obs[dim_y], sigma[dim_y]}             (n_data = 2*dim_y)
+ *   FN  : see mlb_ode.h layout in DESIGN.md        HH: idem                        */
+typedef struct mlb_model_desc {
+  int32_t model;           /* MLB_MODEL_*                                   */
+  int32_t dim_y;           /* number of observations                        */
+  int32_t parametrization; /* MLB_PARAM_*                                   */
+  int32_t n_data;
+  const double* data;
+} mlb_model_desc;
+
+typedef struct mlb_model mlb_model; /* opaque */
+
+/* Solver + integrator options; mirrors the keyword arguments of the reference solvers
+ * (solvers.py:16-26, 172-183) and of Mici's ConstrainedLeapfrogIntegrator
+ * (utils.py:322-327).  Passed by pointer per call, so adapters that mutate tolerances
+ * between calls (adapters.py:45-47,56-58) keep working. */
+typedef struct mlb_solver_opts {
+  int32_t solver;                /* MLB_SOLVER_*                 */
+  int32_t max_iters;             /* default 50                   */
+  int32_t max_line_search_iters; /* default 10                   */
+  int32_t norm;                  /* MLB_NORM_*                   */
+  double constraint_tol;         /* default 1e-9                 */
+  double position_tol;           /* default 1e-8                 */
+  double divergence_tol;         /* default 1e10                 */
+  double reverse_check_tol;      /* default 2 * position_tol     */
+  int32_t reverse_check_norm;    /* MLB_NORM_*                   */
+  int32_t _pad;
+} mlb_solver_opts;
+
+/* ---- lifecycle */
+int mlb_version(void);
+const char* mlb_last_error(void);
+int mlb_model_create(const mlb_model_desc* desc, mlb_model** out);
+void mlb_model_destroy(mlb_model* m);
+int mlb_model_dim_u(const mlb_model* m);
+int mlb_model_dim_y(const mlb_model* m);
+int mlb_model_dim_q(const mlb_model* m); /* dim_u + dim_y (additive) / dim_u + 2 dim_y (hier) */
+int mlb_model_jac_rows(const mlb_model* m);  /* rows of the packed Jacobian-block array  */
+int mlb_model_gram_rows(const mlb_model* m); /* rows of the packed Gram-component array  */
+int mlb_model_gram_dim(const mlb_model* m);  /* K: dim_y (dense) or dim_u (Woodbury)     */
+
+/* Packed block layouts (rows of a [rows][n_chain] SoA array):
+ *   jac : dy_du[i][a] at row i*dim_u + a (i < dim_y), then dy_dv[i] (hier only), then
+ *         dy_dn[i]                               (blocks of systems.py:568-580, 698-710)
+ *   gram: chol[r][c] at row r*K + c (lower triangular, K as above), then d[i] =
+ *         dy_dv^2 + dy_dn^2                      (systems.py:591-594, 613-617, 751-757) */
+
+/* ---- the 13 array-level callables of systems.py:328-346 (one entry per row) */
+
+/* _constr: c(q) = generate_y(...) - y_obs.  q [Q][n] -> c [Y][n].  systems.py:564-566, 694-696 */
+int mlb_constr(const mlb_model* m, int64_t n, int64_t ld, const double* q, double* c,
+               void* stream);
+/* _jacob_constr_blocks: -> packed jac, c.  systems.py:568-580, 698-710 */
+int mlb_jacob_constr_blocks(const mlb_model* m, int64_t n, int64_t ld, const double* q,
+                            double* jac, double* c, void* stream);
+/* _decompose_gram: jac -> packed gram.  systems.py:591-594 / 613-617 / 751-757 */
+int mlb_decompose_gram(const mlb_model* m, int64_t n, int64_t ld, const double* jac,
+                       double* gram, void* stream);
+/* _log_det_sqrt_gram: q -> val [n] (+ aux c, jac, gram if non-NULL).  systems.py:603-609/635-641/785-794 */
+int mlb_log_det_sqrt_gram(const mlb_model* m, int64_t n, int64_t ld, const double* q,
+                          double* val, double* c, double* jac, double* gram, void* stream);
+/* _val_and_grad_log_det_sqrt_gram: q -> val [n], grad [Q][n] (+ aux).  systems.py:332-334 */
+int mlb_val_and_grad_log_det_sqrt_gram(const mlb_model* m, int64_t n, int64_t ld,
+                                       const double* q, double* val, double* grad,
+                                       double* c, double* jac, double* gram, void* stream);
+/* _lmult_by_jacob_constr: J v.  systems.py:582-584, 712-718 */
+int mlb_lmult_by_jacob_constr(const mlb_model* m, int64_t n, int64_t ld, const double* jac,
+                              const double* v, double* out, void* stream);
+/* _rmult_by_jacob_constr: J^T w.  systems.py:586-587, 720-721 */
+int mlb_rmult_by_jacob_constr(const mlb_model* m, int64_t n, int64_t ld, const double* jac,
+                              const double* w, double* out, void* stream);
+/* _lmult_by_pinv_jacob_constr: J^T (J J^T)^-1 w.  systems.py:173-179 */
+int mlb_lmult_by_pinv_jacob_constr(const mlb_model* m, int64_t n, int64_t ld,
+                                   const double* jac, const double* gram, const double* w,
+                                   double* out, void* stream);
+/* _lmult_by_inv_jacob_product: (J_l J_r^T)^-1 w (non-symmetric, LU).  systems.py:599-601/626-633/770-783 */
+int mlb_lmult_by_inv_jacob_product(const mlb_model* m, int64_t n, int64_t ld,
+                                   const double* jac_l, const double* jac_r,
+                                   const double* w, double* out, void* stream);
+/* _normal_space_component: J^T (J J^T)^-1 J v.  systems.py:181-188 */
+int mlb_normal_space_component(const mlb_model* m, int64_t n, int64_t ld, const double* jac,
+                               const double* gram, const double* v, double* out,
+                               void* stream);
+/* _quasi_newton_projection / _newton_projection / _newton_projection_with_line_search
+ * (systems.py:190-326), selected by opts->solver; the two Mici solvers likewise.  The
+ * Jacobian blocks (and Gram components for quasi-Newton) of the previous point are
+ * passed packed, as the reference solvers fetch them from the cached previous state
+ * (solvers.py:60-61,131,209).  Outputs: q_out [Q][n] (may alias q), mu_over_dt [Q][n]
+ * (= what the reference subtracts from `state.mom`, solvers.py:84), iters, norm_dq, err,
+ * n_constr_calls (line search; may be NULL), status. */
+int mlb_solve_projection(const mlb_model* m, int64_t n, int64_t ld, const double* q,
+                         const double* jac_prev, const double* gram_prev, double dt,
+                         const mlb_solver_opts* opts, double* q_out, double* mu_over_dt,
+                         int32_t* iters, double* norm_dq, double* err,
+                         int32_t* n_constr_calls, int32_t* status, void* stream);
+
+/* neg_log_dens / grad_neg_log_dens of the extended prior (systems.py:52-87 wrappers;
+ * eight_schools.py:49-53, toy_2d_model.py:72-74).  grad may be NULL. */
+int mlb_neg_log_dens(const mlb_model* m, int64_t n, int64_t ld, const double* q, double* val,
+                     double* grad, void* stream);
+/* h1 = nld + log_det_sqrt_gram, dh1_dpos (systems.py:407-411); h1/dh1 may be NULL. */
+int mlb_h1(const mlb_model* m, int64_t n, int64_t ld, const double* q, double* h1,
+           double* dh1_dpos, void* stream);
+/* project_onto_cotangent_space: p -= J^T (J J^T)^-1 J p at position q (systems.py:464-466);
+ * in place on p. */
+int mlb_project_onto_cotangent_space(const mlb_model* m, int64_t n, int64_t ld,
+                                     const double* q, double* p, void* stream);
+
+/* ---- fused drivers (replace the Mici loop around the callables) */
+
+/* n_step constrained leapfrog steps A(dt/2) B(dt) A(dt/2) with reversibility check per
+ * chain, state kept on chip between steps.  q, p updated in place to the last
+ * successfully completed step.  dt_per_chain may be NULL (use dt).  Optional outputs
+ * (NULL to skip): iters_fwd / iters_rev (summed projection iterations), h_init, h_final. */
+int mlb_leapfrog_steps(const mlb_model* m, int64_t n, int64_t ld, double* q, double* p,
+                       double dt, const double* dt_per_chain, int32_t n_step,
+                       const mlb_solver_opts* opts, int32_t* status, int32_t* n_done,
+                       int32_t* iters_fwd, int32_t* iters_rev, double* h_init,
+                       double* h_final, void* stream);
+
+/* Dual-averaging step-size adaptation state, one per chain, SoA rows:
+ *   0 iter, 1 smoothed_log_step_size, 2 adapt_stat_error, 3 log_step_size_reg_target,
+ *   4 current step size (in/out).  (Mici DualAveragingStepSizeAdapter; utils.py:281-285) */
+#define MLB_ADAPT_ROWS 5
+typedef struct mlb_adapt_opts {
+  double adapt_stat_target;             /* 0.8  (utils.py:82-87)  */
+  double log_step_size_reg_coefficient; /* 0.05 (utils.py:88-93)  */
+  double iter_decay_coeff;              /* 0.75 */
+  double iter_offset;                   /* 10   */
+} mlb_adapt_opts;
+
+/* Per-chain sampling statistics accumulated by mlb_hmc_sample, SoA rows:
+ *   0 sum accept_stat, 1 n_accepted, 2 n_convergence_error, 3 n_non_reversible_step,
+ *   4 n_hamiltonian_diverged, 5 leapfrog steps completed, 6 projection iterations. */
+#define MLB_STAT_ROWS 7
+
+/* n_iter static-HMC transitions per chain in ONE launch (momentum refresh, n_step
+ * constrained leapfrog steps with |dh| > max_delta_h test, Metropolis accept; notebook
+ * cell 44 `simulate_proposal` / Mici StaticMetropolisHMC).  Random numbers: Philox4x32-10
+ * keyed by (seed, chain0 + chain, iter0 + iteration), so results do not depend on how
+ * chains are sharded over GPUs; or supplied (`mom_noise` [n_iter][Q][n], `unif`
+ * [n_iter][n]) for decision-by-decision parity tests.  `adapt` ([MLB_ADAPT_ROWS][n],
+ * NULL = no adaptation) is updated per transition and its row 4 used as the chain's step
+ * size.  `trace_q` ([n_iter / trace_every][Q][n], NULL to skip) receives positions,
+ * `trace_accept` ([n_iter][n], NULL to skip) per-transition accept_stat,
+ * `stats` [MLB_STAT_ROWS][n] is accumulated into (not zeroed). */
+int mlb_hmc_sample(const mlb_model* m, int64_t n, int64_t ld, double* q, double dt,
+                   int32_t n_step, int32_t n_iter, const mlb_solver_opts* opts,
+                   double max_delta_h, uint64_t seed, uint64_t chain0, uint32_t iter0,
+                   const double* mom_noise, const double* unif, double* adapt,
+                   const mlb_adapt_opts* adapt_opts, double* trace_q, int32_t trace_every,
+                   double* trace_accept, double* stats, int32_t* last_status,
+                   void* stream);
+
+/* Philox streams used above, exposed for tests (host function, host output). */
+void mlb_philox_normals_host(uint64_t seed, uint64_t chain, uint32_t iter, int32_t n,
+                             double* out);
+double mlb_philox_uniform_host(uint64_t seed, uint64_t chain, uint32_t iter);
+
+/* ---- host-buffer entry point (what a reference-side binding calls; see
+ * INTEGRATION.md).  q, p are HOST arrays in the reference's natural layout
+ * [n_chain][Q] row-major (one NumPy `state.pos` per row); the call stages them through
+ * pinned memory, transposes on device, runs mlb_leapfrog_steps and copies results back.
+ * Output arrays are host arrays of length n (may be NULL except status). */
+int mlb_leapfrog_steps_host(const mlb_model* m, int64_t n, double* q, double* p, double dt,
+                            int32_t n_step, const mlb_solver_opts* opts, int32_t* status,
+                            int32_t* n_done, int32_t* iters_fwd, int32_t* iters_rev,
+                            double* h_init, double* h_final);
+
+/* Transposes between the reference's [n][dim] row-major layout and the SoA layout. */
+int mlb_aos_to_soa(int64_t n, int32_t dim, const double* aos, double* soa, int64_t ld,
+                   void* stream);
+int mlb_soa_to_aos(int64_t n, int32_t dim, const double* soa, int64_t ld, double* aos,
+                   void* stream);
+
+/* Launch counter: number of kernels this library has launched in this process (used by
+ * bench.py's `gpu_launches`). */
+int64_t mlb_launch_count(void);
+
+/* FP64 FMA peak microbenchmark (roofline denominator; MEASURED_PEAKS.json has no fp64
+ * entry).  Returns achieved TFLOP/s of a dependent-chain DFMA loop over the full chip. */
+double mlb_measure_fp64_tflops(int32_t repeats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLB_H_ */

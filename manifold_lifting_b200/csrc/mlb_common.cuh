@@ -1,0 +1,167 @@
+// Common device helpers: norms, tiny dense factorizations in registers, Philox.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdint>
+
+#include "../../include/mlb.h"
+
+#define MLB_DEV __device__ __forceinline__
+#define MLB_HD __host__ __device__ __forceinline__
+
+namespace mlb {
+
+// Solver / integrator options in kernel-parameter form (see mlb_solver_opts).
+struct Opts {
+  double ctol, ptol, dtol, rev_tol;
+  int max_iters, max_ls, norm, rev_norm;
+};
+
+// ---- norms (reference mlift/solvers.py:6-13); NaN-propagating like numpy/jax max
+template <int N>
+MLB_DEV double vec_norm(const double (&v)[N], int kind) {
+  if (kind == MLB_NORM_MAX) {
+    double m = 0.0;
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double a = fabs(v[i]);
+      bad |= (a != a);
+      m = a > m ? a : m;
+    }
+    return bad ? nan("") : m;
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) s = fma(v[i], v[i], s);
+  return sqrt(s);
+}
+
+// ---- K x K factorizations, fully unrolled, static indexing only (stay in registers)
+
+// in-place lower Cholesky; false if a pivot is not positive (or NaN)
+template <int K>
+MLB_DEV bool chol_lower(double (&a)[K][K]) {
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    double s = a[j][j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) s -= a[j][k] * a[j][k];
+    ok &= (s > 0.0);
+    double d = sqrt(s);
+    a[j][j] = d;
+    double rd = 1.0 / d;
+#pragma unroll
+    for (int i = j + 1; i < K; ++i) {
+      double t = a[i][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) t -= a[i][k] * a[j][k];
+      a[i][j] = t * rd;
+    }
+#pragma unroll
+    for (int i = 0; i < j; ++i) a[i][j] = 0.0;
+  }
+  return ok;
+}
+
+// solve L L^T x = b in place
+template <int K>
+MLB_DEV void chol_solve(const double (&L)[K][K], double (&b)[K]) {
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    double t = b[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) t -= L[i][k] * b[k];
+    b[i] = t / L[i][i];
+  }
+#pragma unroll
+  for (int i = K - 1; i >= 0; --i) {
+    double t = b[i];
+#pragma unroll
+    for (int k = i + 1; k < K; ++k) t -= L[k][i] * b[k];
+    b[i] = t / L[i][i];
+  }
+}
+
+// LU with partial pivoting (np.linalg.solve semantics, reference systems.py:601,632);
+// a destroyed, b overwritten by the solution.  Pivot search by conditional row swaps.
+template <int K>
+MLB_DEV bool lu_solve(double (&a)[K][K], double (&b)[K]) {
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+#pragma unroll
+    for (int i = j + 1; i < K; ++i) {
+      bool sw = fabs(a[i][j]) > fabs(a[j][j]);
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        double x = a[j][k], y = a[i][k];
+        a[j][k] = sw ? y : x;
+        a[i][k] = sw ? x : y;
+      }
+      double x = b[j], y = b[i];
+      b[j] = sw ? y : x;
+      b[i] = sw ? x : y;
+    }
+    ok &= (fabs(a[j][j]) > 0.0);
+    double rp = 1.0 / a[j][j];
+#pragma unroll
+    for (int i = j + 1; i < K; ++i) {
+      double f = a[i][j] * rp;
+#pragma unroll
+      for (int k = j + 1; k < K; ++k) a[i][k] -= f * a[j][k];
+      b[i] -= f * b[j];
+    }
+  }
+#pragma unroll
+  for (int i = K - 1; i >= 0; --i) {
+    double t = b[i];
+#pragma unroll
+    for (int k = i + 1; k < K; ++k) t -= a[i][k] * b[k];
+    b[i] = t / a[i][i];
+  }
+  return ok;
+}
+
+// ---- Philox4x32-10 counter-based RNG (identical stream to oracle/c/chmc_oracle.cpp)
+MLB_HD void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+    uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+    uint32_t n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+    uint32_t n3 = (uint32_t)p0;
+    c[0] = n0, c[1] = n1, c[2] = n2, c[3] = n3;
+    k0 += 0x9E3779B9u, k1 += 0xBB67AE85u;
+  }
+}
+
+MLB_HD double u01(uint32_t hi, uint32_t lo) {  // (0,1), 53 bits
+  uint64_t x = (((uint64_t)hi << 32) | lo) >> 11;
+  return ((double)x + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+// stream 0: momentum normals, pair j -> normals (2j, 2j+1); stream 1: accept uniform
+MLB_HD void philox_normal_pair(uint64_t seed, uint64_t chain, uint32_t iter, uint32_t j,
+                               double& n0, double& n1) {
+  uint32_t c[4] = {j, iter, (uint32_t)chain, (uint32_t)(chain >> 32) & 0x7fffffffu};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  double u1 = u01(c[0], c[1]), u2 = u01(c[2], c[3]);
+  double r = sqrt(-2.0 * log(u1)), th = 6.283185307179586476925286766559 * u2;
+  double s, co;
+  sincos(th, &s, &co);
+  n0 = r * co, n1 = r * s;
+}
+
+MLB_HD double philox_uniform(uint64_t seed, uint64_t chain, uint32_t iter) {
+  uint32_t c[4] = {0u, iter, (uint32_t)chain,
+                   ((uint32_t)(chain >> 32) & 0x7fffffffu) | 0x80000000u};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  return u01(c[0], c[1]);
+}
+
+}  // namespace mlb

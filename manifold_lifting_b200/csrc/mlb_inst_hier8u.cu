@@ -1,0 +1,5 @@
+// Kernel instantiations for one model (compiled as its own translation unit).
+#include "mlb_launch.cuh"
+namespace mlb {
+extern const ModelOps ops_hier8u = make_ops<HierModel<8, 0>>(MLB_MODEL_HIER, 8, 0);
+}

@@ -1,0 +1,559 @@
+// sm_100a kernels + C ABI for the one-chain-per-thread models (toy, eight-schools).
+//
+// Execution model: chains are embarrassingly parallel (the reference runs one OS process
+// per chain, toy_2d_model.py:450); here one CUDA thread owns one chain, the whole chain
+// state (q, p, Jacobian blocks, Gram factor, gradient) lives in registers, and chain
+// state in HBM is component-major so that a warp's 32 loads of component k are one
+// coalesced 256 B transaction.  Model constants travel as __grid_constant__ kernel
+// parameters (constant bank operands).  The fused drivers keep state on chip across
+// leapfrog steps / HMC transitions so HBM is touched once per launch.
+#pragma once
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mlb_chmc.cuh"
+
+namespace mlb { struct ModelOps; }
+
+struct mlb_model {
+  int model, dim_y, param, U, Y, Q, jac_rows, gram_rows, K;
+  std::vector<double> data;
+  const struct mlb::ModelOps* ops;
+};
+
+namespace mlb {
+
+std::string& last_error();           // thread-local, defined in mlb_api.cu
+std::atomic<int64_t>& launch_count();  // defined in mlb_api.cu
+#define g_err (::mlb::last_error())
+#define g_launches (::mlb::launch_count())
+
+#define MLB_CUDA_OK(expr)                                                       \
+  do {                                                                          \
+    cudaError_t e_ = (expr);                                                    \
+    if (e_ != cudaSuccess) {                                                    \
+      g_err = std::string(#expr) + ": " + cudaGetErrorString(e_);               \
+      return MLB_ERR_CUDA;                                                      \
+    }                                                                           \
+  } while (0)
+
+#define MLB_ARG(cond)                                   \
+  do {                                                  \
+    if (!(cond)) {                                      \
+      g_err = std::string("bad argument: ") + #cond;    \
+      return MLB_ERR_ARG;                               \
+    }                                                   \
+  } while (0)
+
+template <int D>
+MLB_DEV void load_vec(double (&v)[D], const double* a, int64_t ld, int64_t i) {
+#pragma unroll
+  for (int k = 0; k < D; ++k) v[k] = a[(int64_t)k * ld + i];
+}
+template <int D>
+MLB_DEV void store_vec(const double (&v)[D], double* a, int64_t ld, int64_t i) {
+#pragma unroll
+  for (int k = 0; k < D; ++k) a[(int64_t)k * ld + i] = v[k];
+}
+
+constexpr int kBlock = 64;  // threads per CTA for the heavy per-chain kernels
+
+#define MLB_CHAIN_INDEX()                                          \
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; \
+  if (i >= n) return;
+
+// ------------------------------------------------------------ individual operations
+
+template <class M>
+__global__ void __launch_bounds__(kBlock) k_constr(const __grid_constant__
+                                                   typename M::Params P,
+                                                   int64_t n, int64_t ld, const double* q,
+                                                   double* c) {
+  MLB_CHAIN_INDEX();
+  double qv[M::Q], cv[M::Y];
+  load_vec<M::Q>(qv, q, ld, i);
+  M::constr(P, qv, cv);
+  store_vec<M::Y>(cv, c, ld, i);
+}
+
+template <class M>
+__global__ void __launch_bounds__(kBlock)
+    k_jacob(const __grid_constant__ typename M::Params P, int64_t n, int64_t ld,
+            const double* q, double* jac, double* c) {
+  MLB_CHAIN_INDEX();
+  double qv[M::Q], cv[M::Y];
+  typename M::B::Jac J;
+  load_vec<M::Q>(qv, q, ld, i);
+  M::jacob(P, qv, J, cv);
+  M::B::store_jac(J, jac, ld, i);
+  if (c) store_vec<M::Y>(cv, c, ld, i);
+}
+
+template <class M>
+__global__ void __launch_bounds__(kBlock)
+    k_decompose(int64_t n, int64_t ld, const double* jac, double* gram) {
+  MLB_CHAIN_INDEX();
+  typename M::B::Jac J;
+  typename M::B::Gram G;
+  M::B::load_jac(J, jac, ld, i);
+  M::B::decompose_gram(J, G);
+  M::B::store_gram(G, gram, ld, i);
+}
+
+// log_det_sqrt_gram, optionally with gradient, aux outputs and h1 / dh1_dpos
+template <class M>
+__global__ void __launch_bounds__(kBlock)
+    k_logdet(const __grid_constant__ typename M::Params P, int64_t n, int64_t ld,
+             const double* q, double* val, double* grad, double* c, double* jac,
+             double* gram, double* nld_val, double* nld_grad, double* h1, double* dh1) {
+  MLB_CHAIN_INDEX();
+  constexpr int Q = M::Q;
+  double qv[Q], cv[M::Y];
+  typename M::B::Jac J;
+  typename M::B::Gram G;
+  load_vec<Q>(qv, q, ld, i);
+  M::jacob(P, qv, J, cv);
+  M::B::decompose_gram(J, G);
+  const double ld_ = M::B::log_det_sqrt_gram(G);
+  if (val) val[i] = ld_;
+  if (c) store_vec<M::Y>(cv, c, ld, i);
+  if (jac) M::B::store_jac(J, jac, ld, i);
+  if (gram) M::B::store_gram(G, gram, ld, i);
+  if (grad || nld_val || nld_grad || h1 || dh1) {
+    double gn[Q], gl[Q];
+    const double nv = M::nld(P, qv, gn);
+#pragma unroll
+    for (int k = 0; k < Q; ++k) gl[k] = 0.0;
+    M::add_grad_logdet(P, qv, J, G, gl);
+    if (grad) store_vec<Q>(gl, grad, ld, i);
+    if (nld_val) nld_val[i] = nv;
+    if (nld_grad) store_vec<Q>(gn, nld_grad, ld, i);
+    if (h1) h1[i] = nv + ld_;
+    if (dh1) {
+#pragma unroll
+      for (int k = 0; k < Q; ++k) gn[k] += gl[k];
+      store_vec<Q>(gn, dh1, ld, i);
+    }
+  }
+}
+
+template <class M>
+__global__ void __launch_bounds__(kBlock)
+    k_nld(const __grid_constant__ typename M::Params P, int64_t n, int64_t ld,
+          const double* q, double* val, double* grad) {
+  MLB_CHAIN_INDEX();
+  double qv[M::Q], g[M::Q];
+  load_vec<M::Q>(qv, q, ld, i);
+  const double v = M::nld(P, qv, g);
+  if (val) val[i] = v;
+  if (grad) store_vec<M::Q>(g, grad, ld, i);
+}
+
+enum { OP_LMULT = 0, OP_RMULT = 1, OP_PINV = 2, OP_NSC = 3, OP_INVJP = 4 };
+
+template <class M, int OP>
+__global__ void __launch_bounds__(kBlock)
+    k_block_op(int64_t n, int64_t ld, const double* jac, const double* jac_r,
+               const double* gram, const double* vec, double* out) {
+  MLB_CHAIN_INDEX();
+  using B = typename M::B;
+  constexpr int Q = M::Q, Y = M::Y;
+  typename B::Jac J;
+  B::load_jac(J, jac, ld, i);
+  if (OP == OP_LMULT) {
+    double v[Q], o[Y];
+    load_vec<Q>(v, vec, ld, i);
+    B::lmult_jacob(J, v, o);
+    store_vec<Y>(o, out, ld, i);
+  } else if (OP == OP_RMULT) {
+    double w[Y], o[Q];
+    load_vec<Y>(w, vec, ld, i);
+    B::rmult_jacob(J, w, o);
+    store_vec<Q>(o, out, ld, i);
+  } else if (OP == OP_PINV) {
+    typename B::Gram G;
+    B::load_gram(G, gram, ld, i);
+    double w[Y], o[Q];
+    load_vec<Y>(w, vec, ld, i);
+    B::lmult_pinv(J, G, w, o);
+    store_vec<Q>(o, out, ld, i);
+  } else if (OP == OP_NSC) {
+    typename B::Gram G;
+    B::load_gram(G, gram, ld, i);
+    double v[Q], w[Y], o[Q];
+    load_vec<Q>(v, vec, ld, i);
+    B::lmult_jacob(J, v, w);
+    B::lmult_pinv(J, G, w, o);
+    store_vec<Q>(o, out, ld, i);
+  } else {
+    typename B::Jac Jr;
+    B::load_jac(Jr, jac_r, ld, i);
+    double w[Y], o[Y];
+    load_vec<Y>(w, vec, ld, i);
+    bool ok = B::lmult_inv_jacob_product(J, Jr, w, o);
+    if (!ok) {
+#pragma unroll
+      for (int k = 0; k < Y; ++k) o[k] = nan("");
+    }
+    store_vec<Y>(o, out, ld, i);
+  }
+}
+
+template <class M>
+__global__ void __launch_bounds__(kBlock)
+    k_project_cotangent(const __grid_constant__ typename M::Params P, int64_t n, int64_t ld,
+                        const double* q, double* p) {
+  MLB_CHAIN_INDEX();
+  double qv[M::Q], pv[M::Q], cv[M::Y];
+  typename M::B::Jac J;
+  typename M::B::Gram G;
+  load_vec<M::Q>(qv, q, ld, i);
+  load_vec<M::Q>(pv, p, ld, i);
+  M::jacob(P, qv, J, cv);
+  M::B::decompose_gram(J, G);
+  M::B::project_cotangent(J, G, pv);
+  store_vec<M::Q>(pv, p, ld, i);
+}
+
+template <class M, int SOLVER>
+__global__ void __launch_bounds__(kBlock)
+    k_solve(const __grid_constant__ typename M::Params P, int64_t n, int64_t ld,
+            const double* q, const double* jac_prev, const double* gram_prev, double dt,
+            Opts o, double* q_out, double* mu_out, int32_t* iters, double* norm_dq,
+            double* err, int32_t* n_constr, int32_t* status) {
+  MLB_CHAIN_INDEX();
+  using B = typename M::B;
+  double qv[M::Q], mu[M::Q];
+  typename B::Jac Jp;
+  typename B::Gram Gp;
+  load_vec<M::Q>(qv, q, ld, i);
+  B::load_jac(Jp, jac_prev, ld, i);
+  if (gram_prev) {
+    B::load_gram(Gp, gram_prev, ld, i);
+  } else {
+    B::decompose_gram(Jp, Gp);
+  }
+  SolveOut r = solve_projection<M, SOLVER>(P, qv, Jp, Gp, dt, o, mu);
+  store_vec<M::Q>(qv, q_out, ld, i);
+  if (mu_out) store_vec<M::Q>(mu, mu_out, ld, i);
+  if (iters) iters[i] = r.iters;
+  if (norm_dq) norm_dq[i] = r.ndq;
+  if (err) err[i] = r.err;
+  if (n_constr) n_constr[i] = r.n_constr;
+  status[i] = r.status;
+}
+
+// ----------------------------------------------------------------- fused drivers
+
+template <class M, int SOLVER>
+__global__ void __launch_bounds__(kBlock)
+    k_leapfrog_steps(const __grid_constant__ typename M::Params P, int64_t n, int64_t ld,
+                     double* q, double* p, double dt, const double* dt_pc, int n_step,
+                     Opts o, int32_t* status, int32_t* n_done, int32_t* iters_fwd,
+                     int32_t* iters_rev, double* h_init, double* h_final) {
+  MLB_CHAIN_INDEX();
+  constexpr int Q = M::Q;
+  double qv[Q], pv[Q];
+  load_vec<Q>(qv, q, ld, i);
+  load_vec<Q>(pv, p, ld, i);
+  const double dti = dt_pc ? dt_pc[i] : dt;
+  Eval<M> E;
+  int st = evaluate_at<M>(P, qv, E) ? MLB_ST_OK : MLB_ST_LINALG;
+  if (h_init) h_init[i] = E.nld + E.logdet + half_sq_norm<Q>(pv);
+  int done = 0, tf = 0, tr = 0;
+  for (int s = 0; s < n_step && st == MLB_ST_OK; ++s) {
+    int f, r;
+    st = leapfrog_step<M, SOLVER>(P, qv, pv, E, dti, o, f, r);
+    tf += f, tr += r;
+    done += (st == MLB_ST_OK);
+  }
+  store_vec<Q>(qv, q, ld, i);
+  store_vec<Q>(pv, p, ld, i);
+  status[i] = st;
+  if (n_done) n_done[i] = done;
+  if (iters_fwd) iters_fwd[i] = tf;
+  if (iters_rev) iters_rev[i] = tr;
+  if (h_final) h_final[i] = E.nld + E.logdet + half_sq_norm<Q>(pv);
+}
+
+struct SampleArgs {
+  double dt, max_delta_h;
+  int n_step, n_iter, trace_every;
+  uint64_t seed, chain0;
+  uint32_t iter0;
+  const double* mom_noise;
+  const double* unif;
+  double* adapt;
+  double a_target, a_reg, a_decay, a_offset;
+  double* trace_q;
+  double* trace_accept;
+  double* stats;
+  int32_t* last_status;
+};
+
+template <class M, int SOLVER>
+__global__ void __launch_bounds__(kBlock)
+    k_hmc_sample(const __grid_constant__ typename M::Params P, int64_t n, int64_t ld,
+                 double* q, Opts o, SampleArgs a) {
+  MLB_CHAIN_INDEX();
+  constexpr int Q = M::Q;
+  double qv[Q];
+  load_vec<Q>(qv, q, ld, i);
+  double ad_iter = 0, ad_smooth = 0, ad_err = 0, ad_target = 0, dti = a.dt;
+  if (a.adapt) {
+    ad_iter = a.adapt[0 * ld + i], ad_smooth = a.adapt[1 * ld + i];
+    ad_err = a.adapt[2 * ld + i], ad_target = a.adapt[3 * ld + i];
+    dti = a.adapt[4 * ld + i];
+  }
+  double s_acc = 0, s_nacc = 0, s_conv = 0, s_nonrev = 0, s_hdiv = 0, s_steps = 0, s_its = 0;
+  int last = MLB_ST_OK;
+  for (int it = 0; it < a.n_iter; ++it) {
+    Eval<M> E;
+    int st = evaluate_at<M>(P, qv, E) ? MLB_ST_OK : MLB_ST_LINALG;
+    double pc[Q], qc[Q];
+    if (a.mom_noise) {
+      load_vec<Q>(pc, a.mom_noise + (int64_t)it * Q * ld, ld, i);
+    } else {
+#pragma unroll
+      for (int j = 0; 2 * j < Q; ++j) {
+        double n0, n1;
+        philox_normal_pair(a.seed, a.chain0 + (uint64_t)i, a.iter0 + (uint32_t)it,
+                           (uint32_t)j, n0, n1);
+        pc[2 * j] = n0;
+        if (2 * j + 1 < Q) pc[2 * j + 1] = n1;
+      }
+    }
+    const double u = a.unif ? a.unif[(int64_t)it * ld + i]
+                            : philox_uniform(a.seed, a.chain0 + (uint64_t)i,
+                                             a.iter0 + (uint32_t)it);
+    M::B::project_cotangent(E.J, E.G, pc);
+#pragma unroll
+    for (int k = 0; k < Q; ++k) qc[k] = qv[k];
+    const double h0 = E.nld + E.logdet + half_sq_norm<Q>(pc);
+    double h1 = h0;
+    for (int s = 0; s < a.n_step && st == MLB_ST_OK; ++s) {
+      int f, r;
+      st = leapfrog_step<M, SOLVER>(P, qc, pc, E, dti, o, f, r);
+      s_its += f + r;
+      if (st == MLB_ST_OK) {
+        s_steps += 1;
+        h1 = E.nld + E.logdet + half_sq_norm<Q>(pc);
+        if (fabs(h1 - h0) > a.max_delta_h) st = MLB_ST_H_DIVERGED;
+      }
+    }
+    double a_stat = 0.0;
+    if (st == MLB_ST_OK) {
+      double d = h0 - h1;
+      a_stat = (d != d) ? 0.0 : exp(d < 0.0 ? d : 0.0);
+      if (u < a_stat) {
+#pragma unroll
+        for (int k = 0; k < Q; ++k) qv[k] = qc[k];
+        s_nacc += 1;
+      }
+    }
+    s_acc += a_stat;
+    s_conv += (st == MLB_ST_DIVERGED || st == MLB_ST_NOT_CONVERGED || st == MLB_ST_LINALG);
+    s_nonrev += (st == MLB_ST_NON_REVERSIBLE);
+    s_hdiv += (st == MLB_ST_H_DIVERGED);
+    last = st;
+    if (a.trace_accept) a.trace_accept[(int64_t)it * ld + i] = a_stat;
+    if (a.trace_q && (it + 1) % a.trace_every == 0)
+      store_vec<Q>(qv, a.trace_q + (int64_t)((it + 1) / a.trace_every - 1) * Q * ld, ld, i);
+    if (a.adapt) {  // Mici DualAveragingStepSizeAdapter.update
+      ad_iter += 1;
+      const double w = 1.0 / (a.a_offset + ad_iter);
+      ad_err = (1.0 - w) * ad_err + w * (a.a_target - a_stat);
+      const double sw = pow(1.0 / ad_iter, a.a_decay);
+      const double log_eps = ad_target - ad_err * sqrt(ad_iter) / a.a_reg;
+      ad_smooth = (1.0 - sw) * ad_smooth + sw * log_eps;
+      dti = exp(log_eps);
+    }
+  }
+  store_vec<Q>(qv, q, ld, i);
+  if (a.adapt) {
+    a.adapt[0 * ld + i] = ad_iter, a.adapt[1 * ld + i] = ad_smooth;
+    a.adapt[2 * ld + i] = ad_err, a.adapt[4 * ld + i] = dti;
+  }
+  if (a.stats) {
+    a.stats[0 * ld + i] += s_acc, a.stats[1 * ld + i] += s_nacc;
+    a.stats[2 * ld + i] += s_conv, a.stats[3 * ld + i] += s_nonrev;
+    a.stats[4 * ld + i] += s_hdiv, a.stats[5 * ld + i] += s_steps;
+    a.stats[6 * ld + i] += s_its;
+  }
+  if (a.last_status) a.last_status[i] = last;
+}
+
+
+// ---------------------------------------------------------------- per-model launchers
+
+struct SolveIO {
+  const double *q, *jac_prev, *gram_prev;
+  double dt;
+  double *q_out, *mu_out;
+  int32_t* iters;
+  double *norm_dq, *err;
+  int32_t *n_constr, *status;
+};
+struct StepsIO {
+  double *q, *p;
+  double dt;
+  const double* dt_pc;
+  int n_step;
+  int32_t *status, *n_done, *iters_fwd, *iters_rev;
+  double *h_init, *h_final;
+};
+
+// Table of launchers for one compiled-in model; one translation unit per model so the
+// (model x solver) kernel instantiations compile in parallel.
+struct ModelOps {
+  int model, dim_y, param;
+  int (*constr)(const mlb_model*, int64_t, int64_t, const double*, double*, cudaStream_t);
+  int (*jacob)(const mlb_model*, int64_t, int64_t, const double*, double*, double*, cudaStream_t);
+  int (*decompose)(const mlb_model*, int64_t, int64_t, const double*, double*, cudaStream_t);
+  int (*logdet)(const mlb_model*, int64_t, int64_t, const double*, double*, double*, double*,
+                double*, double*, double*, double*, double*, double*, cudaStream_t);
+  int (*nld)(const mlb_model*, int64_t, int64_t, const double*, double*, double*, cudaStream_t);
+  int (*block_op)(const mlb_model*, int, int64_t, int64_t, const double*, const double*,
+                  const double*, const double*, double*, cudaStream_t);
+  int (*project_cotangent)(const mlb_model*, int64_t, int64_t, const double*, double*,
+                           cudaStream_t);
+  int (*solve)(const mlb_model*, int, int64_t, int64_t, const Opts&, const SolveIO&,
+               cudaStream_t);
+  int (*steps)(const mlb_model*, int, int64_t, int64_t, const Opts&, const StepsIO&,
+               cudaStream_t);
+  int (*sample)(const mlb_model*, int, int64_t, int64_t, double*, const Opts&,
+                const SampleArgs&, cudaStream_t);
+};
+
+inline unsigned grid_for(int64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
+
+inline int finish_launch() {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    g_err = std::string("kernel launch: ") + cudaGetErrorString(e);
+    return MLB_ERR_CUDA;
+  }
+  return MLB_OK;
+}
+
+template <class M>
+struct ParamsOf;  // specialised per model: build the kernel-parameter struct from the handle
+
+template <>
+struct ParamsOf<ToyModel> {
+  static ToyModel::Params make(const mlb_model* m) {
+    return ToyModel::Params{m->data[0], m->data[1], m->data[2]};
+  }
+};
+template <int Y, int PARAM>
+struct ParamsOf<HierModel<Y, PARAM>> {
+  static typename HierModel<Y, PARAM>::Params make(const mlb_model* m) {
+    typename HierModel<Y, PARAM>::Params P;
+    for (int i = 0; i < Y; ++i) P.y_obs[i] = m->data[i], P.sigma[i] = m->data[Y + i];
+    return P;
+  }
+};
+
+template <class F>
+int dispatch_solver(int solver, F&& f) {
+  switch (solver) {
+    case MLB_SOLVER_QUASI_NEWTON: return f.template operator()<MLB_SOLVER_QUASI_NEWTON>();
+    case MLB_SOLVER_NEWTON: return f.template operator()<MLB_SOLVER_NEWTON>();
+    case MLB_SOLVER_NEWTON_LS: return f.template operator()<MLB_SOLVER_NEWTON_LS>();
+    case MLB_SOLVER_MICI_NEWTON: return f.template operator()<MLB_SOLVER_MICI_NEWTON>();
+    case MLB_SOLVER_MICI_QUASI_NEWTON:
+      return f.template operator()<MLB_SOLVER_MICI_QUASI_NEWTON>();
+  }
+  g_err = "unknown solver";
+  return MLB_ERR_ARG;
+}
+
+template <class M>
+struct Launch {
+  static auto P(const mlb_model* m) { return ParamsOf<M>::make(m); }
+  static int constr(const mlb_model* m, int64_t n, int64_t ld, const double* q, double* c,
+                    cudaStream_t s) {
+    k_constr<M><<<grid_for(n), kBlock, 0, s>>>(P(m), n, ld, q, c);
+    return finish_launch();
+  }
+  static int jacob(const mlb_model* m, int64_t n, int64_t ld, const double* q, double* jac,
+                   double* c, cudaStream_t s) {
+    k_jacob<M><<<grid_for(n), kBlock, 0, s>>>(P(m), n, ld, q, jac, c);
+    return finish_launch();
+  }
+  static int decompose(const mlb_model*, int64_t n, int64_t ld, const double* jac,
+                       double* gram, cudaStream_t s) {
+    k_decompose<M><<<grid_for(n), kBlock, 0, s>>>(n, ld, jac, gram);
+    return finish_launch();
+  }
+  static int logdet(const mlb_model* m, int64_t n, int64_t ld, const double* q, double* val,
+                    double* grad, double* c, double* jac, double* gram, double* nld_val,
+                    double* nld_grad, double* h1, double* dh1, cudaStream_t s) {
+    k_logdet<M><<<grid_for(n), kBlock, 0, s>>>(P(m), n, ld, q, val, grad, c, jac, gram,
+                                              nld_val, nld_grad, h1, dh1);
+    return finish_launch();
+  }
+  static int nld(const mlb_model* m, int64_t n, int64_t ld, const double* q, double* val,
+                 double* grad, cudaStream_t s) {
+    k_nld<M><<<grid_for(n), kBlock, 0, s>>>(P(m), n, ld, q, val, grad);
+    return finish_launch();
+  }
+  static int block_op(const mlb_model*, int op, int64_t n, int64_t ld, const double* jac,
+                      const double* jac_r, const double* gram, const double* vec,
+                      double* out, cudaStream_t s) {
+    const unsigned g = grid_for(n);
+    switch (op) {
+      case OP_LMULT: k_block_op<M, OP_LMULT><<<g, kBlock, 0, s>>>(n, ld, jac, jac_r, gram, vec, out); break;
+      case OP_RMULT: k_block_op<M, OP_RMULT><<<g, kBlock, 0, s>>>(n, ld, jac, jac_r, gram, vec, out); break;
+      case OP_PINV: k_block_op<M, OP_PINV><<<g, kBlock, 0, s>>>(n, ld, jac, jac_r, gram, vec, out); break;
+      case OP_NSC: k_block_op<M, OP_NSC><<<g, kBlock, 0, s>>>(n, ld, jac, jac_r, gram, vec, out); break;
+      default: k_block_op<M, OP_INVJP><<<g, kBlock, 0, s>>>(n, ld, jac, jac_r, gram, vec, out); break;
+    }
+    return finish_launch();
+  }
+  static int project_cotangent(const mlb_model* m, int64_t n, int64_t ld, const double* q,
+                               double* p, cudaStream_t s) {
+    k_project_cotangent<M><<<grid_for(n), kBlock, 0, s>>>(P(m), n, ld, q, p);
+    return finish_launch();
+  }
+  static int solve(const mlb_model* m, int solver, int64_t n, int64_t ld, const Opts& o,
+                   const SolveIO& io, cudaStream_t s) {
+    return dispatch_solver(solver, [&]<int S>() {
+      k_solve<M, S><<<grid_for(n), kBlock, 0, s>>>(P(m), n, ld, io.q, io.jac_prev,
+                                                  io.gram_prev, io.dt, o, io.q_out, io.mu_out,
+                                                  io.iters, io.norm_dq, io.err, io.n_constr,
+                                                  io.status);
+      return finish_launch();
+    });
+  }
+  static int steps(const mlb_model* m, int solver, int64_t n, int64_t ld, const Opts& o,
+                   const StepsIO& io, cudaStream_t s) {
+    return dispatch_solver(solver, [&]<int S>() {
+      k_leapfrog_steps<M, S><<<grid_for(n), kBlock, 0, s>>>(
+          P(m), n, ld, io.q, io.p, io.dt, io.dt_pc, io.n_step, o, io.status, io.n_done,
+          io.iters_fwd, io.iters_rev, io.h_init, io.h_final);
+      return finish_launch();
+    });
+  }
+  static int sample(const mlb_model* m, int solver, int64_t n, int64_t ld, double* q,
+                    const Opts& o, const SampleArgs& a, cudaStream_t s) {
+    return dispatch_solver(solver, [&]<int S>() {
+      k_hmc_sample<M, S><<<grid_for(n), kBlock, 0, s>>>(P(m), n, ld, q, o, a);
+      return finish_launch();
+    });
+  }
+};
+
+template <class M>
+ModelOps make_ops(int model, int dim_y, int param) {
+  using L = Launch<M>;
+  return ModelOps{model, dim_y, param, &L::constr, &L::jacob, &L::decompose, &L::logdet,
+                  &L::nld, &L::block_op, &L::project_cotangent, &L::solve, &L::steps,
+                  &L::sample};
+}
+
+}  // namespace mlb

@@ -1,0 +1,115 @@
+"""Model specifications: what replaces the reference's `generate_y` closures.
+
+In the reference a model is an arbitrary Python function `generate_y(u[, v], n, data)`
+traced by JAX (mlift/systems.py:520-527, 662-669).  A Python closure cannot cross a C
+ABI, so here a model is a `ModelSpec`: a model id + constant data blob handed to
+`mlb_model_create`, with the forward map, its Jacobian blocks and the second-derivative
+contraction needed for grad log det hand-written in CUDA (csrc/mlb_models.cuh).
+A `ModelSpec` is passed wherever the reference takes `generate_y`.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class ModelSpec:
+    """Handle of a compiled-in model (wraps `mlb_model*`)."""
+
+    family = None  # "additive" | "hierarchical"
+
+    def __init__(self, model_id, dim_y, parametrization, data):
+        self._data = np.ascontiguousarray(data, dtype=np.float64).ravel()
+        par = {"unbounded": _lib.PARAM_UNBOUNDED, "normal": _lib.PARAM_NORMAL}[parametrization]
+        desc = _lib.ModelDesc(model_id, dim_y, par, self._data.size,
+                              self._data.ctypes.data_as(C.POINTER(C.c_double)))  # fmt: skip
+        h = C.c_void_p()
+        _lib.check(_lib.lib().mlb_model_create(C.byref(desc), C.byref(h)))
+        self.handle = h
+        L = _lib.lib()
+        self.dim_u, self.dim_y, self.dim_q = (L.mlb_model_dim_u(h), L.mlb_model_dim_y(h),
+                                              L.mlb_model_dim_q(h))  # fmt: skip
+        self.jac_rows, self.gram_rows = L.mlb_model_jac_rows(h), L.mlb_model_gram_rows(h)
+        self.gram_dim = L.mlb_model_gram_dim(h)
+        self.parametrization = parametrization
+        self.model_id = model_id
+
+    def __del__(self):
+        try:
+            _lib.lib().mlb_model_destroy(self.handle)
+        except Exception:
+            pass
+
+    def __call__(self, *args, **kwargs):
+        raise TypeError("a ModelSpec stands in for `generate_y`; it is evaluated on the "
+                        "GPU through the system classes, not called from Python")  # fmt: skip
+
+
+class Toy2DModel(ModelSpec):
+    """Toy model F(theta) = theta1^2 + coeff*theta0^2*(theta0^2 - 1/2), y = F + sigma*eta.
+
+    Reference: mlift/example_models/toy_2d_model.py:43-87 (coeff=1) and
+    notebooks/Two-dimensional_example.ipynb (coeff=2, the BASELINE config).
+    """
+
+    family = "additive"
+
+    def __init__(self, sigma, y=1.0, coeff=2.0):
+        super().__init__(_lib.MODEL_TOY, 1, "unbounded", [sigma, y, coeff])
+        self.sigma, self.y, self.coeff = float(sigma), float(y), float(coeff)
+        self.data = {"y_obs": np.array([self.y])}
+
+    def forward_func(self, theta):
+        theta = np.asarray(theta, dtype=np.float64)
+        return theta[..., 1] ** 2 + self.coeff * theta[..., 0] ** 2 * (
+            theta[..., 0] ** 2 - 0.5
+        )
+
+    def lift(self, theta):
+        """theta -> q = (theta, eta) on the manifold (toy_2d_model.py:162-163)."""
+        theta = np.asarray(theta, dtype=np.float64)
+        eta = (self.y - self.forward_func(theta)) / self.sigma
+        return np.concatenate([theta, eta[..., None]], -1)
+
+
+class EightSchoolsModel(ModelSpec):
+    """y = mu + tau v + sigma n with mu~N(0,5), tau~half-Cauchy(5).
+
+    Reference: mlift/example_models/eight_schools.py:28-81.  Any number of "schools"
+    compiled into the library (dim_y in {4, 8, 16}) is accepted.
+    """
+
+    family = "hierarchical"
+
+    def __init__(self, y_obs, sigma, parametrization="unbounded"):
+        y_obs = np.asarray(y_obs, dtype=np.float64)
+        sigma = np.asarray(sigma, dtype=np.float64)
+        super().__init__(_lib.MODEL_HIER, y_obs.size, parametrization,
+                         np.concatenate([y_obs, sigma]))  # fmt: skip
+        self.data = {"y_obs": y_obs, "σ": sigma, "parametrization": parametrization}
+
+    def generate_params(self, u):
+        """Host-side (NumPy) parameter transform, for initial states and traces."""
+        u = np.asarray(u, dtype=np.float64)
+        if self.parametrization == "unbounded":
+            return {"μ": u[..., 0], "τ": np.exp(u[..., 1])}
+        from scipy.special import ndtr
+
+        return {"μ": 5.0 * u[..., 0],
+                "τ": 5.0 * np.tan(np.pi * ((ndtr(u[..., 1]) + 1) / 2 - 0.5))}  # fmt: skip
+
+    def sample_initial_states(self, rng, num_chain):
+        """eight_schools.py:67-81: u ~ prior, v ~ N(0, I), n = (y - x) / sigma."""
+        Y = self.dim_y
+        if self.parametrization == "unbounded":
+            u0 = rng.normal(0.0, 5.0, num_chain)
+            u1 = np.log(np.abs(rng.standard_cauchy(num_chain) * 5.0))
+        else:
+            u0, u1 = rng.standard_normal(num_chain), rng.standard_normal(num_chain)
+        u = np.stack([u0, u1], -1)
+        v = rng.standard_normal((num_chain, Y))
+        par = self.generate_params(u)
+        x = par["μ"][:, None] + par["τ"][:, None] * v
+        n = (self.data["y_obs"][None] - x) / self.data["σ"][None]
+        return np.concatenate([u, v, n], -1)
