@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""Benchmark of the constrained-leapfrog hot path (BASELINE.json metric: constrained
+leapfrog steps/s summed over all chains).
+
+  python bench.py --gpus N --steps K --warmup W            # CUDA arm (this repo)
+  python bench.py --impl reference --gpus N --steps K ...   # CPU arm (oracle port)
+
+A bench "step" is ONE launch of the fused trajectory kernel: `--n-step` constrained
+leapfrog steps (A-B-A with projection and reversibility check) for every chain.
+`value` = chains * n_step * K / (sum of the K CUDA-event intervals, max over ranks).
+Prints ONE JSON line on rank 0.  Data are synthetic.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SOLVERS = {"quasi-newton": 0, "newton": 1, "newton-line-search": 2}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="mlb", choices=("mlb", "reference"))
+    ap.add_argument("--workload", default="hier", choices=("hier", "toy"))
+    ap.add_argument("--n-chain", type=int, default=65536, help="chains PER GPU")
+    ap.add_argument("--n-school", type=int, default=8)
+    ap.add_argument("--n-step", type=int, default=32, help="leapfrog steps per launch")
+    ap.add_argument("--step-size", type=float, default=0.1)
+    ap.add_argument("--solver", default="newton", choices=tuple(SOLVERS))
+    ap.add_argument("--cpu-sample-chains", type=int, default=0,
+                    help="chains in the bounded CPU sample (0 = auto)")  # fmt: skip
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------ workload (host)
+
+
+def synthetic_schools(n_school, seed=202101):
+    rng = np.random.default_rng(seed)
+    sigma = rng.uniform(9.0, 18.0, n_school)
+    y = 4.4 + 3.6 * rng.standard_normal(n_school) + sigma * rng.standard_normal(n_school)
+    return y, sigma
+
+
+def make_inputs(args, n_chain, chain0):
+    """On-manifold positions: hier - u ~ moderate prior draws, v ~ N(0, I),
+    n = (y - x) / sigma; toy - theta ~ N(0, I) lifted.  Momenta ~ N(0, I) (projected on
+    the device / by the oracle before use)."""
+    rng = np.random.default_rng([202101, chain0])
+    if args.workload == "hier":
+        y, sigma = synthetic_schools(args.n_school)
+        u = np.stack([rng.normal(0.0, 5.0, n_chain),
+                      np.clip(np.log(np.abs(rng.standard_cauchy(n_chain) * 5.0)), -2.0, 3.0)], 1)  # fmt: skip
+        v = rng.standard_normal((n_chain, args.n_school))
+        x = u[:, :1] + np.exp(u[:, 1:2]) * v
+        q = np.concatenate([u, v, (y[None] - x) / sigma[None]], 1)
+        data = (y, sigma)
+    else:
+        sig = 0.1
+        th = rng.standard_normal((n_chain, 2))
+        f = th[:, 1] ** 2 + 2.0 * th[:, 0] ** 2 * (th[:, 0] ** 2 - 0.5)
+        q = np.concatenate([th, ((1.0 - f) / sig)[:, None]], 1)
+        data = (sig, 1.0, 2.0)
+    p = rng.standard_normal(q.shape)
+    return data, q, p
+
+
+def workload_name(args):
+    if args.workload == "hier":
+        return (f"eight-schools-shaped hierarchical model (J={args.n_school}, dim_q="
+                f"{2 + 2 * args.n_school}), {args.n_chain} chains per GPU, synthetic data")  # fmt: skip
+    return f"toy 2-D model (sigma=0.1), {args.n_chain} chains per GPU"
+
+
+# ------------------------------------------------------------------ CPU (oracle) leg
+
+
+def cpu_oracle_rate(args, target_seconds=12.0, sample_chains=0):
+    """Times the C++ oracle port on all host cores on a bounded sample of the workload.
+    Returns (steps_per_s, cores, sample_description, seconds)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import c_oracle as co
+
+    cores = co.max_threads()
+    n = sample_chains or 2048 * max(1, cores // 4)
+    data, q, p = make_inputs(args, n, 10**6)
+    if args.workload == "hier":
+        cm = co.OracleModel.hier(*data)
+    else:
+        cm = co.OracleModel.toy(*data)
+    jac, _ = cm.jacob_constr_blocks(q)
+    p = p - cm.normal_space_component(jac, cm.decompose_gram(jac), p)
+    opts = co.solver_opts(SOLVERS[args.solver])
+    cm.leapfrog_steps(q[: 64 * cores], p[: 64 * cores], args.step_size, 2, opts)  # warm
+    t0 = time.perf_counter()
+    r = cm.leapfrog_steps(q, p, args.step_size, args.n_step, opts)
+    dt = time.perf_counter() - t0
+    done = int(r["n_done"].sum())
+    reps = 1
+    if dt < target_seconds / 4:  # enlarge sample towards the target duration
+        reps = int(min(50, target_seconds / max(dt, 1e-3)))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r = cm.leapfrog_steps(q, p, args.step_size, args.n_step, opts)
+        dt = time.perf_counter() - t0
+        done = int(r["n_done"].sum()) * reps
+    desc = (f"{n} chains x {args.n_step} steps x {reps} repeats of the same workload, "
+            f"C++ oracle port, OpenMP over chains")  # fmt: skip
+    return done / dt, cores, desc, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rates, secs = [], []
+    for i in range(args.warmup + args.steps):
+        r, cores, desc, dt = cpu_oracle_rate(args, target_seconds=1.0,
+                                             sample_chains=args.cpu_sample_chains)  # fmt: skip
+        if i >= args.warmup:
+            rates.append(r), secs.append(dt)
+    value = float(np.mean(rates))
+    line = {
+        "impl": "reference", "metric": "constrained leapfrog steps/s (all chains)",
+        "value": value, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args), "n_step": args.n_step,
+                   "step_size": args.step_size, "solver": args.solver,
+                   "note": "reference arm = CPU oracle port on host cores (JAX/Mici are "
+                           "not installable offline); each bench step is a bounded sample"},
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port",
+                         "sample": desc},
+        "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }  # fmt: skip
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------ CUDA leg
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")  # fmt: skip
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)  # fmt: skip
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])), mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), r[5:9]):  # fmt: skip
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}  # fmt: skip
+
+
+def run_mlb(args):
+    import torch
+    import torch.distributed as dist
+
+    import manifold_lifting_b200 as mlb
+    from manifold_lifting_b200 import _lib, flops
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the mlb arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    n, n_step, K, W = args.n_chain, args.n_step, args.steps, max(args.warmup, 3)
+    data, q_host, p_host = make_inputs(args, n, rank * n)
+    if args.workload == "hier":
+        model = mlb.models.EightSchoolsModel(*data)
+        system = mlb.HierarchicalLatentVariableModelSystem(model, model.data, model.dim_u)
+    else:
+        model = mlb.models.Toy2DModel(*data)
+        system = mlb.IndependentAdditiveNoiseModelSystem(model, model.data, model.dim_u)
+    Q = model.dim_q
+    L = _lib.lib()
+    solver = SOLVERS[args.solver]
+    opts = _lib.SolverOpts(solver, 50, 10, 0, 1e-9, 1e-8, 1e10, 2e-8, 0, 0)
+
+    q0 = _lib.to_soa(q_host)
+    st0 = mlb.states.ChainState(q0)
+    p0 = system.project_onto_cotangent_space(_lib.to_soa(p_host), st0)
+    q, p = _lib.soa_clone(q0), _lib.soa_clone(p0)
+    status, n_done, itf, itr = (torch.empty(n, dtype=torch.int32, device="cuda")
+                                for _ in range(4))  # fmt: skip
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def launch(nstep):
+        pq, ld = _lib.p_soa(q, Q)
+        _lib.check(L.mlb_leapfrog_steps(
+            model.handle, C.c_int64(n), C.c_int64(ld), pq, _lib.p_soa(p, Q)[0],
+            C.c_double(args.step_size), None, C.c_int32(nstep), C.byref(opts),
+            _lib.p_vec(status, torch.int32), _lib.p_vec(n_done, torch.int32),
+            _lib.p_vec(itf, torch.int32), _lib.p_vec(itr, torch.int32), None, None,
+            C.c_void_p(stream.cuda_stream)))  # fmt: skip
+
+    def reset():
+        q.copy_(q0), p.copy_(p0)
+        flush.zero_()
+
+    def timed(nstep, iters):
+        evs = []
+        for _ in range(iters):
+            reset()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            launch(nstep)
+            e1.record(stream)
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in evs]
+
+    for _ in range(W):
+        reset(), launch(n_step)
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    launches0 = L.mlb_launch_count()
+    barrier()
+    ms = timed(n_step, K)
+    barrier()
+    launches = L.mlb_launch_count() - launches0
+    clk = clocks.stop()
+    total_ms = float(sum(ms))
+    done_local = float(n_done.sum())  # chain-steps completed in the LAST timed step
+    mean_iters = float((itf.sum() + itr.sum()) / max(done_local, 1.0))
+    failed = float((status != 0).double().mean())
+
+    # --- e2e: host buffers through the C ABI (H2D + kernels + D2H inside the timing)
+    qh = torch.empty(n, Q, dtype=torch.float64).pin_memory()
+    ph = torch.empty(n, Q, dtype=torch.float64).pin_memory()
+    q_src, p_src = q0.cpu().contiguous(), p0.cpu().contiguous()
+    sth = torch.empty(n, dtype=torch.int32).pin_memory()
+    ndh = torch.empty(n, dtype=torch.int32).pin_memory()
+    e2e_iters = max(3, min(K, 10))
+    e2e_s = []
+    for i in range(2 + e2e_iters):
+        qh.copy_(q_src), ph.copy_(p_src)
+        barrier()
+        t0 = time.perf_counter()
+        _lib.check(L.mlb_leapfrog_steps_host(
+            model.handle, C.c_int64(n), C.c_void_p(qh.data_ptr()), C.c_void_p(ph.data_ptr()),
+            C.c_double(args.step_size), C.c_int32(n_step), C.byref(opts),
+            C.c_void_p(sth.data_ptr()), C.c_void_p(ndh.data_ptr()), None, None, None, None))  # fmt: skip
+        torch.cuda.synchronize()
+        if i >= 2:
+            e2e_s.append(time.perf_counter() - t0)
+    e2e_done = float(ndh.sum())
+    e2e_time = float(np.mean(e2e_s))
+
+    # --- HBM view: one leapfrog step per launch, L2 flushed, same chains
+    ms1 = timed(1, max(5, min(K, 20)))
+    done1 = float(n_done.sum())
+    fp64_peak = L.mlb_measure_fp64_tflops(3) if rank == 0 else 0.0
+
+    red = torch.tensor([total_ms, e2e_time, float(np.mean(ms1))], dtype=torch.float64,
+                       device="cuda")  # fmt: skip
+    tot = torch.tensor([done_local * K, e2e_done, done1], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        total_ms, e2e_time, ms1_mean = (float(x) for x in red)
+        steps_all, e2e_all, done1_all = (float(x) for x in tot)
+        value = steps_all / (total_ms * 1e-3)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+        flops_step = flops.step_flops(model, solver, mean_iters)
+        ach_tf = flops_step * done_local / (float(np.mean(ms)) * 1e-3) / 1e12
+        bytes_step = flops.step_bytes(model)
+        ach_gbs = bytes_step * (done1_all / world) / (ms1_mean * 1e-3) / 1e9
+        line = {
+            "metric": "constrained leapfrog steps/s (all chains)", "value": value,
+            "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": workload_name(args), "n_step": n_step,
+                "step_size": args.step_size, "solver": args.solver,
+                "constraint_tol": 1e-9, "position_tol": 1e-8, "reverse_check_tol": 2e-8,
+                "chains_total": n * world, "mean_projection_iters_per_step": mean_iters,
+                "failed_chain_fraction": failed,
+                "timing": "sum of per-step CUDA-event intervals on the launch stream; "
+                          "state reset and L2 flushed (256 MiB memset) between steps, "
+                          "outside the intervals; max over ranks",
+            },
+            "roofline": {
+                "bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": ach_tf / fp64_peak if fp64_peak > 0 else None, "traffic": None,
+                "kernel": "k_leapfrog_steps (fused trajectory)",
+                "algorithmic_flops_per_chain_step": flops_step,
+                "peak_source": "DFMA-loop microbenchmark run live in this process "
+                               "(MEASURED_PEAKS.json has no fp64 entry)",
+            },
+            "roofline_hbm": {
+                "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach_gbs / hbm_peak, "traffic": None,
+                "kernel": "k_leapfrog_steps, one step per launch, L2 flushed",
+                "algorithmic_bytes_per_chain_step": bytes_step,
+                "ms_per_launch": ms1_mean, "peak_source": hbm_src,
+            },
+            "e2e": {"value": e2e_all / e2e_time, "unit": "steps/s",
+                    "h2d_bytes_per_step": 2 * n * Q * 8,
+                    "d2h_bytes_per_step": 2 * n * Q * 8 + 2 * n * 4,
+                    "api": "mlb_leapfrog_steps_host (pinned host [n, Q] buffers in/out)"},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+        }  # fmt: skip
+        if not args.no_cpu_baseline and world == 1:
+            r, cores, desc, secs = cpu_oracle_rate(args, 12.0, args.cpu_sample_chains)
+            line["cpu_baseline"] = {"value": r, "unit": "steps/s", "cores": cores,
+                                    "kind": "port", "sample": desc, "seconds": secs}  # fmt: skip
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    run_reference(a) if a.impl == "reference" else run_mlb(a)

@@ -1,0 +1,59 @@
+"""Analytic algorithmic FP64 operation counts of the constrained leapfrog step (the single
+source for bench.py's FP64 roofline; DESIGN.md section "Kernels and rooflines").
+
+Counting rule: add / sub / mul / div / sqrt / exp / log / abs-max-compare = 1, fma = 2.
+Counts follow the reference's formulas (systems.py:712-794 for the hierarchical Woodbury
+family, systems.py:582-609 for the dense additive family), NOT the instruction stream
+(ncu's executed-instruction counters are the cross-check, see profiles/).
+"""
+
+
+def hier_counts(U, Y):
+    Q = U + 2 * Y
+    c = {}
+    c["constr"] = 5 * Y + 1
+    c["jacob"] = c["constr"] + Y
+    c["decompose"] = 3 * Y + U * Y + 2 * U * U * Y + U + (U * U * U) // 3 + 2 * U
+    c["inv_gram"] = Y + 2 * U * Y + 2 * U * U + 2 * U * Y + 2 * Y
+    c["rmult"] = 2 * U * Y + 2 * Y
+    c["lmult"] = 2 * U * Y + 4 * Y
+    c["pinv"] = c["inv_gram"] + c["rmult"]
+    c["project"] = c["lmult"] + c["pinv"] + Q
+    c["inv_jacprod"] = (3 * Y + U * Y + 2 * U * U * Y + U + Y + 2 * U * Y
+                        + (2 * U * U * U) // 3 + 2 * U * U + 2 * U * Y + 2 * Y)  # fmt: skip
+    c["newton_iter"] = c["jacob"] + Y + c["inv_jacprod"] + c["rmult"] + 2 * Q + Q
+    c["quasi_newton_iter"] = c["constr"] + Y + c["pinv"] + 2 * Q + Q
+    c["logdet"] = 2 * (U + Y) + 2
+    c["nld"] = 4 * Y + 12
+    c["grad_logdet"] = Y * (2 * U * U + 2 * U + 3 * U + 8) + 10
+    c["evaluate"] = c["jacob"] + c["decompose"] + c["logdet"] + c["nld"] + c["grad_logdet"]
+    c["step_fixed"] = (2 * Q + c["project"] + 2 * Q + 2 * Q + c["evaluate"] + c["project"]
+                       + 2 * Q + 2 * Q + 2 * Q + c["project"])  # fmt: skip
+    return c
+
+
+def toy_counts():
+    c = {"constr": 9, "jacob": 16, "decompose": 7, "inv_gram": 2, "rmult": 3, "lmult": 6}
+    c["pinv"] = c["inv_gram"] + c["rmult"]
+    c["project"] = c["lmult"] + c["pinv"] + 3
+    c["inv_jacprod"] = 8
+    c["newton_iter"] = c["jacob"] + 1 + c["inv_jacprod"] + c["rmult"] + 9
+    c["quasi_newton_iter"] = c["constr"] + 1 + c["pinv"] + 9
+    c["logdet"], c["nld"], c["grad_logdet"] = 1, 6, 12
+    c["evaluate"] = c["jacob"] + c["decompose"] + c["logdet"] + c["nld"] + c["grad_logdet"]
+    c["step_fixed"] = 6 + c["project"] + 6 + 6 + c["evaluate"] + c["project"] + 18 + c["project"]
+    return c
+
+
+def step_flops(model, solver, mean_iters_per_step):
+    """Algorithmic flops of one constrained leapfrog step for one chain, given the mean
+    number of projection iterations (forward + reverse) per step."""
+    c = toy_counts() if model.model_id == 0 else hier_counts(model.dim_u, model.dim_y)
+    per_iter = c["quasi_newton_iter"] if solver in (0, 4) else c["newton_iter"]
+    return c["step_fixed"] + mean_iters_per_step * per_iter
+
+
+def step_bytes(model):
+    """Algorithmic HBM bytes of one chain-step: read + write pos, mom, plus
+    16 B of per-chain outputs."""
+    return 32 * model.dim_q + 16
