@@ -125,7 +125,7 @@ MLB_DEV bool lu_solve(double (&a)[K][K], double (&b)[K]) {
   return ok;
 }
 
-// ---- Philox4x32-10 counter-based RNG (identical stream to oracle/c/chmc_oracle.cpp)
+// ---- Philox4x32-10 counter-based RNG (Salmon et al. 2011); the stream layout is part of the ABI
 MLB_HD void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {

@@ -1,0 +1,183 @@
+"""CPU tests of the oracle itself (no GPU): the closed-form C++ oracle against the golden
+fixtures, against the torch autodiff restatement, and against the invariants of SURVEY 8c.
+
+"Parity unpinned": the reference has no tests for the constrained path and cannot run
+here; the only reference-produced numbers are the notebook's Euclidean-leapfrog output.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import c_oracle as co
+from _cases import (ChainState, hier_case, hier_states, rel_err, tangent_momentum, toy_case,
+                    toy_states)  # fmt: skip
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = [("hier", "unbounded"), ("hier", "normal"), ("toy", None)]
+
+
+def make(kind, par, n, seed=7):
+    if kind == "hier":
+        omodel, osys, cm = hier_case(par)
+        return omodel, osys, cm, hier_states(omodel, n, seed)
+    omodel, osys, cm = toy_case(0.1)
+    return omodel, osys, cm, toy_states(omodel, n, seed)
+
+
+def test_notebook_euclidean_leapfrog_known_answer():
+    """The reference tree's only numeric known-answer vector (notebook raw lines 692-753):
+    pins the toy forward function (factor 2), the posterior gradient and leapfrog order."""
+    g = np.load(os.path.join(GOLD, "notebook_euclidean_leapfrog.npz"))
+    sigma, y, eps, k = (float(g[x]) for x in ("sigma", "y", "step_size", "coeff"))
+    from mlift_oracle.models import Toy2D
+
+    model = Toy2D(sigma, y, k)
+
+    def grad_u(theta):
+        t = torch.tensor(theta, requires_grad=True)
+        u = (t**2).sum() / 2 + (y - model.forward_func(t)) ** 2 / (2 * sigma**2)
+        return torch.autograd.grad(u, t)[0].numpy()
+
+    pos, mom = g["pos"][0].copy(), g["mom"][0].copy()
+    for s in (1, 2):
+        mom = mom - 0.5 * eps * grad_u(pos)
+        pos = pos + eps * mom
+        mom = mom - 0.5 * eps * grad_u(pos)
+        assert np.allclose(pos, g["pos"][s], rtol=0, atol=2e-7)
+        assert np.allclose(mom, g["mom"][s], rtol=0, atol=2e-6)
+    # the closed-form C++ toy Jacobian is the same dF/dtheta
+    cm = co.OracleModel.toy(sigma, y, k)
+    q = model.lift(g["pos"])
+    (dy_du, _, dy_dn), c = cm.jacob_constr_blocks(q)
+    t = torch.tensor(g["pos"][1], requires_grad=True)
+    df = torch.autograd.grad(model.forward_func(t), t)[0].numpy()
+    assert np.allclose(dy_du[1, 0], df, rtol=1e-14) and np.allclose(dy_dn, sigma)
+    assert np.abs(c).max() < 1e-12  # lifted points are on the manifold
+
+
+@pytest.mark.parametrize("name,kind,par", [("hier_unbounded", "hier", "unbounded"),
+                                           ("hier_normal", "hier", "normal"),
+                                           ("toy", "toy", None)])  # fmt: skip
+def test_c_oracle_matches_golden_autodiff_steps(name, kind, par):
+    """Closed-form C++ oracle vs committed outputs of the autodiff restatement: projected
+    positions, momenta, Hamiltonian and per-step (forward, reverse) iteration counts."""
+    g = np.load(os.path.join(GOLD, f"autodiff_steps_{name}.npz"))
+    _, _, cm, _ = make(kind, par, 1)
+    for sid in g["solvers"]:
+        r = cm.leapfrog_steps(g["q0"], g["p0"], float(g["dt"]), int(g["n_step"]),
+                              co.solver_opts(int(sid)))  # fmt: skip
+        assert (r["status"] == 0).all()
+        assert rel_err(r["q"], g[f"q_{sid}"]) < 1e-10
+        assert rel_err(r["p"], g[f"p_{sid}"]) < 1e-10
+        assert rel_err(r["h_final"], g[f"h_{sid}"]) < 1e-10
+        its = g[f"iters_{sid}"]  # [chain, step, (fwd, rev)]
+        assert (r["iters_fwd"] == its[:, :, 0].sum(1)).all()
+        assert (r["iters_rev"] == its[:, :, 1].sum(1)).all()
+
+
+@pytest.mark.parametrize("kind,par", CASES)
+def test_c_oracle_ops_match_autodiff(kind, par):
+    """Jacobian blocks, Gram factor, log-det and its gradient (reverse-over-forward in the
+    reference, systems.py:332-334) from autodiff vs the closed forms."""
+    omodel, osys, cm, q = make(kind, par, 5)
+    (dy_du, dy_dv, dy_dn), c = cm.jacob_constr_blocks(q)
+    g_ld, v_ld = cm.grad_log_det_sqrt_gram(q)
+    v_nld, g_nld = cm.neg_log_dens(q)
+    for i in range(q.shape[0]):
+        st = ChainState(q[i])
+        assert rel_err(c[i], osys.constr(st)) < 1e-12
+        if kind == "hier":
+            jb = osys.jacob_constr_blocks(st)
+            assert rel_err(dy_du[i], jb[0]) < 1e-12
+            assert rel_err(dy_dv[i], jb[1]) < 1e-12 and rel_err(dy_dn[i], jb[2]) < 1e-12
+        else:
+            jac = np.asarray(osys.jacob_constr(st))
+            assert rel_err(np.concatenate([dy_du[i].ravel(), dy_dn[i]]), jac.ravel()) < 1e-12
+        assert rel_err(v_ld[i], osys.log_det_sqrt_gram(st)) < 1e-12
+        assert rel_err(g_ld[i], osys.grad_log_det_sqrt_gram(st)) < 1e-10
+        assert rel_err(v_nld[i], osys.neg_log_dens(st)) < 1e-12
+        assert rel_err(g_nld[i], osys.grad_neg_log_dens(st)) < 1e-12
+
+
+@pytest.mark.parametrize("kind,par", CASES)
+def test_grad_log_det_vs_finite_differences(kind, par):
+    _, _, cm, q = make(kind, par, 4)
+    g, _ = cm.grad_log_det_sqrt_gram(q)
+    eps = 1e-6
+    for k in range(q.shape[1]):
+        dq = np.zeros_like(q)
+        dq[:, k] = eps
+        fd = (cm.log_det_sqrt_gram(q + dq) - cm.log_det_sqrt_gram(q - dq)) / (2 * eps)
+        assert np.allclose(fd, g[:, k], rtol=1e-6, atol=1e-8)
+
+
+@pytest.mark.parametrize("kind,par", CASES)
+def test_projection_invariants(kind, par):
+    """on-manifold after projection, J p = 0 after cotangent
+    projection, the three mlift solvers and the two Mici solvers land on one point."""
+    _, _, cm, q = make(kind, par, 200)
+    p = tangent_momentum(cm, q)
+    jac, _ = cm.jacob_constr_blocks(q)
+    assert np.abs(cm.lmult_by_jacob_constr(jac, p)).max() < 1e-10
+    dt = 0.1
+    outs = []
+    for s in range(5):
+        r = cm.solve_projection(q + dt * p, q, dt, co.solver_opts(s))
+        ok = r["status"] == 0
+        assert ok.mean() > 0.9
+        assert np.abs(cm.constr(r["q"]))[ok].max() < 1e-8
+        # the correction lies in span(J_prev^T): q_out = q_try - dt * mu
+        assert rel_err((q + dt * p - dt * r["mu"])[ok], r["q"][ok]) < 1e-12
+        outs.append((ok, r["q"]))
+    ok = np.all([o[0] for o in outs], 0)
+    for _, qo in outs[1:]:
+        assert np.abs(qo - outs[0][1])[ok].max() < 1e-6
+
+
+@pytest.mark.parametrize("kind,par", CASES)
+def test_step_reversibility_and_energy(kind, par):
+    """forward then momentum-flipped steps return to the start;
+    energy error is O(dt^2)."""
+    _, _, cm, q = make(kind, par, 200)
+    p = tangent_momentum(cm, q)
+    opts = co.solver_opts(co.SOLVER_NEWTON)
+    errs = []
+    for dt in (0.1, 0.05):
+        f = cm.leapfrog_steps(q, p, dt, 4, opts)
+        ok = f["status"] == 0
+        b = cm.leapfrog_steps(f["q"][ok], -f["p"][ok], dt, 4, opts)
+        ok2 = b["status"] == 0
+        assert np.abs(b["q"][ok2] - q[ok][ok2]).max() < 1e-6
+        assert np.abs(b["p"][ok2] + p[ok][ok2]).max() < 1e-6
+        errs.append(np.median(np.abs(f["h_final"] - f["h_init"])[ok]))
+    assert errs[1] < errs[0] / 2.5
+
+
+def test_woodbury_equals_dense_gram():
+    """the Woodbury factorisation (systems.py:749-794) agrees with the
+    dense Gram matrix assembled from the same Jacobian blocks."""
+    _, _, cm, q = make("hier", "unbounded", 20)
+    (dy_du, dy_dv, dy_dn), _ = cm.jacob_constr_blocks(q)
+    chol, d = cm.decompose_gram((dy_du, dy_dv, dy_dn))
+    rng = np.random.default_rng(0)
+    w = rng.standard_normal((20, cm.Y))
+    x = cm.lmult_by_pinv_jacob_constr((dy_du, dy_dv, dy_dn), (chol, d), w)
+    for i in range(20):
+        jfull = np.concatenate([dy_du[i], np.diag(dy_dv[i]), np.diag(dy_dn[i])], 1)
+        gram = jfull @ jfull.T
+        assert rel_err(x[i], jfull.T @ np.linalg.solve(gram, w[i])) < 1e-11
+        sign, logdet = np.linalg.slogdet(gram)
+        assert abs(0.5 * logdet - cm.log_det_sqrt_gram(q[i : i + 1])[0]) < 1e-11
+
+
+def test_philox_stream_reference_values():
+    """Counter-based RNG: uniforms in (0,1), normals with unit variance, streams differ
+    by chain and iteration (the sharding-independence contract of SURVEY 8e)."""
+    z = np.array([co.philox_normals(1, c, 0, 18) for c in range(4000)])
+    assert abs(z.mean()) < 0.02 and abs(z.std() - 1.0) < 0.02
+    u = np.array([co.philox_uniform(1, c, 0) for c in range(4000)])
+    assert 0.0 < u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.02
+    assert not np.allclose(co.philox_normals(1, 5, 0, 4), co.philox_normals(1, 5, 1, 4))
+    assert not np.allclose(co.philox_normals(1, 5, 0, 4), co.philox_normals(1, 6, 0, 4))
