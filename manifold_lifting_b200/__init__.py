@@ -6,7 +6,7 @@ imports (`import mlift`, `from mlift.systems import ...`) resolve to the CUDA pa
 """
 import sys
 
-from . import (_lib, adapters, errors, integrators, models, samplers, solvers, states,
+from . import (_lib, adapters, errors, integrators, models, parallel, samplers, solvers, states,
                systems, transitions)  # fmt: skip
 from .adapters import *  # noqa: F401,F403
 from .solvers import *  # noqa: F401,F403
