@@ -258,6 +258,12 @@ int64_t mlb_launch_count(void);
  * entry).  Returns achieved TFLOP/s of a dependent-chain DFMA loop over the full chip. */
 double mlb_measure_fp64_tflops(int32_t repeats);
 
+/* Self-test of the lean fp64 primitives used by the kernels (Newton-refined MUFU
+ * reciprocal / reciprocal square root, csrc/mlb_common.cuh): x [n] device in; rcp, sqrt,
+ * rsqrt [n] device out.  Tests compare them with the IEEE operations. */
+int mlb_selftest_fast_math(int64_t n, const double* x, double* rcp, double* sqrt_out,
+                           double* rsqrt_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,15 @@ __global__ void k_fp64_peak(double* out, int iters) {
   if (s == 12345.678) out[0] = s;
 }
 
+__global__ void k_selftest_fast_math(int64_t n, const double* x, double* r, double* s,
+                                     double* rs) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  r[i] = rcp_fast(x[i]);
+  double t;
+  s[i] = sqrt_rsqrt_fast(x[i], t);
+  rs[i] = t;
+}
 
 }  // namespace mlb
 
@@ -336,6 +345,15 @@ int mlb_leapfrog_steps_host(const mlb_model* m, int64_t n, double* q, double* p,
 #undef MLB_TRY
   cudaFree(dev);
   return MLB_OK;
+}
+
+int mlb_selftest_fast_math(int64_t n, const double* x, double* rcp, double* sqrt_out,
+                           double* rsqrt_out, void* stream) {
+  MLB_ARG(n >= 0 && x && rcp && sqrt_out && rsqrt_out);
+  if (n == 0) return MLB_OK;
+  k_selftest_fast_math<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      n, x, rcp, sqrt_out, rsqrt_out);
+  return finish_launch();
 }
 
 double mlb_measure_fp64_tflops(int32_t repeats) {

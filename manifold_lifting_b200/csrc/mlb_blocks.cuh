@@ -32,6 +32,7 @@ struct Blocks {
   };
   struct Gram {
     double chol[K][K];  // Cholesky factor of the Gram (dense) or capacitance matrix
+    double rdiag[K];    // 1 / diag(chol)
     double d[Y];        // dy_dv^2 + dy_dn^2
     double rd[Y];       // 1 / d (hot-path multiplications instead of divisions)
     bool ok;
@@ -80,7 +81,7 @@ struct Blocks {
     for (int i = 0; i < Y; ++i) {
       double dv = FAM == FAM_HIER ? J.dv[i] : 0.0;
       G.d[i] = fma(dv, dv, J.dn[i] * J.dn[i]);
-      G.rd[i] = 1.0 / G.d[i];
+      G.rd[i] = rcp_fast(G.d[i]);
     }
     if (DENSE) {
 #pragma unroll
@@ -104,7 +105,7 @@ struct Blocks {
           G.chol[b][a] = s;
         }
     }
-    G.ok = chol_lower<K>(G.chol);
+    G.ok = chol_lower<K>(G.chol, G.rdiag);
   }
 
   // Gram^-1 w   (systems.py:596-597 dense; 619-624, 759-768 Woodbury)
@@ -114,7 +115,7 @@ struct Blocks {
       double b[K];
 #pragma unroll
       for (int i = 0; i < Y; ++i) b[i] = w[i];
-      chol_solve<K>(G.chol, b);
+      chol_solve<K>(G.chol, G.rdiag, b);
 #pragma unroll
       for (int i = 0; i < Y; ++i) out[i] = b[i];
     } else {
@@ -126,7 +127,7 @@ struct Blocks {
         for (int i = 0; i < Y; ++i) s = fma(J.du[i][a], w[i] * G.rd[i], s);
         t[a] = s;
       }
-      chol_solve<K>(G.chol, t);
+      chol_solve<K>(G.chol, G.rdiag, t);
 #pragma unroll
       for (int i = 0; i < Y; ++i) {
         double s = w[i];
@@ -146,7 +147,7 @@ struct Blocks {
     for (int i = 0; i < Y; ++i) {
       double dv = FAM == FAM_HIER ? Jl.dv[i] * Jr.dv[i] : 0.0;
       dprod[i] = fma(Jl.dn[i], Jr.dn[i], dv);
-      rd[i] = 1.0 / dprod[i];
+      rd[i] = rcp_fast(dprod[i]);
     }
     bool ok;
     if (DENSE) {
@@ -193,16 +194,21 @@ struct Blocks {
     return ok;
   }
 
-  // 0.5 log det(J J^T)   (systems.py:603-609 dense; 635-641, 785-794 Woodbury)
+  // 0.5 log det(J J^T)   (systems.py:603-609 dense; 635-641, 785-794 Woodbury):
+  // sum_k log chol_kk + 0.5 sum_i log d_i.  Logs are taken of PAIRWISE products (half
+  // as many ~35-instruction log evaluations; a product of two factors overflows only
+  // where the factors' own squares would).
   static MLB_DEV double log_det_sqrt_gram(const Gram& G) {
     double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < K; ++k) s += log(G.chol[k][k]);
+    for (int k = 0; k + 1 < K; k += 2) s += log(G.chol[k][k] * G.chol[k + 1][k + 1]);
+    if (K & 1) s += log(G.chol[K - 1][K - 1]);
     if (!DENSE) {
       double t = 0.0;
 #pragma unroll
-      for (int i = 0; i < Y; ++i) t += log(G.d[i]);
-      s += t / 2;
+      for (int i = 0; i + 1 < Y; i += 2) t += log(G.d[i] * G.d[i + 1]);
+      if (Y & 1) t += log(G.d[Y - 1]);
+      s = fma(0.5, t, s);
     }
     return s;
   }
@@ -271,8 +277,10 @@ struct Blocks {
 #pragma unroll
     for (int r = 0; r < Y; ++r) {
       G.d[r] = gram[(int64_t)(K * K + r) * ld + i];
-      G.rd[r] = 1.0 / G.d[r];
+      G.rd[r] = rcp_fast(G.d[r]);
     }
+#pragma unroll
+    for (int r = 0; r < K; ++r) G.rdiag[r] = rcp_fast(G.chol[r][r]);
     G.ok = true;
   }
 };

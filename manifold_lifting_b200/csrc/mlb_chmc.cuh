@@ -74,7 +74,7 @@ MLB_DEV SolveOut solve_projection(const typename M::Params& P, double (&q)[M::Q]
       r.ndq = vec_norm<Q>(delta, o.norm);
     }
 #pragma unroll
-    for (int k = 0; k < Q; ++k) mu_dt[k] = mu[k] / dt;
+    for (int k = 0; k < Q; ++k) mu_dt[k] = mu[k] * rdt;
     r.status = classify(r.err, r.ndq, o);
     return r;
   }
@@ -113,7 +113,7 @@ MLB_DEV SolveOut solve_projection(const typename M::Params& P, double (&q)[M::Q]
       r.n_constr += j;
     }
 #pragma unroll
-    for (int k = 0; k < Q; ++k) mu_dt[k] = (q0[k] - q[k]) / dt;
+    for (int k = 0; k < Q; ++k) mu_dt[k] = (q0[k] - q[k]) * rdt;
     r.status = classify(r.err, r.ndq, o);
     return r;
   }
@@ -174,11 +174,12 @@ struct Eval {
 template <class M>
 MLB_DEV bool evaluate_at(const typename M::Params& P, const double (&q)[M::Q], Eval<M>& E) {
   double c[M::Y];
-  M::jacob(P, q, E.J, c);
+  const typename M::Par par = M::params(q[0], q[1]);  // shared by everything below
+  M::jacob(P, q, par, E.J, c);
   M::B::decompose_gram(E.J, E.G);
   E.logdet = M::B::log_det_sqrt_gram(E.G);
-  E.nld = M::nld(P, q, E.g);
-  M::add_grad_logdet(P, q, E.J, E.G, E.g);
+  E.nld = M::nld(P, q, par, E.g);
+  M::add_grad_logdet(P, q, par, E.J, E.G, E.g);
   return E.G.ok;
 }
 
@@ -190,52 +191,116 @@ MLB_DEV double half_sq_norm(const double (&p)[Q]) {
   return 0.5 * s;
 }
 
-// One constrained leapfrog step.  On success q, p, E are advanced and MLB_ST_OK is
-// returned; on failure they are left at the pre-step values.
-template <class M, int SOLVER>
-MLB_DEV int leapfrog_step(const typename M::Params& P, double (&q)[M::Q], double (&p)[M::Q],
-                          Eval<M>& E, double dt, const Opts& o, int& it_fwd, int& it_rev) {
+template <class M>
+MLB_DEV double hamiltonian(const Eval<M>& E, const double (&p)[M::Q]) {
+  return E.nld + E.logdet + half_sq_norm<M::Q>(p);
+}
+
+// Up to n_step constrained leapfrog steps A(dt/2) B(dt) A(dt/2) with reversibility check
+// (Mici ConstrainedLeapfrogIntegrator) for the chain held by this thread.
+//
+// Code-size design: one step is the operation sequence
+//     [kick, project] solve(+dt) eval  [project] solve(-dt) check  [kick, project]
+// i.e. three "sub-phases" that each start with an (optional) half kick and a cotangent
+// projection at the current evaluation C, the first two followed by a projection solve
+// along the rows of C.J.  The loop below runs sub-phases, so the cotangent projection,
+// the projection solver and the evaluation (Jacobian, Gram factor, gradients) are each
+// instantiated at ONE code site; the straight-line fully-unrolled register code stays
+// inside the instruction cache (the first version inlined 3 + 2 + 2 copies: 64 KB of
+// SASS, and ncu showed the warps stalled on instruction fetch).  Only one evaluation is
+// live at a time: the forward solve is the last user of the previous point's blocks.
+//
+// (qw, pw) is the working state in registers.  The last COMMITTED state (start of the
+// current step) lives in shared memory at cq / cp (element k at cq[k * kStride]): it is
+// what the reversibility check compares against and what a failed step leaves behind.
+// PROJECT_FIRST adds a leading sub-phase that projects pw onto the cotangent space at
+// the start point (momentum refresh of an HMC transition, systems.py:468-471).
+struct TrajOut {
+  int status, done, it_fwd, it_rev;
+  double h_init, h_last;
+};
+
+template <class M, int SOLVER, bool PROJECT_FIRST, bool CHECK_H, int kStride>
+MLB_DEV TrajOut run_trajectory(const typename M::Params& P, double (&qw)[M::Q],
+                               double (&pw)[M::Q], double* cq, double* cp, int n_step,
+                               double dt, const Opts& o, double max_delta_h) {
   using B = typename M::B;
   constexpr int Q = M::Q;
-  it_fwd = 0, it_rev = 0;
-  double pn[Q], qn[Q];
-  // A(dt/2): h1 flow + cotangent projection at q
+  TrajOut t;
+  t.status = MLB_ST_OK, t.done = 0, t.it_fwd = 0, t.it_rev = 0;
+  t.h_init = t.h_last = nan("");
+  Eval<M> C;
+  int sub = PROJECT_FIRST ? -1 : 0;
+  bool first = true;
 #pragma unroll
-  for (int k = 0; k < Q; ++k) pn[k] = fma(-0.5 * dt, E.g[k], p[k]);
-  B::project_cotangent(E.J, E.G, pn);
-  // B(dt): h2 flow, retraction onto the manifold along rows of J(q)
+  for (int k = 0; k < Q; ++k) cq[k * kStride] = qw[k], cp[k * kStride] = pw[k];
+#pragma unroll 1
+  for (;;) {
+    if (first || sub == 1) {  // trajectory start / new position after the forward solve
+      const bool ok = evaluate_at<M>(P, qw, C);
+      if (first && !PROJECT_FIRST) t.h_init = t.h_last = hamiltonian<M>(C, pw);
+      first = false;
+      if (!ok) {
+        t.status = MLB_ST_LINALG;
+        break;
+      }
+      if (!PROJECT_FIRST && n_step <= 0) break;
+    }
+    const bool kick = (sub == 0) || (sub == 2);
 #pragma unroll
-  for (int k = 0; k < Q; ++k) qn[k] = fma(dt, pn[k], q[k]);
-  {
-    double mu_dt[Q];
-    SolveOut f = solve_projection<M, SOLVER>(P, qn, E.J, E.G, dt, o, mu_dt);
-    it_fwd = f.iters;
-    if (f.status != MLB_ST_OK) return f.status;
+    for (int k = 0; k < Q; ++k) pw[k] = kick ? fma(-0.5 * dt, C.g[k], pw[k]) : pw[k];
+    B::project_cotangent(C.J, C.G, pw);
+    if (PROJECT_FIRST && sub == -1) {
+      t.h_init = t.h_last = hamiltonian<M>(C, pw);
 #pragma unroll
-    for (int k = 0; k < Q; ++k) pn[k] -= mu_dt[k];
+      for (int k = 0; k < Q; ++k) cp[k * kStride] = pw[k];
+      if (n_step <= 0) break;
+      sub = 0;
+      continue;
+    }
+    if (sub == 2) {  // step complete: commit
+#pragma unroll
+      for (int k = 0; k < Q; ++k) cq[k * kStride] = qw[k], cp[k * kStride] = pw[k];
+      t.h_last = hamiltonian<M>(C, pw);
+      t.done += 1;
+      if (CHECK_H && fabs(t.h_last - t.h_init) > max_delta_h) {
+        t.status = MLB_ST_H_DIVERGED;
+        break;
+      }
+      if (t.done >= n_step) break;
+      sub = 0;
+      continue;
+    }
+    // B(dt) retraction (sub 0) or the reverse retraction of the reversibility check (sub 1)
+    const double sdt = (sub == 0) ? dt : -dt;
+    double qs[Q], mu[Q];
+#pragma unroll
+    for (int k = 0; k < Q; ++k) qs[k] = fma(sdt, pw[k], qw[k]);
+    const SolveOut r = solve_projection<M, SOLVER>(P, qs, C.J, C.G, sdt, o, mu);
+    if (sub == 0) t.it_fwd += r.iters; else t.it_rev += r.iters;
+    if (r.status != MLB_ST_OK) {
+      t.status = r.status;
+      break;
+    }
+    if (sub == 0) {
+#pragma unroll
+      for (int k = 0; k < Q; ++k) pw[k] -= mu[k], qw[k] = qs[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < Q; ++k) qs[k] -= cq[k * kStride];
+      if (vec_norm<Q>(qs, o.rev_norm) > o.rev_tol) {
+        t.status = MLB_ST_NON_REVERSIBLE;
+        break;
+      }
+    }
+    sub += 1;
   }
-  Eval<M> En;
-  if (!evaluate_at<M>(P, qn, En)) return MLB_ST_LINALG;
-  B::project_cotangent(En.J, En.G, pn);
-  {  // reversibility check: step back from (qn, pn) and compare with q
-    double qb[Q], mub[Q];
+  if (t.status != MLB_ST_OK && t.status != MLB_ST_H_DIVERGED) {
+    // a failed step leaves the chain at its last committed state
 #pragma unroll
-    for (int k = 0; k < Q; ++k) qb[k] = fma(-dt, pn[k], qn[k]);
-    SolveOut b = solve_projection<M, SOLVER>(P, qb, En.J, En.G, -dt, o, mub);
-    it_rev = b.iters;
-    if (b.status != MLB_ST_OK) return b.status;
-#pragma unroll
-    for (int k = 0; k < Q; ++k) qb[k] -= q[k];
-    if (vec_norm<Q>(qb, o.rev_norm) > o.rev_tol) return MLB_ST_NON_REVERSIBLE;
+    for (int k = 0; k < Q; ++k) qw[k] = cq[k * kStride], pw[k] = cp[k * kStride];
   }
-  // A(dt/2) at the new position
-#pragma unroll
-  for (int k = 0; k < Q; ++k) pn[k] = fma(-0.5 * dt, En.g[k], pn[k]);
-  B::project_cotangent(En.J, En.G, pn);
-#pragma unroll
-  for (int k = 0; k < Q; ++k) q[k] = qn[k], p[k] = pn[k];
-  E = En;
-  return MLB_ST_OK;
+  return t;
 }
 
 }  // namespace mlb

@@ -18,19 +18,51 @@ struct Opts {
   int max_iters, max_ls, norm, rev_norm;
 };
 
-// ---- norms (reference mlift/solvers.py:6-13); NaN-propagating like numpy/jax max
+// ---- lean fp64 primitives
+// The compiler's IEEE double division / sqrt expand to ~15-25 instructions plus an
+// out-of-line slow path each; the hot path has dozens of call sites, which made the fused
+// kernels larger than the instruction cache.  These versions refine the hardware
+// approximation (MUFU.RCP64H / MUFU.RSQ64H, ~2^-22 relative) with two Newton steps:
+// error <= ~1 ulp for normal, non-zero finite arguments (not correctly rounded, no
+// subnormal handling; tests/test_gpu_parity.py::test_fast_math_primitives checks them
+// against the IEEE operations).  0 -> NaN rather than inf: callers test pivots.
+MLB_DEV double rcp_fast(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+
+// s > 0: returns sqrt(s), writes 1 / sqrt(s)
+MLB_DEV double sqrt_rsqrt_fast(double s, double& rs) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(s));
+  double h = 0.5 * s;
+  r = fma(r, fma(-h * r, r, 0.5), r);
+  r = fma(r, fma(-h * r, r, 0.5), r);
+  double d = s * r;
+  d = fma(fma(-d, d, s), 0.5 * r, d);
+  rs = fma(r, fma(-d, r, 1.0), r);
+  return d;
+}
+
+// ---- norms (reference mlift/solvers.py:6-13).  The maximum norm propagates NaN like
+// numpy / jax `max`: for non-negative doubles the IEEE bit patterns order like unsigned
+// integers and every NaN pattern is above +inf, so an integer max of |v| does both jobs
+// off the fp64 pipe.
 template <int N>
 MLB_DEV double vec_norm(const double (&v)[N], int kind) {
   if (kind == MLB_NORM_MAX) {
-    double m = 0.0;
-    bool bad = false;
+    unsigned long long m = 0ull;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      double a = fabs(v[i]);
-      bad |= (a != a);
+      unsigned long long a =
+          (unsigned long long)__double_as_longlong(v[i]) & 0x7fffffffffffffffull;
       m = a > m ? a : m;
     }
-    return bad ? nan("") : m;
+    return __longlong_as_double((long long)m);
   }
   double s = 0.0;
 #pragma unroll
@@ -40,24 +72,24 @@ MLB_DEV double vec_norm(const double (&v)[N], int kind) {
 
 // ---- K x K factorizations, fully unrolled, static indexing only (stay in registers)
 
-// in-place lower Cholesky; false if a pivot is not positive (or NaN)
+// in-place lower Cholesky; rdiag <- reciprocal diagonal; false if a pivot is not positive
 template <int K>
-MLB_DEV bool chol_lower(double (&a)[K][K]) {
+MLB_DEV bool chol_lower(double (&a)[K][K], double (&rdiag)[K]) {
   bool ok = true;
 #pragma unroll
   for (int j = 0; j < K; ++j) {
     double s = a[j][j];
 #pragma unroll
-    for (int k = 0; k < j; ++k) s -= a[j][k] * a[j][k];
+    for (int k = 0; k < j; ++k) s = fma(-a[j][k], a[j][k], s);
     ok &= (s > 0.0);
-    double d = sqrt(s);
-    a[j][j] = d;
-    double rd = 1.0 / d;
+    double rd;
+    a[j][j] = sqrt_rsqrt_fast(s, rd);
+    rdiag[j] = rd;
 #pragma unroll
     for (int i = j + 1; i < K; ++i) {
       double t = a[i][j];
 #pragma unroll
-      for (int k = 0; k < j; ++k) t -= a[i][k] * a[j][k];
+      for (int k = 0; k < j; ++k) t = fma(-a[i][k], a[j][k], t);
       a[i][j] = t * rd;
     }
 #pragma unroll
@@ -68,20 +100,20 @@ MLB_DEV bool chol_lower(double (&a)[K][K]) {
 
 // solve L L^T x = b in place
 template <int K>
-MLB_DEV void chol_solve(const double (&L)[K][K], double (&b)[K]) {
+MLB_DEV void chol_solve(const double (&L)[K][K], const double (&rdiag)[K], double (&b)[K]) {
 #pragma unroll
   for (int i = 0; i < K; ++i) {
     double t = b[i];
 #pragma unroll
-    for (int k = 0; k < i; ++k) t -= L[i][k] * b[k];
-    b[i] = t / L[i][i];
+    for (int k = 0; k < i; ++k) t = fma(-L[i][k], b[k], t);
+    b[i] = t * rdiag[i];
   }
 #pragma unroll
   for (int i = K - 1; i >= 0; --i) {
     double t = b[i];
 #pragma unroll
-    for (int k = i + 1; k < K; ++k) t -= L[k][i] * b[k];
-    b[i] = t / L[i][i];
+    for (int k = i + 1; k < K; ++k) t = fma(-L[k][i], b[k], t);
+    b[i] = t * rdiag[i];
   }
 }
 
@@ -90,6 +122,7 @@ MLB_DEV void chol_solve(const double (&L)[K][K], double (&b)[K]) {
 template <int K>
 MLB_DEV bool lu_solve(double (&a)[K][K], double (&b)[K]) {
   bool ok = true;
+  double rp[K];
 #pragma unroll
   for (int j = 0; j < K; ++j) {
 #pragma unroll
@@ -106,21 +139,21 @@ MLB_DEV bool lu_solve(double (&a)[K][K], double (&b)[K]) {
       b[i] = sw ? x : y;
     }
     ok &= (fabs(a[j][j]) > 0.0);
-    double rp = 1.0 / a[j][j];
+    rp[j] = rcp_fast(a[j][j]);
 #pragma unroll
     for (int i = j + 1; i < K; ++i) {
-      double f = a[i][j] * rp;
+      double f = a[i][j] * rp[j];
 #pragma unroll
-      for (int k = j + 1; k < K; ++k) a[i][k] -= f * a[j][k];
-      b[i] -= f * b[j];
+      for (int k = j + 1; k < K; ++k) a[i][k] = fma(-f, a[j][k], a[i][k]);
+      b[i] = fma(-f, b[j], b[i]);
     }
   }
 #pragma unroll
   for (int i = K - 1; i >= 0; --i) {
     double t = b[i];
 #pragma unroll
-    for (int k = i + 1; k < K; ++k) t -= a[i][k] * b[k];
-    b[i] = t / a[i][i];
+    for (int k = i + 1; k < K; ++k) t = fma(-a[i][k], b[k], t);
+    b[i] = t * rp[i];
   }
   return ok;
 }

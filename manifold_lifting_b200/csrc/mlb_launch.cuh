@@ -124,10 +124,11 @@ __global__ void __launch_bounds__(kBlock)
   if (gram) M::B::store_gram(G, gram, ld, i);
   if (grad || nld_val || nld_grad || h1 || dh1) {
     double gn[Q], gl[Q];
-    const double nv = M::nld(P, qv, gn);
+    const typename M::Par par = M::params(qv[0], qv[1]);
+    const double nv = M::nld(P, qv, par, gn);
 #pragma unroll
     for (int k = 0; k < Q; ++k) gl[k] = 0.0;
-    M::add_grad_logdet(P, qv, J, G, gl);
+    M::add_grad_logdet(P, qv, par, J, G, gl);
     if (grad) store_vec<Q>(gl, grad, ld, i);
     if (nld_val) nld_val[i] = nv;
     if (nld_grad) store_vec<Q>(gn, nld_grad, ld, i);
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(kBlock)
   MLB_CHAIN_INDEX();
   double qv[M::Q], g[M::Q];
   load_vec<M::Q>(qv, q, ld, i);
-  const double v = M::nld(P, qv, g);
+  const double v = M::nld(P, qv, M::params(qv[0], qv[1]), g);
   if (val) val[i] = v;
   if (grad) store_vec<M::Q>(g, grad, ld, i);
 }
@@ -254,29 +255,23 @@ __global__ void __launch_bounds__(kBlock)
                      double* q, double* p, double dt, const double* dt_pc, int n_step,
                      Opts o, int32_t* status, int32_t* n_done, int32_t* iters_fwd,
                      int32_t* iters_rev, double* h_init, double* h_final) {
-  MLB_CHAIN_INDEX();
   constexpr int Q = M::Q;
+  __shared__ double commit[2 * Q][kBlock];  // last committed (q, p) of each chain
+  MLB_CHAIN_INDEX();
   double qv[Q], pv[Q];
   load_vec<Q>(qv, q, ld, i);
   load_vec<Q>(pv, p, ld, i);
   const double dti = dt_pc ? dt_pc[i] : dt;
-  Eval<M> E;
-  int st = evaluate_at<M>(P, qv, E) ? MLB_ST_OK : MLB_ST_LINALG;
-  if (h_init) h_init[i] = E.nld + E.logdet + half_sq_norm<Q>(pv);
-  int done = 0, tf = 0, tr = 0;
-  for (int s = 0; s < n_step && st == MLB_ST_OK; ++s) {
-    int f, r;
-    st = leapfrog_step<M, SOLVER>(P, qv, pv, E, dti, o, f, r);
-    tf += f, tr += r;
-    done += (st == MLB_ST_OK);
-  }
+  const TrajOut t = run_trajectory<M, SOLVER, false, false, kBlock>(
+      P, qv, pv, &commit[0][threadIdx.x], &commit[Q][threadIdx.x], n_step, dti, o, 0.0);
   store_vec<Q>(qv, q, ld, i);
   store_vec<Q>(pv, p, ld, i);
-  status[i] = st;
-  if (n_done) n_done[i] = done;
-  if (iters_fwd) iters_fwd[i] = tf;
-  if (iters_rev) iters_rev[i] = tr;
-  if (h_final) h_final[i] = E.nld + E.logdet + half_sq_norm<Q>(pv);
+  status[i] = t.status;
+  if (n_done) n_done[i] = t.done;
+  if (iters_fwd) iters_fwd[i] = t.it_fwd;
+  if (iters_rev) iters_rev[i] = t.it_rev;
+  if (h_init) h_init[i] = t.h_init;
+  if (h_final) h_final[i] = t.h_last;
 }
 
 struct SampleArgs {
@@ -298,10 +293,9 @@ template <class M, int SOLVER>
 __global__ void __launch_bounds__(kBlock)
     k_hmc_sample(const __grid_constant__ typename M::Params P, int64_t n, int64_t ld,
                  double* q, Opts o, SampleArgs a) {
-  MLB_CHAIN_INDEX();
   constexpr int Q = M::Q;
-  double qv[Q];
-  load_vec<Q>(qv, q, ld, i);
+  __shared__ double commit[2 * Q][kBlock];
+  MLB_CHAIN_INDEX();
   double ad_iter = 0, ad_smooth = 0, ad_err = 0, ad_target = 0, dti = a.dt;
   if (a.adapt) {
     ad_iter = a.adapt[0 * ld + i], ad_smooth = a.adapt[1 * ld + i];
@@ -310,47 +304,45 @@ __global__ void __launch_bounds__(kBlock)
   }
   double s_acc = 0, s_nacc = 0, s_conv = 0, s_nonrev = 0, s_hdiv = 0, s_steps = 0, s_its = 0;
   int last = MLB_ST_OK;
+#pragma unroll 1
   for (int it = 0; it < a.n_iter; ++it) {
-    Eval<M> E;
-    int st = evaluate_at<M>(P, qv, E) ? MLB_ST_OK : MLB_ST_LINALG;
+    // the chain's current position stays in q (global); the proposal lives in registers
     double pc[Q], qc[Q];
+    load_vec<Q>(qc, q, ld, i);
     if (a.mom_noise) {
       load_vec<Q>(pc, a.mom_noise + (int64_t)it * Q * ld, ld, i);
     } else {
-#pragma unroll
+      // rolled loop (the Philox + Box-Muller body is ~400 instructions): normals go
+      // through this thread's shared-memory column, then into registers
+      double* col = &commit[Q][threadIdx.x];
+#pragma unroll 1
       for (int j = 0; 2 * j < Q; ++j) {
         double n0, n1;
         philox_normal_pair(a.seed, a.chain0 + (uint64_t)i, a.iter0 + (uint32_t)it,
                            (uint32_t)j, n0, n1);
-        pc[2 * j] = n0;
-        if (2 * j + 1 < Q) pc[2 * j + 1] = n1;
+        col[(2 * j) * kBlock] = n0;
+        if (2 * j + 1 < Q) col[(2 * j + 1) * kBlock] = n1;
       }
+#pragma unroll
+      for (int k = 0; k < Q; ++k) pc[k] = col[k * kBlock];
     }
     const double u = a.unif ? a.unif[(int64_t)it * ld + i]
                             : philox_uniform(a.seed, a.chain0 + (uint64_t)i,
                                              a.iter0 + (uint32_t)it);
-    M::B::project_cotangent(E.J, E.G, pc);
-#pragma unroll
-    for (int k = 0; k < Q; ++k) qc[k] = qv[k];
-    const double h0 = E.nld + E.logdet + half_sq_norm<Q>(pc);
-    double h1 = h0;
-    for (int s = 0; s < a.n_step && st == MLB_ST_OK; ++s) {
-      int f, r;
-      st = leapfrog_step<M, SOLVER>(P, qc, pc, E, dti, o, f, r);
-      s_its += f + r;
-      if (st == MLB_ST_OK) {
-        s_steps += 1;
-        h1 = E.nld + E.logdet + half_sq_norm<Q>(pc);
-        if (fabs(h1 - h0) > a.max_delta_h) st = MLB_ST_H_DIVERGED;
-      }
-    }
+    const TrajOut t = run_trajectory<M, SOLVER, true, true, kBlock>(
+        P, qc, pc, &commit[0][threadIdx.x], &commit[Q][threadIdx.x], a.n_step, dti, o,
+        a.max_delta_h);
+    const int st = t.status;
+    s_its += t.it_fwd + t.it_rev;
+    s_steps += t.done;
     double a_stat = 0.0;
+    bool accept = false;
     if (st == MLB_ST_OK) {
-      double d = h0 - h1;
+      double d = t.h_init - t.h_last;
       a_stat = (d != d) ? 0.0 : exp(d < 0.0 ? d : 0.0);
-      if (u < a_stat) {
-#pragma unroll
-        for (int k = 0; k < Q; ++k) qv[k] = qc[k];
+      accept = u < a_stat;
+      if (accept) {
+        store_vec<Q>(qc, q, ld, i);
         s_nacc += 1;
       }
     }
@@ -360,8 +352,10 @@ __global__ void __launch_bounds__(kBlock)
     s_hdiv += (st == MLB_ST_H_DIVERGED);
     last = st;
     if (a.trace_accept) a.trace_accept[(int64_t)it * ld + i] = a_stat;
-    if (a.trace_q && (it + 1) % a.trace_every == 0)
-      store_vec<Q>(qv, a.trace_q + (int64_t)((it + 1) / a.trace_every - 1) * Q * ld, ld, i);
+    if (a.trace_q && (it + 1) % a.trace_every == 0) {
+      if (!accept) load_vec<Q>(qc, q, ld, i);
+      store_vec<Q>(qc, a.trace_q + (int64_t)((it + 1) / a.trace_every - 1) * Q * ld, ld, i);
+    }
     if (a.adapt) {  // Mici DualAveragingStepSizeAdapter.update
       ad_iter += 1;
       const double w = 1.0 / (a.a_offset + ad_iter);
@@ -372,7 +366,6 @@ __global__ void __launch_bounds__(kBlock)
       dti = exp(log_eps);
     }
   }
-  store_vec<Q>(qv, q, ld, i);
   if (a.adapt) {
     a.adapt[0 * ld + i] = ad_iter, a.adapt[1 * ld + i] = ad_smooth;
     a.adapt[2 * ld + i] = ad_err, a.adapt[4 * ld + i] = dti;

@@ -21,6 +21,8 @@ struct ToyModel {
   struct Params {
     double sigma, y, k;
   };
+  struct Par {};  // nothing to share between the evaluations at one position
+  static MLB_DEV Par params(const double, const double) { return Par{}; }
 
   static MLB_DEV void constr(const Params& P, const double (&q)[Q], double (&c)[Y]) {
     double t0 = q[0] * q[0];
@@ -34,14 +36,18 @@ struct ToyModel {
     J.dv[0] = 0.0;
     J.dn[0] = P.sigma;
   }
-  static MLB_DEV double nld(const Params&, const double (&q)[Q], double (&g)[Q]) {
+  static MLB_DEV void jacob(const Params& P, const double (&q)[Q], const Par&, B::Jac& J,
+                            double (&c)[Y]) {
+    jacob(P, q, J, c);
+  }
+  static MLB_DEV double nld(const Params&, const double (&q)[Q], const Par&, double (&g)[Q]) {
     g[0] = q[0], g[1] = q[1], g[2] = q[2];
     return 0.5 * (q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
   }
   // adds d(0.5 log det G)/dq to g
-  static MLB_DEV void add_grad_logdet(const Params& P, const double (&q)[Q], const B::Jac& J,
-                                      const B::Gram& G, double (&g)[Q]) {
-    double rg = 1.0 / (G.chol[0][0] * G.chol[0][0]);
+  static MLB_DEV void add_grad_logdet(const Params& P, const double (&q)[Q], const Par&,
+                                      const B::Jac& J, const B::Gram& G, double (&g)[Q]) {
+    double rg = G.rdiag[0] * G.rdiag[0];
     g[0] += J.du[0][0] * P.k * (12.0 * q[0] * q[0] - 1.0) * rg;
     g[1] += J.du[0][1] * 2.0 * rg;
   }
@@ -93,7 +99,10 @@ struct HierModel {
   }
   static MLB_DEV void jacob(const Params& P, const double (&q)[Q], typename B::Jac& J,
                             double (&c)[Y]) {
-    Par p = params(q[0], q[1]);
+    jacob(P, q, params(q[0], q[1]), J, c);
+  }
+  static MLB_DEV void jacob(const Params& P, const double (&q)[Q], const Par& p,
+                            typename B::Jac& J, double (&c)[Y]) {
 #pragma unroll
     for (int i = 0; i < Y; ++i) {
       c[i] = fma(p.tau, q[2 + i], p.mu) + fma(P.sigma[i], q[2 + Y + i], -P.y_obs[i]);
@@ -104,17 +113,18 @@ struct HierModel {
     }
   }
   // extended prior nld (eight_schools.py:49-53) with gradient
-  static MLB_DEV double nld(const Params&, const double (&q)[Q], double (&g)[Q]) {
+  static MLB_DEV double nld(const Params&, const double (&q)[Q], const Par& p,
+                            double (&g)[Q]) {
     double val;
     if (PARAM == MLB_PARAM_UNBOUNDED) {
       // normal(0,5) on u0; half-Cauchy(5) pulled back through tau = exp(u1):
-      // log1p((tau/5)^2) - log(d tau/d u1)   (distributions.py:78-80, 449-450)
-      double tau = exp(q[1]);
-      double r = tau / 5.0, r2 = r * r;
-      double s = q[0] / 5.0;
-      val = s * s / 2.0 + log1p(r2) - log(tau);
-      g[0] = q[0] / 25.0;
-      g[1] = 2.0 * r2 / (1.0 + r2) - 1.0;
+      // log1p((tau/5)^2) - log(d tau/d u1)   (distributions.py:78-80, 449-450), and
+      // log(d tau / d u1) = log(exp(u1)) = u1
+      double r = p.tau * 0.2, r2 = r * r;
+      double s = q[0] * 0.2;
+      val = 0.5 * s * s + log1p(r2) - q[1];
+      g[0] = q[0] * 0.04;
+      g[1] = fma(2.0 * r2, rcp_fast(1.0 + r2), -1.0);
     } else {
       val = 0.5 * q[0] * q[0] + 0.5 * q[1] * q[1];
       g[0] = q[0], g[1] = q[1];
@@ -127,20 +137,19 @@ struct HierModel {
       g[2 + i] = q[2 + i];
       g[2 + Y + i] = q[2 + Y + i];
     }
-    return val + s / 2.0 + t / 2.0;
+    return val + 0.5 * (s + t);
   }
   // d(0.5 log det G) = sum_ia B_ia dA_ia + 0.5 sum_i (G^-1)_ii dD_i with B = G^-1 A
   // = D^-1 A C^-1 (Woodbury).  Only mu(u0), tau(u1) have second derivatives.
-  static MLB_DEV void add_grad_logdet(const Params&, const double (&q)[Q],
+  static MLB_DEV void add_grad_logdet(const Params&, const double (&q)[Q], const Par& p,
                                       const typename B::Jac& J, const typename B::Gram& G,
                                       double (&g)[Q]) {
     static_assert(!B::DENSE, "hierarchical model needs dim_y > dim_u");
-    Par p = params(q[0], q[1]);
     double s0 = 0.0, s1 = 0.0, sd = 0.0;
 #pragma unroll
     for (int i = 0; i < Y; ++i) {
       double x[2] = {J.du[i][0], J.du[i][1]};
-      chol_solve<2>(G.chol, x);
+      chol_solve<2>(G.chol, G.rdiag, x);
       double b0 = x[0] * G.rd[i], b1 = x[1] * G.rd[i];
       double gii = G.rd[i] - (J.du[i][0] * x[0] + J.du[i][1] * x[1]) * (G.rd[i] * G.rd[i]);
       s0 += b0;

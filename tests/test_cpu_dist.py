@@ -45,8 +45,8 @@ def _worker(rank, world, port, n_total, q):
         "gathered": par.all_gather_chains(x[:, :3]).numpy(),
     }  # fmt: skip
     # the step-size finalisation reduction (adapters.DualAveragingStepSizeAdapter.finalize)
-    log_eps = torch.log(torch.linspace(0.1, 0.2, n_total))[first : first + count]
-    tot = torch.stack([torch.exp(log_eps).sum(), torch.tensor(float(count))])
+    log_eps = torch.log(torch.linspace(0.1, 0.2, n_total, dtype=torch.float64))[first : first + count]
+    tot = torch.stack([torch.exp(log_eps).sum(), torch.tensor(float(count), dtype=torch.float64)])
     par.all_reduce_sum_(tot)
     res["step_size"] = float(tot[0] / tot[1])
     q.put((rank, res))
@@ -128,4 +128,4 @@ def test_two_rank_reductions_match_single_process():
             assert abs(s[k] - s1[k]) < 1e-9 * max(1.0, abs(s1[k])), k
         assert got[r]["counts"] == {"failed": 3.0, "steps": 20.0}
         assert np.array_equal(got[r]["gathered"], x[:, :3].numpy())
-        assert abs(got[r]["step_size"] - float(torch.linspace(0.1, 0.2, n_total).mean())) < 1e-14
+        assert abs(got[r]["step_size"] - float(torch.linspace(0.1, 0.2, n_total, dtype=torch.float64).mean())) < 1e-14
