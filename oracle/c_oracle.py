@@ -96,6 +96,14 @@ class OracleModel:
         par = PARAM_NORMAL if parametrization == "normal" else PARAM_UNBOUNDED
         return cls(MODEL_HIER, y_obs.size, par, np.concatenate([y_obs, sigma]))
 
+    @classmethod
+    def fn(cls, y_obs, t_seq, dt, parametrization="unbounded"):
+        """FitzHugh-Nagumo: the static RK4 step schedule (reference ode.py:45-53) is
+        computed here on the host and passed as data."""
+        data, _ = fn_model_data(y_obs, t_seq, dt)
+        par = PARAM_NORMAL if parametrization == "normal" else PARAM_UNBOUNDED
+        return cls(MODEL_FN, int(np.asarray(y_obs).size), par, data)
+
     def __del__(self):
         try:
             lib().orc_model_destroy(self.h)
@@ -226,6 +234,29 @@ class OracleModel:
             _p(acc), _p(a_stat), _p(n_done), _p(its), _p(h))  # fmt: skip
         return dict(q=q, status=status, accepted=acc, accept_stat=a_stat, n_done=n_done,
                     iters_total=its, h=h)  # fmt: skip
+
+
+def rk4_schedule(t_seq, dt):
+    """Step sizes and, per output time, the index of the step landing on it (reference
+    mlift/ode.py:45-53 `_compute_dt_seq`)."""
+    t_seq = np.asarray(t_seq, dtype=np.float64)
+    dt = float(np.asarray(dt).reshape(-1)[0])
+    gaps = t_seq[1:] - t_seq[:-1]
+    n_full, rem = np.divmod(gaps, dt)
+    n_full = n_full.astype(np.int64)
+    n_full[rem > 0] += 1
+    last = n_full.cumsum() - 1
+    dt_seq = np.full(last[-1] + 1, dt)
+    dt_seq[last[rem > 0]] = rem[rem > 0]
+    return dt_seq, last
+
+
+def fn_model_data(y_obs, t_seq, dt):
+    """Data blob of the FN model: {n_steps, y_obs[Y], dt_seq[n_steps], obs_step[Y]}."""
+    dt_seq, last = rk4_schedule(t_seq, dt)
+    y_obs = _f(y_obs).ravel()
+    assert last.size == y_obs.size
+    return np.concatenate([[float(dt_seq.size)], y_obs, dt_seq, last.astype(np.float64)]), dt_seq
 
 
 def philox_normals(seed, chain, iteration, n):

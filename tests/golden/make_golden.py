@@ -82,6 +82,73 @@ def autodiff_steps():
         print(name, "done")
 
 
+def fitzhugh_nagumo():
+    """FN fixtures: (i) the arrays of the reference's data file the model needs
+    (data/fitzhugh-nagumo-simulated-data.npz: t_seq, dt, y_mean_obs, n_obs - DATA, read at
+    fitzhugh_nagumo.py:146-149), (ii) autodiff-oracle outputs at two states per
+    parametrisation and one full constrained leapfrog step per solver."""
+    import torch
+    from mlift_oracle import solvers as osolvers
+    from mlift_oracle.mici import ChainState, ConstrainedLeapfrogIntegrator
+    from mlift_oracle.models import FitzHughNagumo
+    from mlift_oracle.systems import IndependentAdditiveNoiseModelSystem
+
+    d = np.load("/root/reference/data/fitzhugh-nagumo-simulated-data.npz")
+    out = {"t_seq": d["t_seq"], "dt": d["dt"], "y_mean_obs": d["y_mean_obs"],
+           "n_obs": d["n_obs"], "obs_noise_std": 0.1}  # fmt: skip
+    y_obs = d["y_mean_obs"] + 0.1 * d["n_obs"]
+    loc = np.array([0, 0, 0, -1, -3, -2, -1.0])
+    u_true = np.log([3, 1, 3, 1 / 3, 1 / 15, 1 / 15, 0.1])
+    rng = np.random.default_rng(0)
+    for par in ("unbounded", "normal"):
+        m = FitzHughNagumo(y_obs, d["t_seq"], d["dt"], par)
+        osys = IndependentAdditiveNoiseModelSystem(
+            m.generate_y, m.data, m.dim_u, m.extended_prior_neg_log_dens)
+        qs, jac, dn, c, ld, gld, nld, gnld = ([] for _ in range(8))
+        for _ in range(2):
+            u = np.concatenate([u_true - (loc if par == "normal" else 0), [-1, 1]])
+            q = m.lift(u + 0.05 * rng.standard_normal(9))
+            q[9:] += 0.01 * rng.standard_normal(q.size - 9)  # off-manifold: c != 0
+            st = ChainState(q)
+            jb = osys.jacob_constr_blocks(st)
+            qs.append(q), jac.append(np.asarray(jb[0])), dn.append(np.asarray(jb[1]))
+            c.append(np.asarray(osys.constr(st)))
+            ld.append(float(osys.log_det_sqrt_gram(st)))
+            gld.append(np.asarray(osys.grad_log_det_sqrt_gram(st)))
+            nld.append(float(osys.neg_log_dens(st)))
+            gnld.append(np.asarray(osys.grad_neg_log_dens(st)))
+        for k, v in dict(q=qs, dy_du=jac, dy_dn=dn, c=c, logdet=ld, grad_logdet=gld, nld=nld,
+                         grad_nld=gnld).items():  # fmt: skip
+            out[f"{par}_{k}"] = np.array(v)
+        print("fn ops", par, "done")
+        if par != "unbounded":
+            continue
+        q0 = m.lift(np.concatenate([u_true, [-1, 1]]) + 0.02 * rng.standard_normal(9))
+        st0 = ChainState(q0)
+        p0 = rng.standard_normal(q0.size)
+        p0 = np.asarray(osys.project_onto_cotangent_space(torch.as_tensor(p0), st0))
+        out["step_q0"], out["step_p0"], out["step_dt"] = q0, p0, 0.02
+        for sid, fn in ((0, osolvers.solve_projection_onto_manifold_quasi_newton),
+                        (1, osolvers.solve_projection_onto_manifold_newton)):  # fmt: skip
+            integ = ConstrainedLeapfrogIntegrator(
+                osys, 0.02, projection_solver=fn,
+                projection_solver_kwargs=dict(constraint_tol=1e-9, position_tol=1e-8,
+                                              max_iters=50))  # fmt: skip
+            s1 = integ.step(ChainState(q0, p0))
+            out[f"step_q_{sid}"], out[f"step_p_{sid}"] = np.asarray(s1.pos), np.asarray(s1.mom)
+            out[f"step_iters_{sid}"] = np.array(integ.last_iters)
+            out[f"step_h_{sid}"] = float(osys.h(s1))
+            print("fn step solver", sid, integ.last_iters)
+    np.savez(os.path.join(HERE, "fitzhugh_nagumo.npz"),
+             source="data arrays: reference data/fitzhugh-nagumo-simulated-data.npz; "
+                    "outputs: oracle/mlift_oracle autodiff restatement", **out)  # fmt: skip
+
+
 if __name__ == "__main__":
-    notebook_kat()
-    autodiff_steps()
+    which = sys.argv[1:] or ["kat", "steps", "fn"]
+    if "kat" in which:
+        notebook_kat()
+    if "steps" in which:
+        autodiff_steps()
+    if "fn" in which:
+        fitzhugh_nagumo()
