@@ -1,7 +1,7 @@
 // C ABI of libmlb.so (see include/mlb.h): argument checking, model registry, dispatch to
 // the per-model launcher tables compiled in mlb_inst_*.cu, layout helpers and the
 // host-buffer entry point.
-#include "mlb_launch.cuh"
+#include "mlb_stream_launch.cuh"
 
 namespace mlb {
 
@@ -15,15 +15,51 @@ std::atomic<int64_t>& launch_count() {
 }
 
 extern const ModelOps ops_toy, ops_hier4u, ops_hier4n, ops_hier8u, ops_hier8n, ops_hier16u,
-    ops_hier16n;
+    ops_hier16n, ops_fn_u, ops_fn_n;
 
 static const ModelOps* find_ops(int model, int dim_y, int param) {
-  const ModelOps* all[] = {&ops_toy,    &ops_hier4u,  &ops_hier4n, &ops_hier8u,
-                           &ops_hier8n, &ops_hier16u, &ops_hier16n};
+  const ModelOps* all[] = {&ops_toy,    &ops_hier4u,  &ops_hier4n, &ops_hier8u, &ops_hier8n,
+                           &ops_hier16u, &ops_hier16n, &ops_fn_u,   &ops_fn_n};
   for (const ModelOps* o : all)
-    if (o->model == model && o->dim_y == dim_y && (model == MLB_MODEL_TOY || o->param == param))
+    if (o->model == model && (o->dim_y == dim_y || o->dim_y == 0) &&
+        (model == MLB_MODEL_TOY || o->param == param))
       return o;
   return nullptr;
+}
+
+// Device copy of an ODE model's constants: {y_obs[Y], dt_seq[n_steps]} as doubles followed
+// by obs_step[Y] as int32, in one allocation made on first use on the calling thread's
+// current device (one process drives one GPU).
+int ode_data(const mlb_model* m, OdeData* out) {
+  std::lock_guard<std::mutex> lock(m->dev_mutex);
+  int dev = 0;
+  MLB_CUDA_OK(cudaGetDevice(&dev));
+  const int Y = m->Y, ns = m->n_steps;
+  if (m->dev_blob && m->dev_id != dev) {
+    g_err = "an ODE model handle is bound to the device of its first use";
+    return MLB_ERR_ARG;
+  }
+  if (!m->dev_blob) {
+    const size_t nd = (size_t)Y + ns;
+    std::vector<char> host(nd * sizeof(double) + (size_t)Y * sizeof(int));
+    std::memcpy(host.data(), m->data.data() + 1, nd * sizeof(double));
+    int* steps = reinterpret_cast<int*>(host.data() + nd * sizeof(double));
+    for (int i = 0; i < Y; ++i) steps[i] = (int)m->data[1 + nd + i];
+    void* p = nullptr;
+    MLB_CUDA_OK(cudaMalloc(&p, host.size()));
+    cudaError_t e = cudaMemcpy(p, host.data(), host.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      cudaFree(p);
+      g_err = std::string("model constants upload: ") + cudaGetErrorString(e);
+      return MLB_ERR_CUDA;
+    }
+    m->dev_blob = p, m->dev_id = dev;
+  }
+  const double* d = static_cast<const double*>(m->dev_blob);
+  out->y_obs = d, out->dt_seq = d + Y;
+  out->obs_step = reinterpret_cast<const int*>(d + Y + ns);
+  out->Y = Y, out->n_steps = ns;
+  return MLB_OK;
 }
 
 static Opts to_opts(const mlb_solver_opts* s) {
@@ -88,13 +124,23 @@ int64_t mlb_launch_count(void) { return g_launches.load(); }
 int mlb_model_create(const mlb_model_desc* d, mlb_model** out) {
   MLB_ARG(d && out && d->data);
   bool hier = false, dense = false;
-  int U = 0, Y = 0;
+  int U = 0, Y = 0, n_steps = 0;
   if (d->model == MLB_MODEL_TOY) {
     MLB_ARG(d->n_data >= 3 && d->dim_y == 1);
     U = 2, Y = 1, dense = true;
   } else if (d->model == MLB_MODEL_HIER) {
     MLB_ARG(d->n_data >= 2 * d->dim_y && d->dim_y >= 3);
     U = 2, Y = d->dim_y, hier = true;
+  } else if (d->model == MLB_MODEL_FN) {
+    // data = {n_steps, y_obs[Y], dt_seq[n_steps], obs_step[Y]}
+    MLB_ARG(d->dim_y >= 1 && d->n_data >= 1 + d->dim_y);
+    n_steps = (int)d->data[0];
+    MLB_ARG(n_steps >= 1 && d->n_data >= 1 + 2 * d->dim_y + n_steps);
+    for (int i = 0; i < d->dim_y; ++i) {
+      const double st = d->data[1 + d->dim_y + n_steps + i];
+      MLB_ARG(st >= 0 && st < n_steps && (i == 0 || st >= d->data[d->dim_y + n_steps + i]));
+    }
+    U = 9, Y = d->dim_y;
   } else {
     g_err = "model not available in this library build";
     return MLB_ERR_UNSUPPORTED;
@@ -107,7 +153,7 @@ int mlb_model_create(const mlb_model_desc* d, mlb_model** out) {
   mlb_model* m = new mlb_model();
   m->model = d->model, m->dim_y = d->dim_y, m->param = d->parametrization;
   m->data.assign(d->data, d->data + d->n_data);
-  m->U = U, m->Y = Y, m->ops = ops;
+  m->U = U, m->Y = Y, m->ops = ops, m->n_steps = n_steps;
   m->Q = U + (hier ? 2 : 1) * Y;
   m->K = dense ? Y : U;
   m->jac_rows = Y * U + (hier ? 2 : 1) * Y;
@@ -115,7 +161,10 @@ int mlb_model_create(const mlb_model_desc* d, mlb_model** out) {
   *out = m;
   return MLB_OK;
 }
-void mlb_model_destroy(mlb_model* m) { delete m; }
+void mlb_model_destroy(mlb_model* m) {
+  if (m && m->dev_blob) cudaFree(m->dev_blob);
+  delete m;
+}
 int mlb_model_dim_u(const mlb_model* m) { return m->U; }
 int mlb_model_dim_y(const mlb_model* m) { return m->Y; }
 int mlb_model_dim_q(const mlb_model* m) { return m->Q; }

@@ -11,6 +11,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -22,6 +23,11 @@ struct mlb_model {
   int model, dim_y, param, U, Y, Q, jac_rows, gram_rows, K;
   std::vector<double> data;
   const struct mlb::ModelOps* ops;
+  // ODE models: device copy of the constants, uploaded on first use (mlb_api.cu)
+  mutable std::mutex dev_mutex;
+  mutable void* dev_blob = nullptr;
+  mutable int dev_id = -1;
+  int n_steps = 0;
 };
 
 namespace mlb {

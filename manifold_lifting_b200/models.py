@@ -113,3 +113,72 @@ class EightSchoolsModel(ModelSpec):
         x = par["μ"][:, None] + par["τ"][:, None] * v
         n = (self.data["y_obs"][None] - x) / self.data["σ"][None]
         return np.concatenate([u, v, n], -1)
+
+
+def rk4_step_schedule(t_seq, dt):
+    """Static RK4 step schedule of the reference (`_compute_dt_seq`, mlift/ode.py:45-53):
+    between consecutive output times take floor(gap / dt) steps of `dt` plus one shorter
+    step for the remainder.  Returns (dt_seq, index of the step landing on each output)."""
+    t_seq = np.asarray(t_seq, dtype=np.float64)
+    dt = float(np.asarray(dt).reshape(-1)[0])
+    gaps = t_seq[1:] - t_seq[:-1]
+    full_steps, remainders = np.divmod(gaps, dt)
+    full_steps = full_steps.astype(np.int64)
+    full_steps[remainders > 0] += 1
+    last = full_steps.cumsum() - 1
+    dt_seq = np.full(last[-1] + 1, dt)
+    dt_seq[last[remainders > 0]] = remainders[remainders > 0]
+    return dt_seq, last
+
+
+class FitzHughNagumoModel(ModelSpec):
+    """FitzHugh-Nagumo ODE model observed through x0 with additive noise.
+
+    Reference: mlift/example_models/fitzhugh_nagumo.py:20-64 with the fixed-step RK4
+    integrator of mlift/ode.py:9-53.  u = (alpha, beta, gamma, delta, epsilon, zeta, sigma
+    [all log-normal priors, unconstrained through exp], x_init[2] ~ N(0, 1)); dim_u = 9,
+    dim_y = len(y_obs), q = (u, n).  `data` keys as in the reference: y_obs, t_seq, dt.
+    """
+
+    family = "additive"
+    LOC = np.array([0.0, 0.0, 0.0, -1.0, -3.0, -2.0, -1.0])  # fitzhugh_nagumo.py:20-28
+    PARAM_NAMES = ("α", "β", "γ", "δ", "ϵ", "ζ", "σ")
+
+    def __init__(self, y_obs, t_seq, dt, parametrization="unbounded"):
+        y_obs = np.asarray(y_obs, dtype=np.float64).ravel()
+        dt_seq, last = rk4_step_schedule(t_seq, dt)
+        if last.size != y_obs.size:
+            raise ValueError("t_seq must have len(y_obs) + 1 entries")
+        blob = np.concatenate([[float(dt_seq.size)], y_obs, dt_seq, last.astype(np.float64)])
+        super().__init__(_lib.MODEL_FN, y_obs.size, parametrization, blob)
+        self.data = {"y_obs": y_obs, "t_seq": np.asarray(t_seq, dtype=np.float64),
+                     "dt": float(np.asarray(dt).reshape(-1)[0]),
+                     "parametrization": parametrization}  # fmt: skip
+        self.dt_seq = dt_seq
+
+    def generate_params(self, u):
+        """Host-side parameter transform (prior.py:17-55), for initial states / traces."""
+        u = np.asarray(u, dtype=np.float64)
+        off = self.LOC if self.parametrization == "normal" else 0.0
+        par = {k: np.exp(u[..., i] + (off[i] if self.parametrization == "normal" else 0.0))
+               for i, k in enumerate(self.PARAM_NAMES)}  # fmt: skip
+        par["x_init"] = u[..., 7:9]
+        return par
+
+    def lift(self, u):
+        """On-manifold positions q = (u, n) with n = (y_obs - x(u)) / sigma(u)
+        (fitzhugh_nagumo.py:118-120), the ODE solved on the GPU."""
+        import ctypes as C
+
+        import torch
+
+        u = np.atleast_2d(np.asarray(u, dtype=np.float64))
+        n = u.shape[0]
+        q = _lib.to_soa(np.concatenate([u, np.zeros((n, self.dim_y))], 1))
+        c = _lib.soa_empty(n, self.dim_y)
+        pq, ld = _lib.p_soa(q, self.dim_q)
+        _lib.check(_lib.lib().mlb_constr(self.handle, C.c_int64(n), C.c_int64(ld), pq,
+                                         _lib.p_soa(c)[0], _lib.stream_ptr()))  # fmt: skip
+        sigma = torch.as_tensor(self.generate_params(u)["σ"], device="cuda")
+        q[:, self.dim_u :] = -c / sigma[:, None]  # c(u, n=0) = x(u) - y_obs
+        return q

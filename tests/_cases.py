@@ -66,6 +66,34 @@ def tangent_momentum(cm, q, seed=11):
     return p - cm.normal_space_component(jac, gram, p)
 
 
+def fn_data(golden_dir=None):
+    """Reference FN data arrays (committed fixture) -> (fixture, y_obs)."""
+    import os
+
+    golden_dir = golden_dir or os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(golden_dir, "fitzhugh_nagumo.npz"))
+    return g, g["y_mean_obs"] + float(g["obs_noise_std"]) * g["n_obs"]
+
+
+FN_LOC = np.array([0.0, 0.0, 0.0, -1.0, -3.0, -2.0, -1.0])
+FN_U_TRUE = np.concatenate([np.log([3, 1, 3, 1 / 3, 1 / 15, 1 / 15, 0.1]), [-1.0, 1.0]])
+
+
+def fn_states(cm, n, seed=5, par="unbounded", spread=0.05, off_manifold=0.0):
+    """On-manifold FN positions: u = truth + spread * N(0, I), n = (y - x(u)) / sigma(u)
+    (SURVEY 8d config 4), lifted with the CPU oracle."""
+    rng = np.random.default_rng(seed)
+    u = FN_U_TRUE[None] + spread * rng.standard_normal((n, 9))
+    if par == "normal":
+        u[:, :7] -= FN_LOC[None]
+    q = np.concatenate([u, np.zeros((n, cm.Y))], 1)
+    sigma = np.exp(u[:, 6] + (FN_LOC[6] if par == "normal" else 0.0))
+    q[:, 9:] = -cm.constr(q) / sigma[:, None]
+    if off_manifold:
+        q[:, 9:] += off_manifold * rng.standard_normal((n, cm.Y))
+    return q
+
+
 def rel_err(a, b):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b) / (1e-300 + np.maximum(np.abs(b), 1.0))))

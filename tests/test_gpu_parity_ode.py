@@ -1,0 +1,180 @@
+"""GPU parity for the ODE-constrained (FitzHugh-Nagumo) model: CUDA streaming kernels
+through the C ABI vs the C++ oracle (bulk) and vs the committed torch-autodiff fixtures."""
+import numpy as np
+import pytest
+import torch
+
+import c_oracle as co
+from _cases import fn_data, fn_states, rel_err, tangent_momentum
+from test_gpu_parity import same_iters
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def cpu(t):
+    return t.detach().cpu().numpy()
+
+
+def fn_case(par="unbounded"):
+    import manifold_lifting_b200 as mlb
+
+    g, y_obs = fn_data()
+    cm = co.OracleModel.fn(y_obs, g["t_seq"], g["dt"], par)
+    gm = mlb.models.FitzHughNagumoModel(y_obs, g["t_seq"], g["dt"], par)
+    gs = mlb.IndependentAdditiveNoiseModelSystem(gm, gm.data, gm.dim_u)
+    return mlb, g, cm, gm, gs
+
+
+def scaled_err(a, b):
+    """max |a - b| relative to the largest entry of each chain's row (Jacobian rows span
+    ten orders of magnitude; 1e-10 is asked of the vector, not of its smallest entry)."""
+    a, b = np.asarray(a), np.asarray(b)
+    a, b = a.reshape(a.shape[0], -1), b.reshape(b.shape[0], -1)
+    return float((np.abs(a - b).max(1) / np.maximum(np.abs(b).max(1), 1.0)).max())
+
+
+@pytest.mark.parametrize("par", ["unbounded", "normal"])
+def test_fn_individual_ops_match_oracle(par):
+    mlb, g, cm, gm, gs = fn_case(par)
+    assert (gm.dim_u, gm.dim_y, gm.dim_q) == (9, 200, 209)
+    q = fn_states(cm, 70, par=par, off_manifold=0.01)
+    rng = np.random.default_rng(3)
+    assert scaled_err(cpu(gs._constr(q)), cm.constr(q)) < TOL
+    jac, c = gs._jacob_constr_blocks(q)
+    ojac, oc = cm.jacob_constr_blocks(q)
+    assert scaled_err(cpu(c), oc) < TOL
+    assert scaled_err(cpu(jac[0]), ojac[0]) < TOL and rel_err(cpu(jac[1]), ojac[2]) < TOL
+    gram = gs._decompose_gram(jac)
+    ogram = cm.decompose_gram(ojac)
+    assert scaled_err(cpu(gram[0]), ogram[0]) < 1e-9 and rel_err(cpu(gram[1]), ogram[1]) < TOL
+    (val, aux), grad = gs._val_and_grad_log_det_sqrt_gram(q)
+    og, oval = cm.grad_log_det_sqrt_gram(q)
+    assert rel_err(cpu(val), oval) < TOL
+    assert scaled_err(cpu(grad), og) < 1e-9  # second-order sensitivities, cond(C) ~ 1e10
+    val2, _ = gs._log_det_sqrt_gram(q)
+    assert rel_err(cpu(val2), oval) < TOL
+    v = rng.standard_normal((q.shape[0], cm.Q))
+    w = rng.standard_normal((q.shape[0], cm.Y))
+    assert scaled_err(cpu(gs._lmult_by_jacob_constr(jac, v)), cm.lmult_by_jacob_constr(ojac, v)) < TOL
+    assert scaled_err(cpu(gs._rmult_by_jacob_constr(jac, w)), cm.rmult_by_jacob_constr(ojac, w)) < TOL
+    # Woodbury solves are ill-conditioned (cond ~ 1e10): parity to 1e-6 of the vector norm
+    assert scaled_err(cpu(gs._lmult_by_pinv_jacob_constr(jac, gram, w)),
+                      cm.lmult_by_pinv_jacob_constr(ojac, ogram, w)) < 1e-6  # fmt: skip
+    assert scaled_err(cpu(gs._normal_space_component(jac, gram, v)),
+                      cm.normal_space_component(ojac, ogram, v)) < 1e-6  # fmt: skip
+    q2 = q + 1e-3 * rng.standard_normal(q.shape)
+    jac2, _ = gs._jacob_constr_blocks(q2)
+    ojac2, _ = cm.jacob_constr_blocks(q2)
+    assert scaled_err(cpu(gs._lmult_by_inv_jacob_product(jac2, jac, w)),
+                      cm.lmult_by_inv_jacob_product(ojac2, ojac, w)) < 1e-6  # fmt: skip
+    st = mlb.states.ChainState(q)
+    oval, ograd = cm.neg_log_dens(q)
+    assert rel_err(cpu(gs.neg_log_dens(st)), oval) < TOL
+    assert rel_err(cpu(gs.grad_neg_log_dens(st)), ograd) < TOL
+    assert scaled_err(cpu(gs.dh1_dpos(st)), ograd + og) < 1e-9
+
+
+def test_fn_ops_match_autodiff_golden():
+    """Directly against the torch autodiff restatement (reference construction:
+    jacfwd Jacobian, reverse-over-forward gradient of the log-det term)."""
+    for par in ("unbounded", "normal"):
+        mlb, g, cm, gm, gs = fn_case(par)
+        q = g[f"{par}_q"]
+        jac, c = gs._jacob_constr_blocks(q)
+        assert scaled_err(cpu(c), g[f"{par}_c"]) < TOL
+        assert scaled_err(cpu(jac[0]), g[f"{par}_dy_du"]) < TOL
+        (val, _), grad = gs._val_and_grad_log_det_sqrt_gram(q)
+        assert rel_err(cpu(val), g[f"{par}_logdet"]) < TOL
+        assert scaled_err(cpu(grad), g[f"{par}_grad_logdet"]) < 1e-9
+        st = mlb.states.ChainState(q)
+        assert rel_err(cpu(gs.neg_log_dens(st)), g[f"{par}_nld"]) < TOL
+
+
+@pytest.mark.parametrize("solver", [co.SOLVER_QUASI_NEWTON, co.SOLVER_NEWTON, co.SOLVER_NEWTON_LS])
+def test_fn_projection_solvers_match_oracle(solver):
+    mlb, g, cm, gm, gs = fn_case()
+    q = fn_states(cm, 96)
+    p = tangent_momentum(cm, q)
+    dt = 0.02
+    q_try = q + dt * p
+    ref = cm.solve_projection(q_try, q, dt, co.solver_opts(solver))
+    jac, _ = gs._jacob_constr_blocks(q)
+    gram = gs._decompose_gram(jac)
+    q_out, mu, it, ndq, err, n_c, status = gs._solve(
+        solver, q_try, jac, gram, dt, 1e-9, 1e-8, 1e10, 50, "maximum")
+    assert (cpu(status) == ref["status"]).all()
+    same = same_iters(cpu(it), ref["iters"], 0.05)
+    ok = (ref["status"] == 0) & same
+    assert ok.mean() > 0.8
+    assert scaled_err(cpu(q_out)[ok], ref["q"][ok]) < 1e-9
+    assert scaled_err(cpu(mu)[ok], ref["mu"][ok]) < 1e-7
+    assert np.abs(cpu(gs._constr(q_out))[ok]).max() < 1e-8
+
+
+@pytest.mark.parametrize("solver", [co.SOLVER_QUASI_NEWTON, co.SOLVER_NEWTON, co.SOLVER_NEWTON_LS])
+def test_fn_fused_leapfrog_steps_match_oracle(solver):
+    mlb, g, cm, gm, gs = fn_case()
+    q = fn_states(cm, 64)
+    p = tangent_momentum(cm, q)
+    dt, n_step = 0.01, 2
+    ref = cm.leapfrog_steps(q, p, dt, n_step, co.solver_opts(solver))
+    integ = mlb.integrators.ConstrainedLeapfrogIntegrator(
+        gs, dt, projection_solver={v: k for k, v in mlb.solvers.SOLVER_IDS.items()}[solver],
+        projection_solver_kwargs=dict(constraint_tol=1e-9, position_tol=1e-8, max_iters=50))
+    out = integ.steps(mlb.states.ChainState(q, p), n_step)
+    assert (cpu(out.status) == ref["status"]).all()
+    assert (cpu(out.n_done) == ref["n_done"]).all()
+    same = (same_iters(cpu(out.iters_fwd), ref["iters_fwd"], 0.1)
+            & same_iters(cpu(out.iters_rev), ref["iters_rev"], 0.1))
+    ok = (ref["status"] == 0) & same
+    assert ok.mean() > 0.8
+    assert scaled_err(cpu(out.pos)[ok], ref["q"][ok]) < 1e-9
+    assert scaled_err(cpu(out.mom)[ok], ref["p"][ok]) < 1e-6  # cond(C) ~ 1e10 projections
+    assert rel_err(cpu(out.h_init), ref["h_init"]) < TOL
+    assert rel_err(cpu(out.h_final)[ok], ref["h_final"][ok]) < 1e-9
+
+
+def test_fn_step_matches_autodiff_golden():
+    mlb, g, cm, gm, gs = fn_case()
+    for sid, fn in ((0, mlb.jitted_solve_projection_onto_manifold_quasi_newton),
+                    (1, mlb.jitted_solve_projection_onto_manifold_newton)):  # fmt: skip
+        integ = mlb.integrators.ConstrainedLeapfrogIntegrator(
+            gs, float(g["step_dt"]), projection_solver=fn,
+            projection_solver_kwargs=dict(constraint_tol=1e-9, position_tol=1e-8, max_iters=50))
+        out = integ.steps(mlb.states.ChainState(g["step_q0"][None], g["step_p0"][None]), 1,
+                          raise_on_failure=False)  # fmt: skip
+        assert int(out.status[0]) == 0
+        assert (int(out.iters_fwd[0]), int(out.iters_rev[0])) == tuple(g[f"step_iters_{sid}"])
+        assert scaled_err(cpu(out.pos), g[f"step_q_{sid}"][None]) < 1e-9
+        assert scaled_err(cpu(out.mom), g[f"step_p_{sid}"][None]) < 1e-6
+        assert rel_err(cpu(out.h_final), g[f"step_h_{sid}"]) < 1e-9
+
+
+def test_fn_full_size_properties_16384_chains():
+    """BASELINE config 4 at full size: on-manifold after the steps, tangent momentum,
+    bounded energy error, reversibility (properties; the oracle is not run at this size)."""
+    mlb, g, cm, gm, gs = fn_case()
+    n = 16384
+    rng = np.random.default_rng(202101)
+    from _cases import FN_U_TRUE
+
+    u = FN_U_TRUE[None] + 0.1 * rng.standard_normal((n, 9))
+    q = gm.lift(u)
+    assert float(gs._constr(q).abs().max()) < 1e-9
+    st = mlb.states.ChainState(q)
+    st.mom = gs.sample_momentum(st, torch.Generator(device="cuda").manual_seed(1))
+    integ = mlb.integrators.ConstrainedLeapfrogIntegrator(
+        gs, 0.005, projection_solver=mlb.jitted_solve_projection_onto_manifold_newton,
+        projection_solver_kwargs=dict(constraint_tol=1e-9, position_tol=1e-8, max_iters=50))
+    out = integ.steps(st, 2)
+    ok = out.status == 0
+    assert float(ok.double().mean()) > 0.97
+    assert float(gs._constr(out.pos)[ok].abs().max()) < 1e-8
+    dh = (out.h_final - out.h_init)[ok].abs()
+    assert float(dh.median()) < 0.05
+    back = mlb.states.ChainState(out.pos[ok], out.mom[ok], dir=-1)
+    back = integ.steps(back, 2)
+    ok2 = back.status == 0
+    assert float(ok2.double().mean()) > 0.97
+    assert float((back.pos[ok2] - st.pos[ok][ok2]).abs().max()) < 1e-5
