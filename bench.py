@@ -32,16 +32,24 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="mlb", choices=("mlb", "reference"))
-    ap.add_argument("--workload", default="hier", choices=("hier", "toy"))
-    ap.add_argument("--n-chain", type=int, default=65536, help="chains PER GPU")
+    ap.add_argument("--workload", default="hier", choices=("hier", "toy", "fn"))
+    ap.add_argument("--n-chain", type=int, default=0,
+                    help="chains PER GPU (default 65536; 16384 for fn)")  # fmt: skip
     ap.add_argument("--n-school", type=int, default=8)
-    ap.add_argument("--n-step", type=int, default=32, help="leapfrog steps per launch")
-    ap.add_argument("--step-size", type=float, default=0.1)
+    ap.add_argument("--n-step", type=int, default=0,
+                    help="leapfrog steps per launch (default 32; 2 for fn)")  # fmt: skip
+    ap.add_argument("--step-size", type=float, default=0.0,
+                    help="default 0.1 (0.01 for fn)")  # fmt: skip
     ap.add_argument("--solver", default="newton", choices=tuple(SOLVERS))
     ap.add_argument("--cpu-sample-chains", type=int, default=0,
                     help="chains in the bounded CPU sample (0 = auto)")  # fmt: skip
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    fn = a.workload == "fn"
+    a.n_chain = a.n_chain or (16384 if fn else 65536)
+    a.n_step = a.n_step or (2 if fn else 32)
+    a.step_size = a.step_size or (0.01 if fn else 0.1)
+    return a
 
 
 # ------------------------------------------------------------------ workload (host)
@@ -52,6 +60,33 @@ def synthetic_schools(n_school, seed=202101):
     sigma = rng.uniform(9.0, 18.0, n_school)
     y = 4.4 + 3.6 * rng.standard_normal(n_school) + sigma * rng.standard_normal(n_school)
     return y, sigma
+
+
+FN_U_TRUE = np.concatenate([np.log([3.0, 1.0, 3.0, 1 / 3, 1 / 15, 1 / 15, 0.1]), [-1.0, 1.0]])
+
+
+def synthetic_fn_data(seed=202101, n_obs=200, t_end=20.0, dt=0.05, noise_std=0.1):
+    """simulate the FitzHugh-Nagumo ODE at the reference's true
+    parameters (fitzhugh-nagumo-simulated-data.npz metadata) with host RK4 and add
+    N(0, 0.1^2) observation noise."""
+    a, b, g, d, e, z = np.exp(FN_U_TRUE[:6])
+    t_seq = np.linspace(0.0, t_end, n_obs + 1)
+
+    def f(x):
+        return np.array([a * x[0] - b * x[0] ** 3 + g * x[1], -d * x[0] - e * x[1] + z])
+
+    x, xs = FN_U_TRUE[7:9].copy(), []
+    per = int(round((t_seq[1] - t_seq[0]) / dt))
+    for _ in range(n_obs):
+        for _ in range(per):
+            k1 = f(x)
+            k2 = f(x + dt * k1 / 2)
+            k3 = f(x + dt * k2 / 2)
+            k4 = f(x + dt * k3)
+            x = x + dt * (k1 + 2 * k2 + 2 * k3 + k4) / 6
+        xs.append(x[0])
+    rng = np.random.default_rng(seed)
+    return np.array(xs) + noise_std * rng.standard_normal(n_obs), t_seq, dt
 
 
 def make_inputs(args, n_chain, chain0):
@@ -67,6 +102,12 @@ def make_inputs(args, n_chain, chain0):
         x = u[:, :1] + np.exp(u[:, 1:2]) * v
         q = np.concatenate([u, v, (y[None] - x) / sigma[None]], 1)
         data = (y, sigma)
+    elif args.workload == "fn":
+        # u = truth + 0.1 N(0, I); the noise coordinates n = (y - x(u)) / sigma(u) are
+        # filled in by the caller (needs an ODE solve: GPU `lift` / oracle `constr`)
+        data = synthetic_fn_data()
+        u = FN_U_TRUE[None] + 0.1 * rng.standard_normal((n_chain, 9))
+        q = np.concatenate([u, np.zeros((n_chain, data[0].size))], 1)
     else:
         sig = 0.1
         th = rng.standard_normal((n_chain, 2))
@@ -81,6 +122,9 @@ def workload_name(args):
     if args.workload == "hier":
         return (f"eight-schools-shaped hierarchical model (J={args.n_school}, dim_q="
                 f"{2 + 2 * args.n_school}), {args.n_chain} chains per GPU, synthetic data")  # fmt: skip
+    if args.workload == "fn":
+        return (f"FitzHugh-Nagumo ODE model (RK4 dt=0.05, 200 obs, dim_q=209), "
+                f"{args.n_chain} chains per GPU, synthetic observations")  # fmt: skip
     return f"toy 2-D model (sigma=0.1), {args.n_chain} chains per GPU"
 
 
@@ -94,16 +138,20 @@ def cpu_oracle_rate(args, target_seconds=12.0, sample_chains=0):
     import c_oracle as co
 
     cores = co.max_threads()
-    n = sample_chains or 2048 * max(1, cores // 4)
+    n = sample_chains or (16 * cores if args.workload == "fn" else 2048 * max(1, cores // 4))
     data, q, p = make_inputs(args, n, 10**6)
     if args.workload == "hier":
         cm = co.OracleModel.hier(*data)
+    elif args.workload == "fn":
+        cm = co.OracleModel.fn(*data)
+        q[:, 9:] = -cm.constr(q) / np.exp(q[:, 6:7])  # lift onto the manifold
     else:
         cm = co.OracleModel.toy(*data)
     jac, _ = cm.jacob_constr_blocks(q)
     p = p - cm.normal_space_component(jac, cm.decompose_gram(jac), p)
     opts = co.solver_opts(SOLVERS[args.solver])
-    cm.leapfrog_steps(q[: 64 * cores], p[: 64 * cores], args.step_size, 2, opts)  # warm
+    nw = min(n, cores if args.workload == "fn" else 64 * cores)
+    cm.leapfrog_steps(q[:nw], p[:nw], args.step_size, 1, opts)  # warm
     t0 = time.perf_counter()
     r = cm.leapfrog_steps(q, p, args.step_size, args.n_step, opts)
     dt = time.perf_counter() - t0
@@ -235,6 +283,10 @@ def run_mlb(args):
     if args.workload == "hier":
         model = mlb.models.EightSchoolsModel(*data)
         system = mlb.HierarchicalLatentVariableModelSystem(model, model.data, model.dim_u)
+    elif args.workload == "fn":
+        model = mlb.models.FitzHughNagumoModel(*data)
+        system = mlb.IndependentAdditiveNoiseModelSystem(model, model.data, model.dim_u)
+        q_host = model.lift(q_host[:, :9])
     else:
         model = mlb.models.Toy2DModel(*data)
         system = mlb.IndependentAdditiveNoiseModelSystem(model, model.data, model.dim_u)
@@ -359,7 +411,8 @@ def run_mlb(args):
             "roofline": {
                 "bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": ach_tf / fp64_peak if fp64_peak > 0 else None, "traffic": None,
-                "kernel": "k_leapfrog_steps (fused trajectory)",
+                "kernel": ("ks_leapfrog_steps" if args.workload == "fn" else "k_leapfrog_steps")
+                          + " (fused trajectory)",
                 "algorithmic_flops_per_chain_step": flops_step,
                 "peak_source": "DFMA-loop microbenchmark run live in this process "
                                "(MEASURED_PEAKS.json has no fp64 entry)",
@@ -367,7 +420,8 @@ def run_mlb(args):
             "roofline_hbm": {
                 "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ach_gbs / hbm_peak, "traffic": None,
-                "kernel": "k_leapfrog_steps, one step per launch, L2 flushed",
+                "kernel": ("ks_leapfrog_steps" if args.workload == "fn" else "k_leapfrog_steps")
+                          + ", one step per launch, L2 flushed",
                 "algorithmic_bytes_per_chain_step": bytes_step,
                 "ms_per_launch": ms1_mean, "peak_source": hbm_src,
             },

@@ -125,7 +125,7 @@ struct Stream {
     for (int a = 0; a < U; ++a)
 #pragma unroll
       for (int b = 0; b < U; ++b) C.L[a][b] = (a == b) ? 1.0 : 0.0;
-#pragma unroll 1
+#pragma unroll 4
     for (int i = 0; i < Y; ++i) {
       const double dn = jac[U * Y + i], d = dn * dn, rd = rcp_fast(d);
       if (gram) gram[U * U + i] = d;
@@ -169,7 +169,7 @@ struct Stream {
 #pragma unroll
     for (int a = 0; a < U; ++a) s += log(C.L[a][a]);
     double t = 0.0, prev = gram[U * U], lp = log(prev);
-#pragma unroll 1
+#pragma unroll 4
     for (int i = 0; i < Y; ++i) {  // d is constant for scalar-noise models: reuse the log
       const double d = gram[U * U + i];
       if (d != prev) prev = d, lp = log(d);
@@ -182,7 +182,7 @@ struct Stream {
   MLB_DEV static void lmult(int Y, const Col& jac, const Col& v, const Col& out) {
     double vu[U];
     load_u(v, vu);
-#pragma unroll 1
+#pragma unroll 4
     for (int i = 0; i < Y; ++i) {
       double s = jac[U * Y + i] * v[U + i];
 #pragma unroll
@@ -195,7 +195,7 @@ struct Stream {
     double su[U];
 #pragma unroll
     for (int a = 0; a < U; ++a) su[a] = 0.0;
-#pragma unroll 1
+#pragma unroll 4
     for (int i = 0; i < Y; ++i) {
       const double wi = w[i];
 #pragma unroll
@@ -214,7 +214,7 @@ struct Stream {
     double t[U];
 #pragma unroll
     for (int a = 0; a < U; ++a) t[a] = 0.0;
-#pragma unroll 1
+#pragma unroll 4
     for (int i = 0; i < Y; ++i) {
       const double dn = jac[U * Y + i], wr = wx[i] * rcp_fast(dn * dn);
 #pragma unroll
@@ -224,7 +224,7 @@ struct Stream {
     double su[U];
 #pragma unroll
     for (int a = 0; a < U; ++a) su[a] = 0.0;
-#pragma unroll 1
+#pragma unroll 4
     for (int i = 0; i < Y; ++i) {
       const double dn = jac[U * Y + i];
       double s = wx[i];
@@ -259,7 +259,7 @@ struct Stream {
 #pragma unroll
       for (int b = 0; b < U; ++b) mat[a][b] = (a == b) ? 1.0 : 0.0;
     }
-#pragma unroll 1
+#pragma unroll 4
     for (int i = 0; i < Y; ++i) {
       const double rd = rcp_fast(jl[U * Y + i] * jr[U * Y + i]);
       const double wr = w[i] * rd;
@@ -339,7 +339,7 @@ struct Stream {
 #pragma unroll
     for (int a = 0; a < U; ++a) trM += Minv[a][a];
     double gs = (double)Y - ((double)U - trM), half_nn = 0.0;
-#pragma unroll 1
+#pragma unroll 4
     for (int i = 0; i < Y; ++i) {
       const double dn = jac[U * Y + i], rd = rcp_fast(dn * dn), ni = q[U + i];
       double row[U];
@@ -414,14 +414,14 @@ struct Stream {
         // delta = J_prev^T Gram_prev^-1 c
 #pragma unroll
         for (int a = 0; a < U; ++a) s[a] = 0.0;
-#pragma unroll 1
+#pragma unroll 4
         for (int i = 0; i < Y; ++i) {
           const double dn = jp[U * Y + i], cr = c[i] * rcp_fast(dn * dn);
 #pragma unroll
           for (int a = 0; a < U; ++a) s[a] = fma(jp[i * U + a], cr, s[a]);
         }
         chol_solve<U>(Cp.L, Cp.rdiag, s);
-#pragma unroll 1
+#pragma unroll 4
         for (int i = 0; i < Y; ++i) {
           const double x = inv_jacprod_x(Y, i, jp, jp, c[i], s);
 #pragma unroll
@@ -438,7 +438,7 @@ struct Stream {
         }
         if (SOLVER == MLB_SOLVER_NEWTON) {
           r.err = err_here;
-#pragma unroll 1
+#pragma unroll 4
           for (int i = 0; i < Y; ++i) {
             const double x = inv_jacprod_x(Y, i, jt, jp, c[i], s);
 #pragma unroll
@@ -448,7 +448,7 @@ struct Stream {
             nacc = norm_accum(nacc, dni, o.norm);
           }
         } else {  // Newton with backtracking line search (systems.py:272-326)
-#pragma unroll 1
+#pragma unroll 4
           for (int i = 0; i < Y; ++i) {
             const double x = inv_jacprod_x(Y, i, jt, jp, c[i], s);
 #pragma unroll
@@ -467,7 +467,7 @@ struct Stream {
             step *= 0.5;
             j += 1;
           } while (j < o.max_ls && new_err > err_here);
-#pragma unroll 1
+#pragma unroll 4
           for (int i = 0; i < Y; ++i) {
             const double dni = used * dir[i];
             q[U + i] -= dni, mu[U + i] += dni;

@@ -45,10 +45,42 @@ def toy_counts():
     return c
 
 
+def fn_counts(Y, n_steps, U=9, ND=8):
+    """FitzHugh-Nagumo (streaming family).  Per RK4 stage: primal RHS 12 + RK4 update 8;
+    per tangent direction J_f s (8) + forcing (2) + update (8); per second-order pair
+    J_f X (8) + forcing (8) + update (8).  Second-order work is counted ONCE per pair
+    (the kernel recomputes the first-order part once per pair group; that redundancy is
+    not algorithmic work)."""
+    NP = ND * (ND + 1) // 2
+    stage0, stage1, stage2 = 20, 3 + 18 * ND, 24 * NP
+    c = {}
+    c["constr"] = 4 * n_steps * stage0 + 3 * Y
+    c["jacob"] = 4 * n_steps * (stage0 + stage1) + 5 * Y
+    c["second_order"] = 4 * n_steps * (stage0 + stage1 + stage2) + 4 * NP * Y
+    c["decompose"] = Y * (U * (U + 1) + U + 8) + U * U * U // 3 + 20 * U
+    c["inv_gram"] = Y * (2 * U + 8) + 2 * U * U + Y * (2 * U + 8)
+    c["rmult"] = Y * (2 * U + 1)
+    c["lmult"] = Y * (2 * U + 2)
+    c["pinv"] = c["inv_gram"] + c["rmult"]
+    c["project"] = c["lmult"] + c["pinv"] + (U + Y)
+    c["inv_jacprod"] = Y * (2 * U * U + 3 * U + 8) + 2 * U * U * U // 3 + 2 * U * U \
+        + Y * (2 * U + 8)
+    Q = U + Y
+    c["newton_iter"] = c["jacob"] + Y + c["inv_jacprod"] + c["rmult"] + 3 * Q
+    c["quasi_newton_iter"] = c["constr"] + Y + c["pinv"] + 3 * Q
+    c["grad_logdet"] = 2 * U * U * U + Y * (2 * U * U + U + 6) + c["second_order"]
+    c["evaluate"] = c["jacob"] + c["decompose"] + (U + 2) * 30 + 3 * Q + c["grad_logdet"]
+    c["step_fixed"] = 3 * c["project"] + 12 * Q + c["evaluate"]
+    return c
+
+
 def step_flops(model, solver, mean_iters_per_step):
     """Algorithmic flops of one constrained leapfrog step for one chain, given the mean
     number of projection iterations (forward + reverse) per step."""
-    c = toy_counts() if model.model_id == 0 else hier_counts(model.dim_u, model.dim_y)
+    if model.model_id == 2:
+        c = fn_counts(model.dim_y, int(model.dt_seq.size))
+    else:
+        c = toy_counts() if model.model_id == 0 else hier_counts(model.dim_u, model.dim_y)
     per_iter = c["quasi_newton_iter"] if solver in (0, 4) else c["newton_iter"]
     return c["step_fixed"] + mean_iters_per_step * per_iter
 
