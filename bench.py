@@ -169,7 +169,7 @@ def cpu_oracle_rate(args, target_seconds=12.0, sample_chains=0):
     return done / dt, cores, desc, dt
 
 
-def run_reference(args):
+def run_reference(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -196,7 +196,7 @@ def run_reference(args):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }  # fmt: skip
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------ CUDA leg
@@ -256,7 +256,7 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}  # fmt: skip
 
 
-def run_mlb(args):
+def run_mlb(args, emit):
     import torch
     import torch.distributed as dist
 
@@ -436,12 +436,30 @@ def run_mlb(args):
             r, cores, desc, secs = cpu_oracle_rate(args, 12.0, args.cpu_sample_chains)
             line["cpu_baseline"] = {"value": r, "unit": "steps/s", "cores": cores,
                                     "kind": "port", "sample": desc, "seconds": secs}  # fmt: skip
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-if __name__ == "__main__":
+def main():
     a = parse_args()
-    run_reference(a) if a.impl == "reference" else run_mlb(a)
+    # stdout carries exactly ONE JSON line: anything libraries print to fd 1 (e.g. NCCL's
+    # version banner) is diverted to stderr for the duration of the run.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    lines = []
+    emit = lambda obj: lines.append(json.dumps(obj))  # noqa: E731
+    try:
+        run_reference(a, emit) if a.impl == "reference" else run_mlb(a, emit)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for ln in lines:
+        print(ln, flush=True)
+
+
+if __name__ == "__main__":
+    main()

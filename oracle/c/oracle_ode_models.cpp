@@ -1,4 +1,5 @@
-// ODE-constrained models for the CPU oracle: FitzHugh-Nagumo.  TEST INFRASTRUCTURE ONLY.
+// ODE-constrained models for the CPU oracle: FitzHugh-Nagumo, Hodgkin-Huxley.
+// TEST INFRASTRUCTURE ONLY.
 //
 // Restates (paths under /root/reference/mlift/):
 //   * example_models/fitzhugh_nagumo.py:20-58   priors, dx_dt, generate_y
@@ -106,10 +107,32 @@ Jet<N, H> jexp(const Jet<N, H>& x) {
   double e = std::exp(x.v);
   return chain(x, e, e, e);
 }
-inline double operator_value(double x) { return x; }
 template <int N, bool H>
-double operator_value(const Jet<N, H>& x) { return x.v; }
+Jet<N, H> jexpm1(const Jet<N, H>& x) {
+  double e = std::expm1(x.v);
+  return chain(x, e, e + 1.0, e + 1.0);
+}
+template <int N, bool H>
+Jet<N, H> jrecip(const Jet<N, H>& x) {
+  double r = 1.0 / x.v;
+  return chain(x, r, -r * r, 2.0 * r * r * r);
+}
+template <int N, bool H>
+Jet<N, H> operator/(const Jet<N, H>& x, const Jet<N, H>& y) { return x * jrecip(y); }
+template <int N, bool H>
+Jet<N, H> operator+(const Jet<N, H>& x, double c) { Jet<N, H> r = x; r.v += c; return r; }
+template <int N, bool H>
+Jet<N, H> operator+(double c, const Jet<N, H>& x) { return x + c; }
+template <int N, bool H>
+Jet<N, H> operator-(const Jet<N, H>& x, double c) { return x + (-c); }
+template <int N, bool H>
+Jet<N, H> operator-(double c, const Jet<N, H>& x) { return (-x) + c; }
+template <int N, bool H>
+Jet<N, H> operator*(const Jet<N, H>& x, double s) { return s * x; }
+template <int N, bool H>
+Jet<N, H> operator/(double c, const Jet<N, H>& x) { return c * jrecip(x); }
 inline double jexp(double x) { return std::exp(x); }
+inline double jexpm1(double x) { return std::expm1(x); }
 
 // double as the order-0 "jet"
 template <class T>
@@ -276,11 +299,217 @@ struct FnModel : Model {
   }
 };
 
+
+// ------------------------------------------------------------------ Hodgkin-Huxley
+// hh_current_stimulus.py:19-203: 5-state conductance model (v, n, m, h, p) advanced with
+// exponential-Euler steps over t = linspace(0, end_time, n) (`integrate_ode`, :142-178),
+// initialised at the steady state for v = E_leak (:125-139), observed through v at the
+// stimulus window (:189-193).  u = (k_tau_p_1, g_bar_Na, g_bar_K, g_bar_M, g_leak, v_t,
+// sigma): five log-normal parameters, v_t ~ N(-60, 10), sigma log-normal (:19-27).
+// data = {n_steps, y_obs[Y], dt_seq[n_steps], obs_step[Y], stim[n_steps], consts[27]}
+// with consts in the order of HH_CONSTS below (the per-step stimulus current, :117-122, is
+// evaluated on the host from the same comparisons).
+struct HhModel : Model {
+  static constexpr int ND = 6, NC = 27;
+  enum { k_alpha_n_1, k_alpha_n_2, k_alpha_n_3, k_beta_n_1, k_beta_n_2, k_beta_n_3,
+         k_alpha_m_1, k_alpha_m_2, k_alpha_m_3, k_beta_m_1, k_beta_m_2, k_beta_m_3,
+         k_alpha_h_1, k_alpha_h_2, k_alpha_h_3, k_beta_h_1, k_beta_h_2, k_beta_h_3,
+         k_p_infinity_1, k_p_infinity_2, k_tau_p_2, k_tau_p_3, k_tau_p_4, E_Na, E_K, E_leak,
+         c_m };
+  int param, n_steps;
+  std::vector<double> y_obs, dt_seq, stim, K;
+  std::vector<int> obs_step;
+  double loc[7] = {8.0, 4.0, 2.0, -3.0, -3.0, -60.0, 0.0};
+  double scale[7] = {1.0, 1.0, 1.0, 1.0, 1.0, 10.0, 1.0};
+
+  HhModel(int Y_, int param_, const double* d) : param(param_) {
+    family = FAMILY_ADDITIVE, U = 7, Y = Y_, Q = 7 + Y_, dense = false;
+    n_steps = (int)d[0];
+    const double* p = d + 1;
+    y_obs.assign(p, p + Y), p += Y;
+    dt_seq.assign(p, p + n_steps), p += n_steps;
+    for (int i = 0; i < Y; ++i) obs_step.push_back((int)p[i]);
+    p += Y;
+    stim.assign(p, p + n_steps), p += n_steps;
+    K.assign(p, p + NC);
+  }
+
+  template <class T> static T xoe(const T& x) { return x / jexpm1(x); }
+  static double xoe(double x) { return x / std::expm1(x); }
+
+  template <class T>
+  struct Par {
+    T k_tau_p_1, g_Na, g_K, g_M, g_leak, v_t;
+  };
+  template <class T> T alpha_n(const T& v, const Par<T>& p) const {
+    return K[k_alpha_n_1] * xoe(-(v - p.v_t - K[k_alpha_n_2]) / K[k_alpha_n_3]) * K[k_alpha_n_3];
+  }
+  template <class T> T beta_n(const T& v, const Par<T>& p) const {
+    return K[k_beta_n_1] * jexp(-(v - p.v_t - K[k_beta_n_2]) / K[k_beta_n_3]);
+  }
+  template <class T> T alpha_m(const T& v, const Par<T>& p) const {
+    return K[k_alpha_m_1] * xoe(-(v - p.v_t - K[k_alpha_m_2]) / K[k_alpha_m_3]) * K[k_alpha_m_3];
+  }
+  template <class T> T beta_m(const T& v, const Par<T>& p) const {
+    return K[k_beta_m_1] * xoe((v - p.v_t - K[k_beta_m_2]) / K[k_beta_m_3]) * K[k_beta_m_3];
+  }
+  template <class T> T alpha_h(const T& v, const Par<T>& p) const {
+    return K[k_alpha_h_1] * jexp(-(v - p.v_t - K[k_alpha_h_2]) / K[k_alpha_h_3]);
+  }
+  template <class T> T beta_h(const T& v, const Par<T>& p) const {
+    return K[k_beta_h_1] / (jexp(-(v - p.v_t - K[k_beta_h_2]) / K[k_beta_h_3]) + 1.0);
+  }
+  template <class T> T p_inf(const T& v) const {
+    return 1.0 / (1.0 + jexp((-v + K[k_p_infinity_1]) / K[k_p_infinity_2]));
+  }
+  template <class T> T tau_p(const T& v, const Par<T>& p) const {
+    return p.k_tau_p_1 / (K[k_tau_p_2] * jexp((v + K[k_tau_p_3]) / K[k_tau_p_4]) +
+                          jexp(-(v + K[k_tau_p_3]) / K[k_tau_p_4]));
+  }
+
+  static void seed_dir(double&, int) {}
+  template <int N, bool H>
+  static void seed_dir(Jet<N, H>& x, int d) { x.g[d] = 1.0; }
+
+  template <class T>
+  Par<T> params(const double* u) const {
+    T t[6];
+    for (int k = 0; k < 6; ++k) {
+      T uk(u[k]);
+      seed_dir(uk, k);
+      if (k < 5)
+        t[k] = jexp(param == PARAM_NORMAL ? uk + loc[k] : uk);
+      else
+        t[k] = param == PARAM_NORMAL ? loc[k] + scale[k] * uk : uk;
+    }
+    return Par<T>{t[0], t[1], t[2], t[3], t[4], t[5]};
+  }
+  double sigma(const double* u) const {
+    return std::exp(u[6] + (param == PARAM_NORMAL ? loc[6] : 0.0));
+  }
+
+  template <class T, class F>
+  void integrate(const Par<T>& p, F&& obs) const {
+    T v(K[E_leak]);
+    T an = alpha_n(v, p), bn = beta_n(v, p), am = alpha_m(v, p), bm = beta_m(v, p);
+    T ah = alpha_h(v, p), bh = beta_h(v, p);
+    T n = an / (an + bn), m = am / (am + bm), h = ah / (ah + bh), pp = p_inf(v);
+    int next = 0;
+    for (int s = 0; s < n_steps && next < Y; ++s) {
+      const double dt = dt_seq[s];
+      T g_K = p.g_K * ((n * n) * (n * n));
+      T g_Na = p.g_Na * (m * m * m) * h;
+      T g_M = p.g_M * pp;
+      T tau_v = K[c_m] / (g_K + g_Na + g_M + p.g_leak);
+      T v_inf = (g_K * K[E_K] + g_Na * K[E_Na] + g_M * K[E_K] + p.g_leak * K[E_leak] + stim[s]) *
+                tau_v / K[c_m];
+      T v_ = v_inf + (v - v_inf) * jexp(-(dt / tau_v));
+      an = alpha_n(v_, p), bn = beta_n(v_, p), am = alpha_m(v_, p), bm = beta_m(v_, p);
+      ah = alpha_h(v_, p), bh = beta_h(v_, p);
+      T tau_n = 1.0 / (an + bn), n_inf = an / (an + bn);
+      T tau_m = 1.0 / (am + bm), m_inf = am / (am + bm);
+      T tau_h = 1.0 / (ah + bh), h_inf = ah / (ah + bh);
+      n = n_inf + (n - n_inf) * jexp(-(dt / tau_n));
+      m = m_inf + (m - m_inf) * jexp(-(dt / tau_m));
+      h = h_inf + (h - h_inf) * jexp(-(dt / tau_h));
+      T pi = p_inf(v_);
+      pp = pi + (pp - pi) * jexp(-(dt / tau_p(v_, p)));
+      v = v_;
+      while (next < Y && obs_step[next] == s) obs(next++, v);
+    }
+  }
+
+  void constr(const double* q, double* c) const override {
+    const double sg = sigma(q);
+    const double* n = q + 7;
+    integrate<double>(params<double>(q), [&](int i, const double& v) {
+      c[i] = v + sg * n[i] - y_obs[i];
+    });
+  }
+  void jacob(const double* q, double* dy_du, double*, double* dy_dn,
+             double* c) const override {
+    using J1 = Jet<ND, false>;
+    const double sg = sigma(q);
+    const double* n = q + 7;
+    integrate<J1>(params<J1>(q), [&](int i, const J1& v) {
+      c[i] = v.v + sg * n[i] - y_obs[i];
+      for (int d = 0; d < ND; ++d) dy_du[(size_t)i * 7 + d] = v.g[d];
+      dy_du[(size_t)i * 7 + 6] = sg * n[i];
+      dy_dn[i] = sg;
+    });
+  }
+  double nld(const double* q, double* grad) const override {
+    double val = 0.0;
+    for (int k = 0; k < 7; ++k) {
+      double z = param == PARAM_NORMAL ? q[k] : (q[k] - loc[k]) / scale[k];
+      val += z * z / 2.0;
+      if (grad) grad[k] = param == PARAM_NORMAL ? z : z / scale[k];
+    }
+    for (int k = 7; k < Q; ++k) {
+      val += q[k] * q[k] / 2.0;
+      if (grad) grad[k] = q[k];
+    }
+    return val;
+  }
+  void grad_logdet(const double* q, const double* dy_du, const double*, const double* dy_dn,
+                   const double* chol, const double*, double* g) const override {
+    const int Un = 7;
+    const double sg = dy_dn[0];
+    double Minv[49];
+    for (int j = 0; j < Un; ++j) {
+      double col[7];
+      for (int i = 0; i < Un; ++i) col[i] = (i == j) ? 1.0 : 0.0;
+      for (int i = 0; i < Un; ++i) {
+        double t = col[i];
+        for (int k = 0; k < i; ++k) t -= chol[i * Un + k] * col[k];
+        col[i] = t / chol[i * Un + i];
+      }
+      for (int i = Un - 1; i >= 0; --i) {
+        double t = col[i];
+        for (int k = i + 1; k < Un; ++k) t -= chol[k * Un + i] * col[k];
+        col[i] = t / chol[i * Un + i];
+      }
+      for (int i = 0; i < Un; ++i) Minv[i * Un + j] = col[i];
+    }
+    std::vector<double> B((size_t)Y * Un);
+    for (int i = 0; i < Y; ++i)
+      for (int a = 0; a < Un; ++a) {
+        double s = 0.0;
+        for (int k = 0; k < Un; ++k) s += dy_du[(size_t)i * Un + k] * Minv[k * Un + a];
+        B[(size_t)i * Un + a] = s / (sg * sg);
+      }
+    for (int k = 0; k < Q; ++k) g[k] = 0.0;
+    double trM = 0.0;
+    for (int a = 0; a < Un; ++a) trM += Minv[a * Un + a];
+    const double* n = q + 7;
+    double g6 = (double)Y - ((double)Un - trM);
+    for (int i = 0; i < Y; ++i) {
+      g6 += B[(size_t)i * Un + 6] * sg * n[i];
+      g[7 + i] = B[(size_t)i * Un + 6] * sg;
+    }
+    g[6] = g6;
+    using J2 = Jet<ND, true>;
+    integrate<J2>(params<J2>(q), [&](int i, const J2& v) {
+      for (int b = 0; b < ND; ++b) {
+        double s = 0.0;
+        for (int a = 0; a < ND; ++a) s += B[(size_t)i * Un + a] * v.h[J2::idx(a, b)];
+        g[b] += s;
+      }
+    });
+  }
+};
+
+Model* make_hh_model(int dim_y, int param, const double* data, int n_data) {
+  if (n_data < 1) return nullptr;
+  int n_steps = (int)data[0];
+  if (n_steps <= 0 || n_data < 1 + 2 * dim_y + 2 * n_steps + HhModel::NC) return nullptr;
+  return new HhModel(dim_y, param, data);
+}
+
 Model* make_fn_model(int dim_y, int param, const double* data, int n_data) {
   if (n_data < 1 + dim_y) return nullptr;
   int n_steps = (int)data[0];
   if (n_steps <= 0 || n_data < 1 + 2 * dim_y + n_steps) return nullptr;
   return new FnModel(dim_y, param, data);
 }
-Model* make_hh_model(int, int, const double*, int) { return nullptr; }
 }  // namespace orc

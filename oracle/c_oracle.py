@@ -104,6 +104,14 @@ class OracleModel:
         par = PARAM_NORMAL if parametrization == "normal" else PARAM_UNBOUNDED
         return cls(MODEL_FN, int(np.asarray(y_obs).size), par, data)
 
+    @classmethod
+    def hh(cls, y_obs, constants, parametrization="unbounded"):
+        """Hodgkin-Huxley current-stimulus model; `constants` is the dict of the
+        reference's data file (hh_current_stimulus.py:287-292)."""
+        data = hh_model_data(y_obs, constants)
+        par = PARAM_NORMAL if parametrization == "normal" else PARAM_UNBOUNDED
+        return cls(MODEL_HH, int(np.asarray(y_obs).size), par, data)
+
     def __del__(self):
         try:
             lib().orc_model_destroy(self.h)
@@ -257,6 +265,43 @@ def fn_model_data(y_obs, t_seq, dt):
     y_obs = _f(y_obs).ravel()
     assert last.size == y_obs.size
     return np.concatenate([[float(dt_seq.size)], y_obs, dt_seq, last.astype(np.float64)]), dt_seq
+
+
+HH_CONSTS = (
+    "k_alpha_n_1", "k_alpha_n_2", "k_alpha_n_3", "k_beta_n_1", "k_beta_n_2", "k_beta_n_3",
+    "k_alpha_m_1", "k_alpha_m_2", "k_alpha_m_3", "k_beta_m_1", "k_beta_m_2", "k_beta_m_3",
+    "k_alpha_h_1", "k_alpha_h_2", "k_alpha_h_3", "k_beta_h_1", "k_beta_h_2", "k_beta_h_3",
+    "k_p_infinity_1", "k_p_infinity_2", "k_tau_p_2", "k_tau_p_3", "k_tau_p_4", "E_Na", "E_K",
+    "E_leak", "c_m",
+)  # fmt: skip
+
+
+def hh_schedule(constants):
+    """Time grid, per-step stimulus current and observation steps of the reference's
+    `integrate_ode` / `generate_from_model` (hh_current_stimulus.py:117-122, 175-193)."""
+    k = {n: float(np.asarray(constants[n])) for n in
+         ("end_time", "dt", "stimulus_start_time", "stimulus_end_time", "i_stimulus",
+          "observation_interval")}  # fmt: skip
+    n_point = int(k["end_time"] / k["dt"]) + 1
+    t_seq = np.linspace(0, k["end_time"], n_point)
+    t0, dt_seq = t_seq[:-1], t_seq[1:] - t_seq[:-1]
+    stim = np.where((t0 < k["stimulus_start_time"]) | (t0 > k["stimulus_end_time"]), 0.0,
+                    k["i_stimulus"])  # fmt: skip
+    idx = np.arange(n_point)[slice(int(k["stimulus_start_time"] / k["dt"]),
+                                   int(k["stimulus_end_time"] / k["dt"]) + 1,
+                                   int(k["observation_interval"] / k["dt"]))]  # fmt: skip
+    assert idx[0] >= 1, "observing the initial state is not supported"
+    return dt_seq, stim, idx - 1  # x_seq[k] is the state after step k - 1
+
+
+def hh_model_data(y_obs, constants):
+    """{n_steps, y_obs[Y], dt_seq[n_steps], obs_step[Y], stim[n_steps], consts[27]}."""
+    dt_seq, stim, obs_step = hh_schedule(constants)
+    y_obs = _f(y_obs).ravel()
+    assert obs_step.size == y_obs.size
+    consts = np.array([float(np.asarray(constants[n])) for n in HH_CONSTS])
+    return np.concatenate([[float(dt_seq.size)], y_obs, dt_seq, obs_step.astype(np.float64),
+                           stim, consts])  # fmt: skip
 
 
 def philox_normals(seed, chain, iteration, n):
