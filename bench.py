@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-chains", type=int, default=0,
                     help="chains in the bounded CPU sample (0 = auto)")  # fmt: skip
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ess", action="store_true", help="skip the ESS/s leg")
     a = ap.parse_args()
     fn = a.workload == "fn"
     a.n_chain = a.n_chain or (16384 if fn else 65536)
@@ -200,6 +201,118 @@ def run_reference(args, emit):
 
 
 # ------------------------------------------------------------------------ CUDA leg
+
+
+# ------------------------------------------------------------------------ ESS/s leg
+
+ESS_WARM, ESS_MAIN, ESS_N_STEP, ESS_SUBSET, ESS_SEED = 150, 200, 8, 8192, 202101
+
+
+def ess_leg(args, mlb, model, system, q0, rank, world, n, with_cpu):
+    """Second half of BASELINE.json's metric: bulk-ESS per second of the latent parameters
+    under static-trajectory constrained HMC (Mici StaticMetropolisHMC semantics, n_step=8,
+    dual-averaging warm-up to accept rate 0.8), GPU sampler vs the CPU oracle sampler.
+
+    The CPU leg continues the SAME chains (Philox streams are keyed by seed / global chain
+    id / iteration) from the GPU's post-warm-up states, so both legs have identical ESS
+    per chain-iteration and the ESS/s ratio isolates throughput; the max |difference| of
+    the two traces is reported as a sampler-level parity figure.  ESS is estimated on
+    the first ESS_SUBSET chains of each rank and scaled to the chain count."""
+    import torch
+
+    from manifold_lifting_b200 import parallel
+    from manifold_lifting_b200.adapters import DualAveragingStepSizeAdapter
+    from manifold_lifting_b200.integrators import ConstrainedLeapfrogIntegrator
+    from manifold_lifting_b200.samplers import StaticMetropolisHMC
+    from manifold_lifting_b200.solvers import SOLVER_IDS
+
+    solver_fn = {v: k for k, v in SOLVER_IDS.items()}[SOLVERS[args.solver]]
+    integ = ConstrainedLeapfrogIntegrator(
+        system, args.step_size, projection_solver=solver_fn,
+        projection_solver_kwargs=dict(constraint_tol=1e-9, position_tol=1e-8, max_iters=50))
+    sampler = StaticMetropolisHMC(system, integ, n_step=ESS_N_STEP, seed=ESS_SEED)
+    state, _, _ = sampler.sample_chains(ESS_WARM, 0, q0, chain_offset=rank * n,
+                                        adapters=[DualAveragingStepSizeAdapter(0.8, 0.05)])  # fmt: skip
+    eps = float(integ.step_size)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    _, traces, stats = sampler.sample_chains(0, ESS_MAIN, state, chain_offset=rank * n,
+                                             trace_dim=model.dim_u)  # fmt: skip
+    torch.cuda.synchronize()
+    secs = time.perf_counter() - t0
+    t = torch.tensor([secs], dtype=torch.float64, device="cuda")
+    parallel.all_reduce_max_(t)
+    secs = float(t[0])
+    u_tr = traces["pos"]  # [n, ESS_MAIN, dim_u]
+    sub = min(ESS_SUBSET, n)
+    names = ("u0", "u1") if model.dim_u == 2 else tuple(f"u{k}" for k in range(model.dim_u))
+    scale = n * world / (sub * world)
+    ess = {nm: parallel.ess(u_tr[:sub, :, k].contiguous(), "bulk") * scale
+           for k, nm in enumerate(names)}  # fmt: skip
+    rhat = {nm: parallel.rhat(u_tr[:sub, :, k].contiguous(), "rank") for k, nm in enumerate(names)}
+    acc = torch.stack([stats["accept_stat"].sum(), stats["convergence_error"].sum()
+                       + stats["non_reversible_step"].sum()])  # fmt: skip
+    parallel.all_reduce_sum_(acc)
+    out = {
+        "sampler": f"static HMC, n_step={ESS_N_STEP}, {ESS_WARM} warm-up + {ESS_MAIN} main "
+                   f"iterations, dual-averaging target 0.8",
+        "step_size": eps, "accept_stat": float(acc[0]) / (n * world),
+        "integrator_error_rate": float(acc[1]) / (n * world),
+        "seconds_main": secs, "chains": n * world,
+        "ess_bulk": ess, "r_hat": rhat, "ess_per_s": {k: v / secs for k, v in ess.items()},
+        "ess_estimated_on_chains": sub * world,
+    }  # fmt: skip
+    if with_cpu and rank == 0:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import c_oracle as co
+
+        cores = co.max_threads()
+        n_cpu = min(sub, 64 * cores)
+        if args.workload == "hier":
+            cm = co.OracleModel.hier(model.data["y_obs"], model.data["σ"])
+        else:
+            cm = co.OracleModel.toy(model.sigma, model.y, model.coeff)
+        qc = state.pos[:n_cpu].cpu().numpy().copy()
+        opts = co.solver_opts(SOLVERS[args.solver])
+        tr = np.empty((n_cpu, ESS_MAIN, model.dim_u))
+        t0 = time.perf_counter()
+        for it in range(ESS_MAIN):
+            r = cm.hmc_transition(qc, eps, ESS_N_STEP, opts, seed=ESS_SEED, chain0=0,
+                                  iteration=ESS_WARM + it)  # fmt: skip
+            qc = r["q"]
+            tr[:, it] = qc[:, : model.dim_u]
+        csecs = time.perf_counter() - t0
+        tr_t = torch.as_tensor(tr)
+        cess = {nm: float(_single_process_ess(tr_t[:, :, k])) for k, nm in enumerate(names)}
+        gpu_sub = u_tr[:n_cpu].cpu().numpy()
+        same = np.abs(gpu_sub - tr).max(axis=(1, 2)) < 1e-6
+        out["cpu"] = {
+            "chains": n_cpu, "cores": cores, "seconds_main": csecs, "ess_bulk": cess,
+            "ess_per_s": {k: v / csecs for k, v in cess.items()},
+            "same_chains_as_gpu_fraction": float(same.mean()),
+            "max_abs_trace_diff_on_same_chains": float(np.abs(gpu_sub - tr)[same].max()),
+        }
+        out["ess_per_s_ratio_gpu_over_cpu"] = {
+            k: out["ess_per_s"][k] / out["cpu"]["ess_per_s"][k] for k in cess}
+    return out
+
+
+def _single_process_ess(x):
+    """parallel.ess without collectives (the CPU leg runs on rank 0 only)."""
+    from manifold_lifting_b200 import parallel as par
+
+    xs = par._split(x.to(dtype=__import__("torch").float64))
+    n_draw = xs.shape[1]
+    flat = xs.reshape(-1)
+    import torch
+
+    order = torch.argsort(flat, stable=True)
+    ranks = torch.empty_like(flat)
+    ranks[order] = torch.arange(1, flat.numel() + 1, dtype=flat.dtype)
+    z = (ranks - 0.375) / (flat.numel() + 0.25)
+    z = (2.0**0.5) * torch.erfinv(2.0 * z - 1.0)
+    stats, ac = par._sufficient(z.reshape(xs.shape))
+    return par._ess_from(stats, ac, n_draw)
 
 
 class ClockSampler:
@@ -436,6 +549,13 @@ def run_mlb(args, emit):
             r, cores, desc, secs = cpu_oracle_rate(args, 12.0, args.cpu_sample_chains)
             line["cpu_baseline"] = {"value": r, "unit": "steps/s", "cores": cores,
                                     "kind": "port", "sample": desc, "seconds": secs}  # fmt: skip
+    ess = None
+    if not args.no_ess and args.workload in ("hier", "toy"):
+        ess = ess_leg(args, mlb, model, system, q0, rank, world, n,
+                      with_cpu=not args.no_cpu_baseline and world == 1)  # fmt: skip
+    if rank == 0:
+        if ess is not None:
+            line["ess"] = ess
         emit(line)
     if world > 1:
         dist.barrier()

@@ -76,7 +76,15 @@ enum { MLB_NORM_MAX = 0, MLB_NORM_EUCLIDEAN = 1 }; /* solvers.py:6-13 */
 /* Model description.  `data` is a HOST array, copied at creation:
  *   TOY : {sigma, y, coeff}                        (n_data = 3)
  *   HIER: {y_obs[dim_y], sigma[dim_y]}             (n_data = 2*dim_y)
- *   FN  : see mlb_ode.h layout in DESIGN.md        HH: idem                        */
+ *   FN  : {n_steps, y_obs[dim_y], dt_seq[n_steps], obs_step[dim_y]}: the static RK4
+ *         schedule of mlift/ode.py:45-53 and, per observation, the index of the step
+ *         that lands on it (n_data = 1 + 2 dim_y + n_steps)
+ *   HH  : {n_steps, y_obs[dim_y], dt_seq[n_steps], obs_step[dim_y], stim[n_steps],
+ *         consts[27]}: time grid and per-step stimulus current of
+ *         hh_current_stimulus.py:117-122,175-178, then the constants of the reference's
+ *         data file in the order k_alpha_n_1..3, k_beta_n_1..3, k_alpha_m_1..3,
+ *         k_beta_m_1..3, k_alpha_h_1..3, k_beta_h_1..3, k_p_infinity_1..2, k_tau_p_2..4,
+ *         E_Na, E_K, E_leak, c_m                                                     */
 typedef struct mlb_model_desc {
   int32_t model;           /* MLB_MODEL_*                                   */
   int32_t dim_y;           /* number of observations                        */
@@ -218,7 +226,8 @@ typedef struct mlb_adapt_opts {
  * chains are sharded over GPUs; or supplied (`mom_noise` [n_iter][Q][n], `unif`
  * [n_iter][n]) for decision-by-decision parity tests.  `adapt` ([MLB_ADAPT_ROWS][n],
  * NULL = no adaptation) is updated per transition and its row 4 used as the chain's step
- * size.  `trace_q` ([n_iter / trace_every][Q][n], NULL to skip) receives positions,
+ * size.  `trace_q` ([n_iter / trace_every][trace_dim][n], NULL to skip) receives the first
+ * `trace_dim` position components (0 = all Q; the latent parameters u come first),
  * `trace_accept` ([n_iter][n], NULL to skip) per-transition accept_stat,
  * `stats` [MLB_STAT_ROWS][n] is accumulated into (not zeroed). */
 int mlb_hmc_sample(const mlb_model* m, int64_t n, int64_t ld, double* q, double dt,
@@ -226,8 +235,8 @@ int mlb_hmc_sample(const mlb_model* m, int64_t n, int64_t ld, double* q, double 
                    double max_delta_h, uint64_t seed, uint64_t chain0, uint32_t iter0,
                    const double* mom_noise, const double* unif, double* adapt,
                    const mlb_adapt_opts* adapt_opts, double* trace_q, int32_t trace_every,
-                   double* trace_accept, double* stats, int32_t* last_status,
-                   void* stream);
+                   int32_t trace_dim, double* trace_accept, double* stats,
+                   int32_t* last_status, void* stream);
 
 /* Philox streams used above, exposed for tests (host function, host output). */
 void mlb_philox_normals_host(uint64_t seed, uint64_t chain, uint32_t iter, int32_t n,

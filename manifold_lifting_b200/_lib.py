@@ -9,7 +9,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmlb.so")
+# MLB_LIB selects an alternative build of the same library (tuning experiments only)
+LIB_PATH = os.environ.get("MLB_LIB") or os.path.join(_HERE, "libmlb.so")
 
 # --- enums (keep in sync with include/mlb.h)
 MODEL_TOY, MODEL_HIER, MODEL_FN, MODEL_HH = 0, 1, 2, 3

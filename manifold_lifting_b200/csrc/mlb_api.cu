@@ -15,11 +15,12 @@ std::atomic<int64_t>& launch_count() {
 }
 
 extern const ModelOps ops_toy, ops_hier4u, ops_hier4n, ops_hier8u, ops_hier8n, ops_hier16u,
-    ops_hier16n, ops_fn_u, ops_fn_n;
+    ops_hier16n, ops_fn_u, ops_fn_n, ops_hh_u, ops_hh_n;
 
 static const ModelOps* find_ops(int model, int dim_y, int param) {
   const ModelOps* all[] = {&ops_toy,    &ops_hier4u,  &ops_hier4n, &ops_hier8u, &ops_hier8n,
-                           &ops_hier16u, &ops_hier16n, &ops_fn_u,   &ops_fn_n};
+                           &ops_hier16u, &ops_hier16n, &ops_fn_u,   &ops_fn_n,
+                           &ops_hh_u,   &ops_hh_n};
   for (const ModelOps* o : all)
     if (o->model == model && (o->dim_y == dim_y || o->dim_y == 0) &&
         (model == MLB_MODEL_TOY || o->param == param))
@@ -27,24 +28,30 @@ static const ModelOps* find_ops(int model, int dim_y, int param) {
   return nullptr;
 }
 
-// Device copy of an ODE model's constants: {y_obs[Y], dt_seq[n_steps]} as doubles followed
-// by obs_step[Y] as int32, in one allocation made on first use on the calling thread's
-// current device (one process drives one GPU).
+// Device copy of an ODE model's arrays: {y_obs[Y], dt_seq[n_steps], aux[n_steps]?} as
+// doubles followed by obs_step[Y] as int32, in one allocation made on first use on the
+// calling thread's current device (one process drives one GPU).  Host data layout
+// (mlb_model_create): {n_steps, y_obs[Y], dt_seq[n_steps], obs_step[Y] [, aux[n_steps],
+// consts[27]]}.
 int ode_data(const mlb_model* m, OdeData* out) {
   std::lock_guard<std::mutex> lock(m->dev_mutex);
   int dev = 0;
   MLB_CUDA_OK(cudaGetDevice(&dev));
   const int Y = m->Y, ns = m->n_steps;
+  const bool has_aux = m->model == MLB_MODEL_HH;
   if (m->dev_blob && m->dev_id != dev) {
     g_err = "an ODE model handle is bound to the device of its first use";
     return MLB_ERR_ARG;
   }
+  const double* h = m->data.data() + 1;  // y_obs, dt_seq, obs_step, [aux, consts]
+  const size_t nd = (size_t)Y + ns + (has_aux ? ns : 0);
   if (!m->dev_blob) {
-    const size_t nd = (size_t)Y + ns;
     std::vector<char> host(nd * sizeof(double) + (size_t)Y * sizeof(int));
-    std::memcpy(host.data(), m->data.data() + 1, nd * sizeof(double));
+    double* hd = reinterpret_cast<double*>(host.data());
+    std::memcpy(hd, h, ((size_t)Y + ns) * sizeof(double));
+    if (has_aux) std::memcpy(hd + Y + ns, h + 2 * (size_t)Y + ns, (size_t)ns * sizeof(double));
     int* steps = reinterpret_cast<int*>(host.data() + nd * sizeof(double));
-    for (int i = 0; i < Y; ++i) steps[i] = (int)m->data[1 + nd + i];
+    for (int i = 0; i < Y; ++i) steps[i] = (int)h[(size_t)Y + ns + i];
     void* p = nullptr;
     MLB_CUDA_OK(cudaMalloc(&p, host.size()));
     cudaError_t e = cudaMemcpy(p, host.data(), host.size(), cudaMemcpyHostToDevice);
@@ -57,8 +64,20 @@ int ode_data(const mlb_model* m, OdeData* out) {
   }
   const double* d = static_cast<const double*>(m->dev_blob);
   out->y_obs = d, out->dt_seq = d + Y;
-  out->obs_step = reinterpret_cast<const int*>(d + Y + ns);
+  out->aux = has_aux ? d + Y + ns : nullptr;
+  out->obs_step = reinterpret_cast<const int*>(d + nd);
   out->Y = Y, out->n_steps = ns;
+  for (int k = 0; k < kOdeConsts; ++k) out->consts[k] = 0.0;
+  if (m->model == MLB_MODEL_HH) {
+    const double* K = h + 2 * (size_t)Y + 2 * (size_t)ns;
+    for (int k = 0; k < 27; ++k) out->consts[k] = K[k];
+    const int recips[9][2] = {{HH_r_alpha_n_3, HH_k_alpha_n_3}, {HH_r_beta_n_3, HH_k_beta_n_3},
+                              {HH_r_alpha_m_3, HH_k_alpha_m_3}, {HH_r_beta_m_3, HH_k_beta_m_3},
+                              {HH_r_alpha_h_3, HH_k_alpha_h_3}, {HH_r_beta_h_3, HH_k_beta_h_3},
+                              {HH_r_p_infinity_2, HH_k_p_infinity_2},
+                              {HH_r_tau_p_4, HH_k_tau_p_4}, {HH_r_c_m, HH_c_m}};
+    for (auto& r : recips) out->consts[r[0]] = 1.0 / K[r[1]];
+  }
   return MLB_OK;
 }
 
@@ -141,6 +160,16 @@ int mlb_model_create(const mlb_model_desc* d, mlb_model** out) {
       MLB_ARG(st >= 0 && st < n_steps && (i == 0 || st >= d->data[d->dim_y + n_steps + i]));
     }
     U = 9, Y = d->dim_y;
+  } else if (d->model == MLB_MODEL_HH) {
+    // data = {n_steps, y_obs[Y], dt_seq[n_steps], obs_step[Y], stim[n_steps], consts[27]}
+    MLB_ARG(d->dim_y >= 1 && d->n_data >= 1);
+    n_steps = (int)d->data[0];
+    MLB_ARG(n_steps >= 1 && d->n_data >= 1 + 2 * d->dim_y + 2 * n_steps + 27);
+    for (int i = 0; i < d->dim_y; ++i) {
+      const double st = d->data[1 + d->dim_y + n_steps + i];
+      MLB_ARG(st >= 0 && st < n_steps && (i == 0 || st >= d->data[d->dim_y + n_steps + i]));
+    }
+    U = 7, Y = d->dim_y;
   } else {
     g_err = "model not available in this library build";
     return MLB_ERR_UNSUPPORTED;
@@ -300,14 +329,16 @@ int mlb_hmc_sample(const mlb_model* m, int64_t n, int64_t ld, double* q, double 
                    double max_delta_h, uint64_t seed, uint64_t chain0, uint32_t iter0,
                    const double* mom_noise, const double* unif, double* adapt,
                    const mlb_adapt_opts* adapt_opts, double* trace_q, int32_t trace_every,
-                   double* trace_accept, double* stats, int32_t* last_status,
-                   void* stream) {
+                   int32_t trace_dim, double* trace_accept, double* stats,
+                   int32_t* last_status, void* stream) {
   MLB_COMMON_ARGS();
   MLB_ARG(q && opts && n_step >= 0 && n_iter >= 0);
   MLB_ARG(!adapt || adapt_opts);
   SampleArgs a;
   a.dt = dt, a.max_delta_h = max_delta_h, a.n_step = n_step, a.n_iter = n_iter;
   a.trace_every = trace_every > 0 ? trace_every : 1;
+  MLB_ARG(trace_dim >= 0 && trace_dim <= m->Q);
+  a.trace_dim = trace_dim > 0 ? trace_dim : m->Q;
   a.seed = seed, a.chain0 = chain0, a.iter0 = iter0;
   a.mom_noise = mom_noise, a.unif = unif, a.adapt = adapt;
   a.a_target = adapt_opts ? adapt_opts->adapt_stat_target : 0.8;

@@ -66,6 +66,9 @@ MLB_DEV void store_vec(const double (&v)[D], double* a, int64_t ld, int64_t i) {
 }
 
 constexpr int kBlock = 64;  // threads per CTA for the heavy per-chain kernels
+#ifndef MLB_LF_MIN_BLOCKS
+#define MLB_LF_MIN_BLOCKS 1  // min resident CTAs per SM asked of the fused kernels
+#endif
 
 #define MLB_CHAIN_INDEX()                                          \
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; \
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(kBlock)
 // ----------------------------------------------------------------- fused drivers
 
 template <class M, int SOLVER>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, MLB_LF_MIN_BLOCKS)
     k_leapfrog_steps(const __grid_constant__ typename M::Params P, int64_t n, int64_t ld,
                      double* q, double* p, double dt, const double* dt_pc, int n_step,
                      Opts o, int32_t* status, int32_t* n_done, int32_t* iters_fwd,
@@ -282,7 +285,7 @@ __global__ void __launch_bounds__(kBlock)
 
 struct SampleArgs {
   double dt, max_delta_h;
-  int n_step, n_iter, trace_every;
+  int n_step, n_iter, trace_every, trace_dim;
   uint64_t seed, chain0;
   uint32_t iter0;
   const double* mom_noise;
@@ -296,7 +299,7 @@ struct SampleArgs {
 };
 
 template <class M, int SOLVER>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, MLB_LF_MIN_BLOCKS)
     k_hmc_sample(const __grid_constant__ typename M::Params P, int64_t n, int64_t ld,
                  double* q, Opts o, SampleArgs a) {
   constexpr int Q = M::Q;
@@ -360,7 +363,10 @@ __global__ void __launch_bounds__(kBlock)
     if (a.trace_accept) a.trace_accept[(int64_t)it * ld + i] = a_stat;
     if (a.trace_q && (it + 1) % a.trace_every == 0) {
       if (!accept) load_vec<Q>(qc, q, ld, i);
-      store_vec<Q>(qc, a.trace_q + (int64_t)((it + 1) / a.trace_every - 1) * Q * ld, ld, i);
+      double* tq = a.trace_q + (int64_t)((it + 1) / a.trace_every - 1) * a.trace_dim * ld + i;
+#pragma unroll
+      for (int k = 0; k < Q; ++k)
+        if (k < a.trace_dim) tq[(int64_t)k * ld] = qc[k];
     }
     if (a.adapt) {  // Mici DualAveragingStepSizeAdapter.update
       ad_iter += 1;

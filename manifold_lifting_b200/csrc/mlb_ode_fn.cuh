@@ -16,17 +16,9 @@
 #pragma once
 #include <utility>
 
-#include "mlb_common.cuh"
+#include "mlb_ode.cuh"
 
 namespace mlb {
-
-// Device-resident constants of an ODE model (uploaded once per model handle).
-struct OdeData {
-  const double* y_obs;   // [Y]
-  const double* dt_seq;  // [n_steps] RK4 step sizes
-  const int* obs_step;   // [Y] index of the step whose end point is observation i
-  int Y, n_steps;
-};
 
 template <int PARAM>
 struct FnOde {

@@ -17,6 +17,7 @@
 #pragma once
 #include "mlb_chmc.cuh"
 #include "mlb_ode_fn.cuh"
+#include "mlb_ode_hh.cuh"
 
 namespace mlb {
 

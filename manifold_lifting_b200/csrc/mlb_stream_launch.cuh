@@ -23,7 +23,7 @@ MLB_DEV Col col(const double* p, int64_t ld, int64_t i) {
 
 template <class M>
 __global__ void __launch_bounds__(kStreamBlock)
-    ks_constr(OdeData D, int64_t n, int64_t ld, const double* q, double* c) {
+    ks_constr(const __grid_constant__ OdeData D, int64_t n, int64_t ld, const double* q, double* c) {
   MLB_STREAM_INDEX();
   const Col qc = col(q, ld, i);
   double u[M::U];
@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(kStreamBlock)
 
 template <class M>
 __global__ void __launch_bounds__(kStreamBlock)
-    ks_jacob(OdeData D, int64_t n, int64_t ld, const double* q, double* jac, double* c) {
+    ks_jacob(const __grid_constant__ OdeData D, int64_t n, int64_t ld, const double* q, double* jac, double* c) {
   MLB_STREAM_INDEX();
   Stream<M>::jacob(D, col(q, ld, i), col(jac, ld, i), col(c, ld, i), MLB_NORM_MAX);
 }
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(kStreamBlock)
 // scratch: [jac_rows + gram_rows + Q + U*Y][lds]
 template <class M>
 __global__ void __launch_bounds__(kStreamBlock)
-    ks_logdet(OdeData D, int64_t n, int64_t ld, const double* q, double* val, double* grad,
+    ks_logdet(const __grid_constant__ OdeData D, int64_t n, int64_t ld, const double* q, double* val, double* grad,
               double* c, double* jac, double* gram, double* nld_val, double* nld_grad,
               double* h1, double* dh1, double* scratch, int64_t lds) {
   MLB_STREAM_INDEX();
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(kStreamBlock)
 
 template <class M>
 __global__ void __launch_bounds__(kStreamBlock)
-    ks_nld(OdeData D, int64_t n, int64_t ld, const double* q, double* val, double* grad) {
+    ks_nld(const __grid_constant__ OdeData D, int64_t n, int64_t ld, const double* q, double* val, double* grad) {
   MLB_STREAM_INDEX();
   constexpr int U = M::U;
   const Col qc = col(q, ld, i);
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(kStreamBlock)
 // scratch: [jac_rows + gram_rows + Y][lds]
 template <class M>
 __global__ void __launch_bounds__(kStreamBlock)
-    ks_project_cotangent(OdeData D, int64_t n, int64_t ld, const double* q, double* p,
+    ks_project_cotangent(const __grid_constant__ OdeData D, int64_t n, int64_t ld, const double* q, double* p,
                          double* scratch, int64_t lds) {
   MLB_STREAM_INDEX();
   using S = Stream<M>;
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kStreamBlock)
 // scratch: [jac_rows + 2 Y + Q][lds]  (Jt, c, dir, mu)
 template <class M, int SOLVER>
 __global__ void __launch_bounds__(kStreamBlock)
-    ks_solve(OdeData D, int64_t n, int64_t ld, const double* q, const double* jac_prev,
+    ks_solve(const __grid_constant__ OdeData D, int64_t n, int64_t ld, const double* q, const double* jac_prev,
              const double* gram_prev, double dt, Opts o, double* q_out, double* mu_out,
              int32_t* iters, double* norm_dq, double* err, int32_t* n_constr,
              int32_t* status, double* scratch, int64_t lds) {
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kStreamBlock)
 // scratch: [StreamScratch::rows][lds]
 template <class M, int SOLVER>
 __global__ void __launch_bounds__(kStreamBlock)
-    ks_leapfrog_steps(OdeData D, int64_t n, int64_t ld, double* q, double* p, double dt,
+    ks_leapfrog_steps(const __grid_constant__ OdeData D, int64_t n, int64_t ld, double* q, double* p, double dt,
                       const double* dt_pc, int n_step, Opts o, int32_t* status,
                       int32_t* n_done, int32_t* iters_fwd, int32_t* iters_rev, double* h_init,
                       double* h_final, double* scratch, int64_t lds) {

@@ -182,3 +182,91 @@ class FitzHughNagumoModel(ModelSpec):
         sigma = torch.as_tensor(self.generate_params(u)["σ"], device="cuda")
         q[:, self.dim_u :] = -c / sigma[:, None]  # c(u, n=0) = x(u) - y_obs
         return q
+
+
+HH_CONSTANT_NAMES = (
+    "k_alpha_n_1", "k_alpha_n_2", "k_alpha_n_3", "k_beta_n_1", "k_beta_n_2", "k_beta_n_3",
+    "k_alpha_m_1", "k_alpha_m_2", "k_alpha_m_3", "k_beta_m_1", "k_beta_m_2", "k_beta_m_3",
+    "k_alpha_h_1", "k_alpha_h_2", "k_alpha_h_3", "k_beta_h_1", "k_beta_h_2", "k_beta_h_3",
+    "k_p_infinity_1", "k_p_infinity_2", "k_tau_p_2", "k_tau_p_3", "k_tau_p_4", "E_Na", "E_K",
+    "E_leak", "c_m",
+)  # fmt: skip
+
+
+def hh_step_schedule(constants):
+    """Time grid, per-step stimulus current and observation steps of the reference's
+    `integrate_ode` / `generate_from_model` (hh_current_stimulus.py:117-122, 175-193):
+    t = linspace(0, end_time, int(end_time / dt) + 1); the stimulus is on unless
+    t < start or t > end; x_seq[start/dt : end/dt + 1 : interval/dt, 0] is observed."""
+    k = {n: float(np.asarray(constants[n])) for n in
+         ("end_time", "dt", "stimulus_start_time", "stimulus_end_time", "i_stimulus",
+          "observation_interval")}  # fmt: skip
+    n_point = int(k["end_time"] / k["dt"]) + 1
+    t_seq = np.linspace(0, k["end_time"], n_point)
+    t0, dt_seq = t_seq[:-1], t_seq[1:] - t_seq[:-1]
+    stim = np.where((t0 < k["stimulus_start_time"]) | (t0 > k["stimulus_end_time"]), 0.0,
+                    k["i_stimulus"])  # fmt: skip
+    idx = np.arange(n_point)[slice(int(k["stimulus_start_time"] / k["dt"]),
+                                   int(k["stimulus_end_time"] / k["dt"]) + 1,
+                                   int(k["observation_interval"] / k["dt"]))]  # fmt: skip
+    if idx[0] < 1:
+        raise ValueError("observing the initial state is not supported")
+    return dt_seq, stim, idx - 1  # x_seq[k] is the state after step k - 1
+
+
+class HodgkinHuxleyModel(ModelSpec):
+    """Hodgkin-Huxley current-stimulus model (5-state conductance model, exponential-Euler
+    steps) observed through the membrane potential with additive noise.
+
+    Reference: mlift/example_models/hh_current_stimulus.py:19-203.  u = (k_tau_p_1,
+    g_bar_Na, g_bar_K, g_bar_M, g_leak, v_t, sigma); dim_u = 7, dim_y = len(y_obs) (1001
+    for the reference's data file).  `constants`: the dict of the reference's
+    `hodgkin-huxley-current-stimulus-data.npz` (rate constants, reversal potentials,
+    stimulus timing, dt, observation_interval).
+    """
+
+    family = "additive"
+    LOC = np.array([8.0, 4.0, 2.0, -3.0, -3.0, -60.0, 0.0])  # hh_current_stimulus.py:19-27
+    SCALE = np.array([1.0, 1.0, 1.0, 1.0, 1.0, 10.0, 1.0])
+    PARAM_NAMES = ("k_tau_p_1", "g_bar_Na", "g_bar_K", "g_bar_M", "g_leak", "v_t", "σ")
+
+    def __init__(self, y_obs, constants, parametrization="unbounded"):
+        y_obs = np.asarray(y_obs, dtype=np.float64).ravel()
+        dt_seq, stim, obs_step = hh_step_schedule(constants)
+        if obs_step.size != y_obs.size:
+            raise ValueError(f"y_obs must have {obs_step.size} entries for these constants")
+        consts = np.array([float(np.asarray(constants[n])) for n in HH_CONSTANT_NAMES])
+        blob = np.concatenate([[float(dt_seq.size)], y_obs, dt_seq,
+                               obs_step.astype(np.float64), stim, consts])  # fmt: skip
+        super().__init__(_lib.MODEL_HH, y_obs.size, parametrization, blob)
+        self.data = {"y_obs": y_obs, "parametrization": parametrization,
+                     **{n: float(np.asarray(constants[n])) for n in HH_CONSTANT_NAMES}}  # fmt: skip
+        self.dt_seq, self.n_steps_used = dt_seq, int(obs_step[-1]) + 1
+
+    def generate_params(self, u):
+        u = np.asarray(u, dtype=np.float64)
+        normal = self.parametrization == "normal"
+        par = {}
+        for i, k in enumerate(self.PARAM_NAMES):
+            if k == "v_t":
+                par[k] = self.LOC[i] + self.SCALE[i] * u[..., i] if normal else u[..., i]
+            else:
+                par[k] = np.exp(u[..., i] + (self.LOC[i] if normal else 0.0))
+        return par
+
+    def lift(self, u):
+        """On-manifold positions q = (u, n), n = (y_obs - x(u)) / sigma(u), ODE on the GPU."""
+        import ctypes as C
+
+        import torch
+
+        u = np.atleast_2d(np.asarray(u, dtype=np.float64))
+        n = u.shape[0]
+        q = _lib.to_soa(np.concatenate([u, np.zeros((n, self.dim_y))], 1))
+        c = _lib.soa_empty(n, self.dim_y)
+        pq, ld = _lib.p_soa(q, self.dim_q)
+        _lib.check(_lib.lib().mlb_constr(self.handle, C.c_int64(n), C.c_int64(ld), pq,
+                                         _lib.p_soa(c)[0], _lib.stream_ptr()))  # fmt: skip
+        sigma = torch.as_tensor(self.generate_params(u)["σ"], device="cuda")
+        q[:, self.dim_u :] = -c / sigma[:, None]
+        return q

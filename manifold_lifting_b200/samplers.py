@@ -41,7 +41,7 @@ class StaticMetropolisHMC:
 
     def _launch(self, q, n_iter, adapt=None, adapt_opts=None, trace_q=None, trace_every=1,
                 trace_accept=None, stats=None, last_status=None, chain_offset=0,
-                mom_noise=None, unif=None):  # fmt: skip
+                mom_noise=None, unif=None, trace_dim=0):  # fmt: skip
         sysm, integ = self.system, self.integrator
         n = q.shape[0]
         opts = integ.solver_opts()
@@ -54,16 +54,17 @@ class StaticMetropolisHMC:
             C.c_double(self.max_delta_h), C.c_uint64(self.seed), C.c_uint64(chain_offset),
             C.c_uint32(self.iteration), p_vec(mom_noise), p_vec(unif), p_vec(adapt),
             None if adapt_opts is None else C.byref(adapt_opts), p_vec(trace_q),
-            C.c_int32(trace_every), p_vec(trace_accept), p_vec(stats),
+            C.c_int32(trace_every), C.c_int32(trace_dim), p_vec(trace_accept), p_vec(stats),
             p_vec(last_status, torch.int32), stream_ptr()))  # fmt: skip
         self.iteration += n_iter
 
     def sample_chains(self, n_warm_up_iter, n_main_iter, init_states, adapters=(),
                       trace_funcs=None, trace_every=1, chain_offset=0,
-                      max_iters_per_launch=None, **unused):  # fmt: skip
+                      max_iters_per_launch=None, trace_dim=None, **unused):  # fmt: skip
         """Returns (final_state, traces, stats).
 
-        traces[name] has shape [n_chain, n_main_iter // trace_every, ...]; stats holds
+        traces[name] has shape [n_chain, n_main_iter // trace_every, ...] (`trace_dim`
+        limits the "pos" trace to the leading components, e.g. dim_u); stats holds
         per-chain means of accept_stat and failure indicators over the main phase
         (names as monitored by the reference, utils.py:335-340)."""
         state = init_states if isinstance(init_states, ChainState) else ChainState(init_states)
@@ -91,7 +92,8 @@ class StaticMetropolisHMC:
         n_trace = n_main_iter // trace_every
         stats = torch.zeros(_lib.STAT_ROWS, n, dtype=torch.float64, device="cuda")
         last = torch.zeros(n, dtype=torch.int32, device="cuda")
-        trace_q = torch.empty(max(n_trace, 1), Q, n, dtype=torch.float64, device="cuda")
+        tdim = Q if not trace_dim else int(trace_dim)
+        trace_q = torch.empty(max(n_trace, 1), tdim, n, dtype=torch.float64, device="cuda")
         chunk = max_iters_per_launch or n_main_iter
         chunk = max(trace_every, (chunk // trace_every) * trace_every)
         done = 0
@@ -100,7 +102,7 @@ class StaticMetropolisHMC:
             tq = trace_q[done // trace_every :] if n_trace > 0 else None
             self._launch(q, k, trace_q=tq if (tq is not None and tq.shape[0] > 0) else None,
                          trace_every=trace_every, stats=stats, last_status=last,
-                         chain_offset=chain_offset)  # fmt: skip
+                         chain_offset=chain_offset, trace_dim=tdim)  # fmt: skip
             done += k
         pos_trace = trace_q[:n_trace].permute(2, 0, 1)  # [n_chain, n_trace, Q] (view)
         traces = {"pos": pos_trace}

@@ -75,6 +75,27 @@ def fn_data(golden_dir=None):
     return g, g["y_mean_obs"] + float(g["obs_noise_std"]) * g["n_obs"]
 
 
+def hh_data(golden_dir=None):
+    """Reference HH constants / observations (committed fixture) -> (fixture, y_obs)."""
+    import os
+
+    golden_dir = golden_dir or os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(golden_dir, "hodgkin_huxley.npz"))
+    return g, g["x_obs"] + float(g["obs_noise_std"]) * g["n_obs"]
+
+
+def hh_states(cm, g, n, seed=5, spread=0.02, off_manifold=0.0):
+    """On-manifold HH positions ("normal" parametrisation): u = u_obs + spread * N(0, I),
+    n = (y - x(u)) / sigma(u), lifted with the CPU oracle."""
+    rng = np.random.default_rng(seed)
+    u = g["u_obs"][None] + spread * rng.standard_normal((n, 7))
+    q = np.concatenate([u, np.zeros((n, cm.Y))], 1)
+    q[:, 7:] = -cm.constr(q) / np.exp(u[:, 6:7])
+    if off_manifold:
+        q[:, 7:] += off_manifold * rng.standard_normal((n, cm.Y))
+    return q
+
+
 FN_LOC = np.array([0.0, 0.0, 0.0, -1.0, -3.0, -2.0, -1.0])
 FN_U_TRUE = np.concatenate([np.log([3, 1, 3, 1 / 3, 1 / 15, 1 / 15, 0.1]), [-1.0, 1.0]])
 

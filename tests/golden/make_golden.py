@@ -144,8 +144,62 @@ def fitzhugh_nagumo():
                     "outputs: oracle/mlift_oracle autodiff restatement", **out)  # fmt: skip
 
 
+def hodgkin_huxley():
+    """HH fixtures: the constants / observations of the reference's data file
+    (data/hodgkin-huxley-current-stimulus-data.npz, read at hh_current_stimulus.py:287-292)
+    and autodiff-oracle outputs at one state in the spiking regime ("normal"
+    parametrisation around the file's `u_obs`) plus one constrained leapfrog step per
+    solver.  ~6 minutes of torch autodiff."""
+    import torch
+    from mlift_oracle import solvers as osolvers
+    from mlift_oracle.mici import ChainState, ConstrainedLeapfrogIntegrator
+    from mlift_oracle.models import HH_CONSTANT_KEYS, HodgkinHuxley
+    from mlift_oracle.systems import IndependentAdditiveNoiseModelSystem
+
+    d = dict(np.load("/root/reference/data/hodgkin-huxley-current-stimulus-data.npz"))
+    out = {k: d[k] for k in HH_CONSTANT_KEYS}
+    out.update(x_obs=d["x_obs"], n_obs=d["n_obs"], u_obs=d["u_obs"], obs_noise_std=1.0)
+    y_obs = d["x_obs"] + 1.0 * d["n_obs"]
+    rng = np.random.default_rng(0)
+    par = "normal"
+    m = HodgkinHuxley(y_obs, d, par)
+    osys = IndependentAdditiveNoiseModelSystem(
+        m.generate_y, m.data, m.dim_u, m.extended_prior_neg_log_dens)
+    q = m.lift(d["u_obs"] + 0.02 * rng.standard_normal(7))
+    q[7:] += 0.01 * rng.standard_normal(q.size - 7)
+    st = ChainState(q)
+    jb = osys.jacob_constr_blocks(st)
+    out.update(q=q, dy_du=np.asarray(jb[0]), dy_dn=np.asarray(jb[1]),
+               c=np.asarray(osys.constr(st)), logdet=float(osys.log_det_sqrt_gram(st)),
+               grad_logdet=np.asarray(osys.grad_log_det_sqrt_gram(st)),
+               nld=float(osys.neg_log_dens(st)),
+               grad_nld=np.asarray(osys.grad_neg_log_dens(st)))  # fmt: skip
+    print("hh ops done")
+    q0 = m.lift(d["u_obs"] + 0.01 * rng.standard_normal(7))
+    st0 = ChainState(q0)
+    p0 = rng.standard_normal(q0.size)
+    p0 = np.asarray(osys.project_onto_cotangent_space(torch.as_tensor(p0), st0))
+    out["step_q0"], out["step_p0"], out["step_dt"] = q0, p0, 0.002
+    for sid, fn in ((0, osolvers.solve_projection_onto_manifold_quasi_newton),
+                    (1, osolvers.solve_projection_onto_manifold_newton)):  # fmt: skip
+        integ = ConstrainedLeapfrogIntegrator(
+            osys, 0.002, projection_solver=fn,
+            projection_solver_kwargs=dict(constraint_tol=1e-9, position_tol=1e-8, max_iters=50))
+        s1 = integ.step(ChainState(q0, p0))
+        out[f"step_q_{sid}"], out[f"step_p_{sid}"] = np.asarray(s1.pos), np.asarray(s1.mom)
+        out[f"step_iters_{sid}"] = np.array(integ.last_iters)
+        out[f"step_h_{sid}"] = float(osys.h(s1))
+        print("hh step solver", sid, integ.last_iters)
+    np.savez(os.path.join(HERE, "hodgkin_huxley.npz"),
+             source="constants / x_obs / n_obs / u_obs: reference "
+                    "data/hodgkin-huxley-current-stimulus-data.npz; outputs: "
+                    "oracle/mlift_oracle autodiff restatement", **out)  # fmt: skip
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kat", "steps", "fn"]
+    which = sys.argv[1:] or ["kat", "steps", "fn", "hh"]
+    if "hh" in which:
+        hodgkin_huxley()
     if "kat" in which:
         notebook_kat()
     if "steps" in which:

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 import c_oracle as co
-from _cases import fn_data, fn_states, rel_err, tangent_momentum
+from _cases import fn_data, fn_states, hh_data, hh_states, rel_err, tangent_momentum
 from test_gpu_parity import same_iters
 
 pytestmark = pytest.mark.gpu
@@ -178,3 +178,129 @@ def test_fn_full_size_properties_16384_chains():
     ok2 = back.status == 0
     assert float(ok2.double().mean()) > 0.97
     assert float((back.pos[ok2] - st.pos[ok][ok2]).abs().max()) < 1e-5
+
+
+# ----------------------------------------------------------------- Hodgkin-Huxley
+# The exponential-Euler HH recurrence in the spiking regime amplifies rounding differences
+# (d y / d u up to ~7e4 per unit u, 1200 steps): parity is asserted relative to each
+# vector's largest entry, at 1e-9 for first-order and 1e-7 for second-order quantities.
+
+
+def hh_case(par="normal"):
+    import manifold_lifting_b200 as mlb
+
+    g, y_obs = hh_data()
+    cm = co.OracleModel.hh(y_obs, g, par)
+    gm = mlb.models.HodgkinHuxleyModel(y_obs, g, par)
+    gs = mlb.IndependentAdditiveNoiseModelSystem(gm, gm.data, gm.dim_u)
+    return mlb, g, cm, gm, gs
+
+
+def test_hh_individual_ops_match_oracle():
+    mlb, g, cm, gm, gs = hh_case()
+    assert (gm.dim_u, gm.dim_y, gm.dim_q) == (7, 1001, 1008)
+    q = hh_states(cm, g, 40, off_manifold=0.01)
+    rng = np.random.default_rng(3)
+    assert scaled_err(cpu(gs._constr(q)), cm.constr(q)) < 1e-9
+    jac, c = gs._jacob_constr_blocks(q)
+    ojac, oc = cm.jacob_constr_blocks(q)
+    assert scaled_err(cpu(c), oc) < 1e-9
+    assert scaled_err(cpu(jac[0]), ojac[0]) < 1e-9 and rel_err(cpu(jac[1]), ojac[2]) < TOL
+    gram = gs._decompose_gram(jac)
+    ogram = cm.decompose_gram(ojac)
+    assert scaled_err(cpu(gram[0]), ogram[0]) < 1e-8
+    (val, aux), grad = gs._val_and_grad_log_det_sqrt_gram(q)
+    og, oval = cm.grad_log_det_sqrt_gram(q)
+    assert rel_err(cpu(val), oval) < 1e-9
+    assert scaled_err(cpu(grad), og) < 1e-7
+    v = rng.standard_normal((q.shape[0], cm.Q))
+    w = rng.standard_normal((q.shape[0], cm.Y))
+    assert scaled_err(cpu(gs._lmult_by_jacob_constr(jac, v)), cm.lmult_by_jacob_constr(ojac, v)) < 1e-9
+    assert scaled_err(cpu(gs._rmult_by_jacob_constr(jac, w)), cm.rmult_by_jacob_constr(ojac, w)) < 1e-9
+    assert scaled_err(cpu(gs._normal_space_component(jac, gram, v)),
+                      cm.normal_space_component(ojac, ogram, v)) < 1e-2  # cond ~ 1e12
+    st = mlb.states.ChainState(q)
+    oval, ograd = cm.neg_log_dens(q)
+    assert rel_err(cpu(gs.neg_log_dens(st)), oval) < TOL
+    assert rel_err(cpu(gs.grad_neg_log_dens(st)), ograd) < TOL
+    # unbounded parametrisation: prior location / scale handling of v_t ~ N(-60, 10)
+    mlb, g, cm_u, gm_u, gs_u = hh_case("unbounded")
+    qu = q[:8].copy()
+    qu[:, :7] = qu[:, :7] * gm.SCALE[None] + gm.LOC[None]
+    assert scaled_err(cpu(gs_u._constr(qu)), cm_u.constr(qu)) < 1e-9
+    ov, ogr = cm_u.neg_log_dens(qu)
+    stu = mlb.states.ChainState(qu)
+    assert rel_err(cpu(gs_u.neg_log_dens(stu)), ov) < TOL
+    assert rel_err(cpu(gs_u.grad_neg_log_dens(stu)), ogr) < TOL
+    ju, _ = gs_u._jacob_constr_blocks(qu)
+    oju, _ = cm_u.jacob_constr_blocks(qu)
+    assert scaled_err(cpu(ju[0]), oju[0]) < 1e-9
+
+
+@pytest.mark.parametrize("solver", [co.SOLVER_QUASI_NEWTON, co.SOLVER_NEWTON, co.SOLVER_NEWTON_LS])
+def test_hh_fused_leapfrog_steps_match_oracle(solver):
+    mlb, g, cm, gm, gs = hh_case()
+    q = hh_states(cm, g, 32, spread=0.01)
+    p = tangent_momentum(cm, q)
+    dt, n_step = 0.005, 1
+    ref = cm.leapfrog_steps(q, p, dt, n_step, co.solver_opts(solver))
+    integ = mlb.integrators.ConstrainedLeapfrogIntegrator(
+        gs, dt, projection_solver={v: k for k, v in mlb.solvers.SOLVER_IDS.items()}[solver],
+        projection_solver_kwargs=dict(constraint_tol=1e-9, position_tol=1e-8, max_iters=50))
+    out = integ.steps(mlb.states.ChainState(q, p), n_step)
+    agree = cpu(out.status) == ref["status"]
+    assert agree.mean() > 0.9
+    same = (cpu(out.iters_fwd) == ref["iters_fwd"]) & (cpu(out.iters_rev) == ref["iters_rev"])
+    ok = (ref["status"] == 0) & agree & same
+    assert ok.mean() > 0.6
+    assert scaled_err(cpu(out.pos)[ok], ref["q"][ok]) < 1e-7
+    # cond(I + A^T A / sigma^2) ~ 1e12: the Woodbury cotangent projection reproduces
+    # momenta to ~1e-3 only (see tests/test_cpu_oracle_ode.py::test_hh_step_...)
+    assert scaled_err(cpu(out.mom)[ok], ref["p"][ok]) < 1e-2
+    assert rel_err(cpu(out.h_init), ref["h_init"]) < 1e-9
+    assert rel_err(cpu(out.h_final)[ok], ref["h_final"][ok]) < 1e-7
+    assert np.abs(cpu(gs._constr(out.pos))[ok]).max() < 1e-7
+
+
+def test_hh_full_size_properties_1024_chains():
+    """BASELINE config 5 per-GPU share (8,192 chains over 8 GPUs = 1,024 per GPU)."""
+    mlb, g, cm, gm, gs = hh_case()
+    n = 1024
+    rng = np.random.default_rng(202101)
+    q = gm.lift(g["u_obs"][None] + 0.05 * rng.standard_normal((n, 7)))
+    assert float(gs._constr(q).abs().max()) < 1e-8
+    st = mlb.states.ChainState(q)
+    st.mom = gs.sample_momentum(st, torch.Generator(device="cuda").manual_seed(1))
+    integ = mlb.integrators.ConstrainedLeapfrogIntegrator(
+        gs, 0.002, projection_solver=mlb.jitted_solve_projection_onto_manifold_newton,
+        projection_solver_kwargs=dict(constraint_tol=1e-9, position_tol=1e-8, max_iters=50))
+    out = integ.steps(st, 1)
+    ok = out.status == 0
+    assert float(ok.double().mean()) > 0.9
+    assert float(gs._constr(out.pos)[ok].abs().max()) < 1e-7
+    dh = (out.h_final - out.h_init)[ok].abs()
+    assert float(dh.median()) < 0.5
+
+
+def test_hh_ops_and_step_match_autodiff_golden():
+    mlb, g, cm, gm, gs = hh_case()
+    q = g["q"][None]
+    jac, c = gs._jacob_constr_blocks(q)
+    assert scaled_err(cpu(c), g["c"][None]) < 1e-9
+    assert scaled_err(cpu(jac[0]), g["dy_du"][None]) < 1e-9
+    (val, _), grad = gs._val_and_grad_log_det_sqrt_gram(q)
+    assert rel_err(cpu(val), g["logdet"]) < 1e-9
+    assert scaled_err(cpu(grad), g["grad_logdet"][None]) < 1e-7
+    for sid, fn in ((0, mlb.jitted_solve_projection_onto_manifold_quasi_newton),
+                    (1, mlb.jitted_solve_projection_onto_manifold_newton)):  # fmt: skip
+        integ = mlb.integrators.ConstrainedLeapfrogIntegrator(
+            gs, float(g["step_dt"]), projection_solver=fn,
+            projection_solver_kwargs=dict(constraint_tol=1e-9, position_tol=1e-8, max_iters=50))
+        out = integ.steps(mlb.states.ChainState(g["step_q0"][None], g["step_p0"][None]), 1,
+                          raise_on_failure=False)  # fmt: skip
+        assert int(out.status[0]) == 0
+        want = g[f"step_iters_{sid}"]
+        assert abs(int(out.iters_fwd[0]) - want[0]) <= 1 and abs(int(out.iters_rev[0]) - want[1]) <= 1
+        assert scaled_err(cpu(out.pos), g[f"step_q_{sid}"][None]) < 1e-7
+        assert scaled_err(cpu(out.mom), g[f"step_p_{sid}"][None]) < 1e-2
+        assert rel_err(cpu(out.h_final), g[f"step_h_{sid}"]) < 1e-7
