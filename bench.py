@@ -290,7 +290,11 @@ def ess_leg(args, mlb, model, system, q0, rank, world, n, with_cpu):
             "chains": n_cpu, "cores": cores, "seconds_main": csecs, "ess_bulk": cess,
             "ess_per_s": {k: v / csecs for k, v in cess.items()},
             "same_chains_as_gpu_fraction": float(same.mean()),
-            "max_abs_trace_diff_on_same_chains": float(np.abs(gpu_sub - tr)[same].max()),
+            # chains whose CPU and GPU traces stay within 1e-6 for all iterations (a
+            # borderline accept decision or iteration-count tie makes a chain diverge;
+            # on strongly curved manifolds such as the toy model most eventually do)
+            "max_abs_trace_diff_on_same_chains": (float(np.abs(gpu_sub - tr)[same].max())
+                                                  if same.any() else None),
         }
         out["ess_per_s_ratio_gpu_over_cpu"] = {
             k: out["ess_per_s"][k] / out["cpu"]["ess_per_s"][k] for k in cess}

@@ -192,6 +192,7 @@ int mlb_model_create(const mlb_model_desc* d, mlb_model** out) {
 }
 void mlb_model_destroy(mlb_model* m) {
   if (m && m->dev_blob) cudaFree(m->dev_blob);
+  if (m && m->host_ws) cudaFree(m->host_ws);
   delete m;
 }
 int mlb_model_dim_u(const mlb_model* m) { return m->U; }
@@ -390,8 +391,17 @@ int mlb_leapfrog_steps_host(const mlb_model* m, int64_t n, double* q, double* p,
   const size_t vec_bytes = (size_t)n * Q * sizeof(double);
   // one device allocation: aos staging (2 vec), soa state (2 vec), per-chain outputs
   const size_t out_bytes = (size_t)n * (4 * sizeof(int32_t) + 2 * sizeof(double));
-  char* dev = nullptr;
-  MLB_CUDA_OK(cudaMalloc((void**)&dev, 4 * vec_bytes + out_bytes));
+  // the staging area lives in the model handle and only grows: no cudaMalloc / cudaFree
+  // (both synchronise the device) on the steady-state path.  Calls on one handle are
+  // serialised by its mutex.
+  std::lock_guard<std::mutex> lock(m->dev_mutex);
+  if (m->host_ws_bytes < 4 * vec_bytes + out_bytes) {
+    if (m->host_ws) cudaFree(m->host_ws);
+    m->host_ws = nullptr, m->host_ws_bytes = 0;
+    MLB_CUDA_OK(cudaMalloc(&m->host_ws, 4 * vec_bytes + out_bytes));
+    m->host_ws_bytes = 4 * vec_bytes + out_bytes;
+  }
+  char* dev = static_cast<char*>(m->host_ws);
   double* d_aos_q = (double*)dev;
   double* d_aos_p = d_aos_q + (size_t)n * Q;
   double* d_q = d_aos_p + (size_t)n * Q;
@@ -402,7 +412,7 @@ int mlb_leapfrog_steps_host(const mlb_model* m, int64_t n, double* q, double* p,
   int32_t *d_done = d_status + n, *d_itf = d_done + n, *d_itr = d_itf + n;
   cudaStream_t s = nullptr;
   int rc = MLB_OK;
-  auto fail = [&](int code) { cudaFree(dev); return code; };
+  auto fail = [&](int code) { return code; };
 #define MLB_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { g_err = std::string(#expr) + ": " + cudaGetErrorString(e_); return fail(MLB_ERR_CUDA); } } while (0)
   MLB_TRY(cudaMemcpyAsync(d_aos_q, q, vec_bytes, cudaMemcpyHostToDevice, s));
   MLB_TRY(cudaMemcpyAsync(d_aos_p, p, vec_bytes, cudaMemcpyHostToDevice, s));
@@ -423,7 +433,6 @@ int mlb_leapfrog_steps_host(const mlb_model* m, int64_t n, double* q, double* p,
   if (h_final) MLB_TRY(cudaMemcpyAsync(h_final, d_h1, n * sizeof(double), cudaMemcpyDeviceToHost, s));
   MLB_TRY(cudaStreamSynchronize(s));
 #undef MLB_TRY
-  cudaFree(dev);
   return MLB_OK;
 }
 

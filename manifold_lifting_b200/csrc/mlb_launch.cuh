@@ -28,6 +28,9 @@ struct mlb_model {
   mutable void* dev_blob = nullptr;
   mutable int dev_id = -1;
   int n_steps = 0;
+  // mlb_leapfrog_steps_host: grow-only device staging area (no malloc / free per call)
+  mutable void* host_ws = nullptr;
+  mutable size_t host_ws_bytes = 0;
 };
 
 namespace mlb {

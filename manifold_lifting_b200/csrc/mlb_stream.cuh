@@ -33,7 +33,7 @@ struct Col {
 // Per-chain scratch of the fused drivers, rows of one [rows][ld] allocation.
 struct StreamScratch {
   Col Jc, Jt, Gc, c, w, g, qs, mu, cq, cp, dir;
-  static int64_t rows(int U, int Y) {
+  __host__ __device__ static int64_t rows(int U, int Y) {
     const int Q = U + Y, jac = U * Y + Y, gram = U * U + Y;
     return 2 * (int64_t)jac + gram + 3 * Y + 5 * Q;
   }

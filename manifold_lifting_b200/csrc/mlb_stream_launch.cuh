@@ -220,6 +220,96 @@ __global__ void __launch_bounds__(kStreamBlock)
   if (h_final) h_final[i] = t.h_last;
 }
 
+// scratch: [StreamScratch::rows + 2 Q][lds]  (proposal position / momentum)
+template <class M, int SOLVER>
+__global__ void __launch_bounds__(kStreamBlock)
+    ks_hmc_sample(const __grid_constant__ OdeData D, int64_t n, int64_t ld, double* q, Opts o,
+                  SampleArgs a, double* scratch, int64_t lds) {
+  MLB_STREAM_INDEX();
+  constexpr int U = M::U;
+  const int Q = U + D.Y;
+  const StreamScratch S = StreamScratch::make(scratch, lds, i, U, D.Y);
+  Col sc = col(scratch, lds, i);
+  const Col qc = sc.rows((int)StreamScratch::rows(U, D.Y)), pc = qc.rows(Q);
+  const Col qv = col(q, ld, i);
+  double ad_iter = 0, ad_smooth = 0, ad_err = 0, ad_target = 0, dti = a.dt;
+  if (a.adapt) {
+    ad_iter = a.adapt[0 * ld + i], ad_smooth = a.adapt[1 * ld + i];
+    ad_err = a.adapt[2 * ld + i], ad_target = a.adapt[3 * ld + i];
+    dti = a.adapt[4 * ld + i];
+  }
+  double s_acc = 0, s_nacc = 0, s_conv = 0, s_nonrev = 0, s_hdiv = 0, s_steps = 0, s_its = 0;
+  int last = MLB_ST_OK;
+#pragma unroll 1
+  for (int it = 0; it < a.n_iter; ++it) {
+    if (a.mom_noise) {
+      const double* mn = a.mom_noise + (int64_t)it * Q * ld + i;
+#pragma unroll 1
+      for (int k = 0; k < Q; ++k) pc[k] = mn[(int64_t)k * ld];
+    } else {
+#pragma unroll 1
+      for (int j = 0; 2 * j < Q; ++j) {
+        double n0, n1;
+        philox_normal_pair(a.seed, a.chain0 + (uint64_t)i, a.iter0 + (uint32_t)it,
+                           (uint32_t)j, n0, n1);
+        pc[2 * j] = n0;
+        if (2 * j + 1 < Q) pc[2 * j + 1] = n1;
+      }
+    }
+#pragma unroll 1
+    for (int k = 0; k < Q; ++k) qc[k] = qv[k];
+    const double u = a.unif ? a.unif[(int64_t)it * ld + i]
+                            : philox_uniform(a.seed, a.chain0 + (uint64_t)i,
+                                             a.iter0 + (uint32_t)it);
+    const TrajOut t = Stream<M>::template trajectory<SOLVER, true, true>(
+        D, qc, pc, S, a.n_step, dti, o, a.max_delta_h);
+    const int st = t.status;
+    s_its += t.it_fwd + t.it_rev;
+    s_steps += t.done;
+    double a_stat = 0.0;
+    if (st == MLB_ST_OK) {
+      const double d = t.h_init - t.h_last;
+      a_stat = (d != d) ? 0.0 : exp(d < 0.0 ? d : 0.0);
+      if (u < a_stat) {
+#pragma unroll 1
+        for (int k = 0; k < Q; ++k) qv[k] = qc[k];
+        s_nacc += 1;
+      }
+    }
+    s_acc += a_stat;
+    s_conv += (st == MLB_ST_DIVERGED || st == MLB_ST_NOT_CONVERGED || st == MLB_ST_LINALG);
+    s_nonrev += (st == MLB_ST_NON_REVERSIBLE);
+    s_hdiv += (st == MLB_ST_H_DIVERGED);
+    last = st;
+    if (a.trace_accept) a.trace_accept[(int64_t)it * ld + i] = a_stat;
+    if (a.trace_q && (it + 1) % a.trace_every == 0) {
+      double* tq = a.trace_q + (int64_t)((it + 1) / a.trace_every - 1) * a.trace_dim * ld + i;
+#pragma unroll 1
+      for (int k = 0; k < a.trace_dim; ++k) tq[(int64_t)k * ld] = qv[k];
+    }
+    if (a.adapt) {  // Mici DualAveragingStepSizeAdapter.update
+      ad_iter += 1;
+      const double w = 1.0 / (a.a_offset + ad_iter);
+      ad_err = (1.0 - w) * ad_err + w * (a.a_target - a_stat);
+      const double sw = pow(1.0 / ad_iter, a.a_decay);
+      const double log_eps = ad_target - ad_err * sqrt(ad_iter) / a.a_reg;
+      ad_smooth = (1.0 - sw) * ad_smooth + sw * log_eps;
+      dti = exp(log_eps);
+    }
+  }
+  if (a.adapt) {
+    a.adapt[0 * ld + i] = ad_iter, a.adapt[1 * ld + i] = ad_smooth;
+    a.adapt[2 * ld + i] = ad_err, a.adapt[4 * ld + i] = dti;
+  }
+  if (a.stats) {
+    a.stats[0 * ld + i] += s_acc, a.stats[1 * ld + i] += s_nacc;
+    a.stats[2 * ld + i] += s_conv, a.stats[3 * ld + i] += s_nonrev;
+    a.stats[4 * ld + i] += s_hdiv, a.stats[5 * ld + i] += s_steps;
+    a.stats[6 * ld + i] += s_its;
+  }
+  if (a.last_status) a.last_status[i] = last;
+}
+
 // ----------------------------------------------------------------------- launchers
 
 // device copy of the model constants, uploaded on first use on the current device
@@ -363,10 +453,24 @@ struct StreamLaunch {
     if (solver == MLB_SOLVER_NEWTON) return go.template operator()<MLB_SOLVER_NEWTON>();
     return go.template operator()<MLB_SOLVER_NEWTON_LS>();
   }
-  static int sample(const mlb_model*, int, int64_t, int64_t, double*, const Opts&,
-                    const SampleArgs&, cudaStream_t) {
-    g_err = "mlb_hmc_sample is not built for ODE models yet (use mlb_leapfrog_steps)";
-    return MLB_ERR_UNSUPPORTED;
+  static int sample(const mlb_model* m, int solver, int64_t n, int64_t ld, double* q,
+                    const Opts& o, const SampleArgs& a, cudaStream_t s) {
+    MLB_ODE();
+    if (solver > MLB_SOLVER_NEWTON_LS) {
+      g_err = "Mici's own solvers are not built for ODE models";
+      return MLB_ERR_UNSUPPORTED;
+    }
+    ScratchBuf sb;
+    const int64_t lds = pad32(n);
+    int rc = sb.alloc(StreamScratch::rows(U, Y) + 2 * (int64_t)m->Q, lds, s);
+    if (rc != MLB_OK) return rc;
+    auto go = [&]<int S>() {
+      ks_hmc_sample<M, S><<<sgrid(n), kStreamBlock, 0, s>>>(D, n, ld, q, o, a, sb.p, lds);
+      return finish_launch();
+    };
+    if (solver == MLB_SOLVER_QUASI_NEWTON) return go.template operator()<MLB_SOLVER_QUASI_NEWTON>();
+    if (solver == MLB_SOLVER_NEWTON) return go.template operator()<MLB_SOLVER_NEWTON>();
+    return go.template operator()<MLB_SOLVER_NEWTON_LS>();
   }
 #undef MLB_ODE
 };
