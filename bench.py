@@ -32,7 +32,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="mlb", choices=("mlb", "reference"))
-    ap.add_argument("--workload", default="hier", choices=("hier", "toy", "fn"))
+    ap.add_argument("--workload", default="hier", choices=("hier", "toy", "fn", "hh"))
     ap.add_argument("--n-chain", type=int, default=0,
                     help="chains PER GPU (default 65536; 16384 for fn)")  # fmt: skip
     ap.add_argument("--n-school", type=int, default=8)
@@ -43,13 +43,16 @@ def parse_args():
     ap.add_argument("--solver", default="newton", choices=tuple(SOLVERS))
     ap.add_argument("--cpu-sample-chains", type=int, default=0,
                     help="chains in the bounded CPU sample (0 = auto)")  # fmt: skip
+    ap.add_argument("--single-kernel", action="store_true",
+                    help="ODE workloads: one-thread-per-chain kernel instead of the "
+                         "host-driven sub-phase kernels (MLB_FLAG_SINGLE_KERNEL)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ess", action="store_true", help="skip the ESS/s leg")
     a = ap.parse_args()
-    fn = a.workload == "fn"
-    a.n_chain = a.n_chain or (16384 if fn else 65536)
-    a.n_step = a.n_step or (2 if fn else 32)
-    a.step_size = a.step_size or (0.01 if fn else 0.1)
+    wl = a.workload
+    a.n_chain = a.n_chain or {"fn": 16384, "hh": 1024}.get(wl, 65536)
+    a.n_step = a.n_step or {"fn": 2, "hh": 1}.get(wl, 32)
+    a.step_size = a.step_size or {"fn": 0.01, "hh": 0.002}.get(wl, 0.1)
     return a
 
 
@@ -90,6 +93,23 @@ def synthetic_fn_data(seed=202101, n_obs=200, t_end=20.0, dt=0.05, noise_std=0.1
     return np.array(xs) + noise_std * rng.standard_normal(n_obs), t_seq, dt
 
 
+def hh_constants():
+    """Model constants of the Hodgkin-Huxley workload (rate constants, reversal potentials,
+    stimulus timing) and the reference's nominal latent vector `u_obs` ("normal"
+    parametrisation), from the committed fixture tests/golden/hodgkin_huxley.npz."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hodgkin_huxley.npz"))
+    return {k: g[k] for k in g.files if g[k].ndim == 0 and k not in ("source",)}, g["u_obs"]
+
+
+def synthetic_hh_data(forward, seed=202101, noise_std=1.0):
+    """observations = membrane potential at the nominal parameters
+    (computed by `forward(u)`: the implementation under test solves the ODE) + N(0, 1)."""
+    consts, u_obs = hh_constants()
+    x = forward(consts, u_obs)
+    rng = np.random.default_rng(seed)
+    return x + noise_std * rng.standard_normal(x.size), consts, u_obs
+
+
 def make_inputs(args, n_chain, chain0):
     """On-manifold positions: hier - u ~ moderate prior draws, v ~ N(0, I),
     n = (y - x) / sigma; toy - theta ~ N(0, I) lifted.  Momenta ~ N(0, I) (projected on
@@ -109,6 +129,12 @@ def make_inputs(args, n_chain, chain0):
         data = synthetic_fn_data()
         u = FN_U_TRUE[None] + 0.1 * rng.standard_normal((n_chain, 9))
         q = np.concatenate([u, np.zeros((n_chain, data[0].size))], 1)
+    elif args.workload == "hh":
+        # data and the noise coordinates need ODE solves: filled in by the caller
+        consts, u_obs = hh_constants()
+        data = None
+        q = u_obs[None] + 0.05 * rng.standard_normal((n_chain, 7))
+        q = np.concatenate([q, np.zeros((n_chain, 1001))], 1)
     else:
         sig = 0.1
         th = rng.standard_normal((n_chain, 2))
@@ -126,6 +152,10 @@ def workload_name(args):
     if args.workload == "fn":
         return (f"FitzHugh-Nagumo ODE model (RK4 dt=0.05, 200 obs, dim_q=209), "
                 f"{args.n_chain} chains per GPU, synthetic observations")  # fmt: skip
+    if args.workload == "hh":
+        return (f"Hodgkin-Huxley current-stimulus model (1100 exp-Euler steps, 1001 obs, "
+                f"dim_q=1008, normal parametrisation), {args.n_chain} chains per GPU, "
+                f"synthetic observations")  # fmt: skip
     return f"toy 2-D model (sigma=0.1), {args.n_chain} chains per GPU"
 
 
@@ -139,19 +169,28 @@ def cpu_oracle_rate(args, target_seconds=12.0, sample_chains=0):
     import c_oracle as co
 
     cores = co.max_threads()
-    n = sample_chains or (16 * cores if args.workload == "fn" else 2048 * max(1, cores // 4))
+    n = sample_chains or {"fn": 16 * cores, "hh": 4 * cores}.get(
+        args.workload, 2048 * max(1, cores // 4))
     data, q, p = make_inputs(args, n, 10**6)
     if args.workload == "hier":
         cm = co.OracleModel.hier(*data)
     elif args.workload == "fn":
         cm = co.OracleModel.fn(*data)
         q[:, 9:] = -cm.constr(q) / np.exp(q[:, 6:7])  # lift onto the manifold
+    elif args.workload == "hh":
+        def forward(consts, u):
+            m0 = co.OracleModel.hh(np.zeros(1001), consts, "normal")
+            return m0.constr(np.concatenate([u, np.zeros(1001)])[None])[0]
+
+        y_obs, consts, _ = synthetic_hh_data(forward)
+        cm = co.OracleModel.hh(y_obs, consts, "normal")
+        q[:, 7:] = -cm.constr(q) / np.exp(q[:, 6:7])
     else:
         cm = co.OracleModel.toy(*data)
     jac, _ = cm.jacob_constr_blocks(q)
     p = p - cm.normal_space_component(jac, cm.decompose_gram(jac), p)
     opts = co.solver_opts(SOLVERS[args.solver])
-    nw = min(n, cores if args.workload == "fn" else 64 * cores)
+    nw = min(n, cores if args.workload in ("fn", "hh") else 64 * cores)
     cm.leapfrog_steps(q[:nw], p[:nw], args.step_size, 1, opts)  # warm
     t0 = time.perf_counter()
     r = cm.leapfrog_steps(q, p, args.step_size, args.n_step, opts)
@@ -404,13 +443,23 @@ def run_mlb(args, emit):
         model = mlb.models.FitzHughNagumoModel(*data)
         system = mlb.IndependentAdditiveNoiseModelSystem(model, model.data, model.dim_u)
         q_host = model.lift(q_host[:, :9])
+    elif args.workload == "hh":
+        def forward(consts, u):
+            m0 = mlb.models.HodgkinHuxleyModel(np.zeros(1001), consts, "normal")
+            return -m0.lift(u[None])[0, 7:].cpu().numpy() * np.exp(u[6])
+
+        y_obs, consts, _ = synthetic_hh_data(forward)
+        model = mlb.models.HodgkinHuxleyModel(y_obs, consts, "normal")
+        system = mlb.IndependentAdditiveNoiseModelSystem(model, model.data, model.dim_u)
+        q_host = model.lift(q_host[:, :7])
     else:
         model = mlb.models.Toy2DModel(*data)
         system = mlb.IndependentAdditiveNoiseModelSystem(model, model.data, model.dim_u)
     Q = model.dim_q
     L = _lib.lib()
     solver = SOLVERS[args.solver]
-    opts = _lib.SolverOpts(solver, 50, 10, 0, 1e-9, 1e-8, 1e10, 2e-8, 0, 0)
+    opts = _lib.SolverOpts(solver, 50, 10, 0, 1e-9, 1e-8, 1e10, 2e-8, 0,
+                           _lib.FLAG_SINGLE_KERNEL if args.single_kernel else 0)
 
     q0 = _lib.to_soa(q_host)
     st0 = mlb.states.ChainState(q0)
@@ -528,7 +577,7 @@ def run_mlb(args, emit):
             "roofline": {
                 "bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": ach_tf / fp64_peak if fp64_peak > 0 else None, "traffic": None,
-                "kernel": ("ks_leapfrog_steps" if args.workload == "fn" else "k_leapfrog_steps")
+                "kernel": ("ks_leapfrog_steps" if args.workload in ("fn", "hh") else "k_leapfrog_steps")
                           + " (fused trajectory)",
                 "algorithmic_flops_per_chain_step": flops_step,
                 "peak_source": "DFMA-loop microbenchmark run live in this process "
@@ -537,7 +586,7 @@ def run_mlb(args, emit):
             "roofline_hbm": {
                 "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ach_gbs / hbm_peak, "traffic": None,
-                "kernel": ("ks_leapfrog_steps" if args.workload == "fn" else "k_leapfrog_steps")
+                "kernel": ("ks_leapfrog_steps" if args.workload in ("fn", "hh") else "k_leapfrog_steps")
                           + ", one step per launch, L2 flushed",
                 "algorithmic_bytes_per_chain_step": bytes_step,
                 "ms_per_launch": ms1_mean, "peak_source": hbm_src,

@@ -109,8 +109,15 @@ typedef struct mlb_solver_opts {
   double divergence_tol;         /* default 1e10                 */
   double reverse_check_tol;      /* default 2 * position_tol     */
   int32_t reverse_check_norm;    /* MLB_NORM_*                   */
-  int32_t _pad;
+  int32_t flags;                 /* MLB_FLAG_* (0 = defaults)    */
 } mlb_solver_opts;
+
+/* mlb_solver_opts.flags.  The streaming (ODE) family runs mlb_leapfrog_steps as a
+ * host-driven sequence of sub-phase kernels whose sweeps are split over sensitivity
+ * directions / pair groups (several warps per batch of 32 chains); the call then blocks
+ * the calling thread while it polls per-iteration convergence counts.  This flag selects
+ * the fully asynchronous single-kernel path instead (one thread per chain). */
+#define MLB_FLAG_SINGLE_KERNEL 1
 
 /* ---- lifecycle */
 int mlb_version(void);

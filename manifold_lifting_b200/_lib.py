@@ -17,6 +17,7 @@ MODEL_TOY, MODEL_HIER, MODEL_FN, MODEL_HH = 0, 1, 2, 3
 PARAM_UNBOUNDED, PARAM_NORMAL = 0, 1
 (SOLVER_QUASI_NEWTON, SOLVER_NEWTON, SOLVER_NEWTON_LS, SOLVER_MICI_NEWTON,
  SOLVER_MICI_QUASI_NEWTON) = range(5)  # fmt: skip
+FLAG_SINGLE_KERNEL = 1
 NORM_MAX, NORM_EUCLIDEAN = 0, 1
 ST_OK, ST_DIVERGED, ST_NOT_CONVERGED, ST_NON_REVERSIBLE, ST_H_DIVERGED, ST_LINALG = range(6)
 ADAPT_ROWS, STAT_ROWS = 5, 7
@@ -47,7 +48,7 @@ class SolverOpts(C.Structure):
         ("max_line_search_iters", C.c_int32), ("norm", C.c_int32),
         ("constraint_tol", C.c_double), ("position_tol", C.c_double),
         ("divergence_tol", C.c_double), ("reverse_check_tol", C.c_double),
-        ("reverse_check_norm", C.c_int32), ("_pad", C.c_int32),
+        ("reverse_check_norm", C.c_int32), ("flags", C.c_int32),
     ]  # fmt: skip
 
 

@@ -86,7 +86,7 @@ static Opts to_opts(const mlb_solver_opts* s) {
   o.ctol = s->constraint_tol, o.ptol = s->position_tol, o.dtol = s->divergence_tol;
   o.rev_tol = s->reverse_check_tol;
   o.max_iters = s->max_iters, o.max_ls = s->max_line_search_iters;
-  o.norm = s->norm, o.rev_norm = s->reverse_check_norm;
+  o.norm = s->norm, o.rev_norm = s->reverse_check_norm, o.flags = s->flags;
   return o;
 }
 
@@ -193,6 +193,10 @@ int mlb_model_create(const mlb_model_desc* d, mlb_model** out) {
 void mlb_model_destroy(mlb_model* m) {
   if (m && m->dev_blob) cudaFree(m->dev_blob);
   if (m && m->host_ws) cudaFree(m->host_ws);
+  if (m && m->pinned_word) cudaFreeHost(m->pinned_word);
+  if (m)
+    for (void* s : m->host_streams)
+      if (s) cudaStreamDestroy((cudaStream_t)s);
   delete m;
 }
 int mlb_model_dim_u(const mlb_model* m) { return m->U; }
@@ -388,52 +392,76 @@ int mlb_leapfrog_steps_host(const mlb_model* m, int64_t n, double* q, double* p,
   MLB_ARG(m && q && p && opts && status && n >= 0);
   if (n == 0) return MLB_OK;
   const int Q = m->Q;
-  const size_t vec_bytes = (size_t)n * Q * sizeof(double);
-  // one device allocation: aos staging (2 vec), soa state (2 vec), per-chain outputs
-  const size_t out_bytes = (size_t)n * (4 * sizeof(int32_t) + 2 * sizeof(double));
-  // the staging area lives in the model handle and only grows: no cudaMalloc / cudaFree
-  // (both synchronise the device) on the steady-state path.  Calls on one handle are
-  // serialised by its mutex.
-  std::lock_guard<std::mutex> lock(m->dev_mutex);
-  if (m->host_ws_bytes < 4 * vec_bytes + out_bytes) {
+  // Chains are independent, so the batch is cut into chunks that flow through
+  // H2D copy -> transpose -> fused kernel -> transpose -> D2H copy on a few streams: the
+  // copies of one chunk overlap the kernel of another (PCIe is full duplex), and the
+  // call costs about max(copy time, kernel time) instead of their sum.  The streaming
+  // (ODE) family keeps one chunk: its batches are small and its kernels long.
+  const bool small_state = m->model == MLB_MODEL_TOY || m->model == MLB_MODEL_HIER;
+  const int64_t chunk = small_state ? 8192 : n;
+  const int n_chunk = (int)((n + chunk - 1) / chunk);
+  // per chunk: aos staging (2 vec), soa state (2 vec), per-chain outputs; the staging area
+  // lives in the model handle and only grows: no cudaMalloc / cudaFree (both synchronise
+  // the device) on the steady-state path.  Calls on one handle are serialised.
+  const size_t per_chain = (size_t)4 * Q * sizeof(double) + 2 * sizeof(double) + 4 * sizeof(int32_t);
+  const size_t need = per_chain * (size_t)n + 256 * (size_t)n_chunk;
+  std::lock_guard<std::mutex> lock(m->host_mutex);
+  if (m->host_ws_bytes < need) {
     if (m->host_ws) cudaFree(m->host_ws);
     m->host_ws = nullptr, m->host_ws_bytes = 0;
-    MLB_CUDA_OK(cudaMalloc(&m->host_ws, 4 * vec_bytes + out_bytes));
-    m->host_ws_bytes = 4 * vec_bytes + out_bytes;
+    MLB_CUDA_OK(cudaMalloc(&m->host_ws, need));
+    m->host_ws_bytes = need;
   }
-  char* dev = static_cast<char*>(m->host_ws);
-  double* d_aos_q = (double*)dev;
-  double* d_aos_p = d_aos_q + (size_t)n * Q;
-  double* d_q = d_aos_p + (size_t)n * Q;
-  double* d_p = d_q + (size_t)n * Q;
-  double* d_h0 = d_p + (size_t)n * Q;
-  double* d_h1 = d_h0 + n;
-  int32_t* d_status = (int32_t*)(d_h1 + n);
-  int32_t *d_done = d_status + n, *d_itf = d_done + n, *d_itr = d_itf + n;
-  cudaStream_t s = nullptr;
+  for (int k = 0; k < mlb_model::kHostStreams; ++k)
+    if (!m->host_streams[k])
+      MLB_CUDA_OK(cudaStreamCreateWithFlags((cudaStream_t*)&m->host_streams[k],
+                                            cudaStreamNonBlocking));
+#define MLB_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { g_err = std::string(#expr) + ": " + cudaGetErrorString(e_); rc = MLB_ERR_CUDA; goto done; } } while (0)
   int rc = MLB_OK;
-  auto fail = [&](int code) { return code; };
-#define MLB_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { g_err = std::string(#expr) + ": " + cudaGetErrorString(e_); return fail(MLB_ERR_CUDA); } } while (0)
-  MLB_TRY(cudaMemcpyAsync(d_aos_q, q, vec_bytes, cudaMemcpyHostToDevice, s));
-  MLB_TRY(cudaMemcpyAsync(d_aos_p, p, vec_bytes, cudaMemcpyHostToDevice, s));
-  if ((rc = mlb_aos_to_soa(n, Q, d_aos_q, d_q, n, s)) != MLB_OK) return fail(rc);
-  if ((rc = mlb_aos_to_soa(n, Q, d_aos_p, d_p, n, s)) != MLB_OK) return fail(rc);
-  rc = mlb_leapfrog_steps(m, n, n, d_q, d_p, dt, nullptr, n_step, opts, d_status, d_done,
-                          d_itf, d_itr, d_h0, d_h1, s);
-  if (rc != MLB_OK) return fail(rc);
-  if ((rc = mlb_soa_to_aos(n, Q, d_q, n, d_aos_q, s)) != MLB_OK) return fail(rc);
-  if ((rc = mlb_soa_to_aos(n, Q, d_p, n, d_aos_p, s)) != MLB_OK) return fail(rc);
-  MLB_TRY(cudaMemcpyAsync(q, d_aos_q, vec_bytes, cudaMemcpyDeviceToHost, s));
-  MLB_TRY(cudaMemcpyAsync(p, d_aos_p, vec_bytes, cudaMemcpyDeviceToHost, s));
-  MLB_TRY(cudaMemcpyAsync(status, d_status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-  if (n_done) MLB_TRY(cudaMemcpyAsync(n_done, d_done, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-  if (iters_fwd) MLB_TRY(cudaMemcpyAsync(iters_fwd, d_itf, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-  if (iters_rev) MLB_TRY(cudaMemcpyAsync(iters_rev, d_itr, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-  if (h_init) MLB_TRY(cudaMemcpyAsync(h_init, d_h0, n * sizeof(double), cudaMemcpyDeviceToHost, s));
-  if (h_final) MLB_TRY(cudaMemcpyAsync(h_final, d_h1, n * sizeof(double), cudaMemcpyDeviceToHost, s));
-  MLB_TRY(cudaStreamSynchronize(s));
+  {
+    char* base = static_cast<char*>(m->host_ws);
+    for (int k = 0; k < n_chunk && rc == MLB_OK; ++k) {
+      const int64_t i0 = k * chunk, nc = std::min(chunk, n - i0);
+      cudaStream_t s = (cudaStream_t)m->host_streams[k % mlb_model::kHostStreams];
+      char* dev = base + (per_chain * (size_t)i0 + 256 * (size_t)k) / 256 * 256;
+      const size_t vec_bytes = (size_t)nc * Q * sizeof(double);
+      double* d_aos_q = (double*)dev;
+      double* d_aos_p = d_aos_q + (size_t)nc * Q;
+      double* d_q = d_aos_p + (size_t)nc * Q;
+      double* d_p = d_q + (size_t)nc * Q;
+      double* d_h0 = d_p + (size_t)nc * Q;
+      double* d_h1 = d_h0 + nc;
+      int32_t* d_status = (int32_t*)(d_h1 + nc);
+      int32_t *d_done = d_status + nc, *d_itf = d_done + nc, *d_itr = d_itf + nc;
+      MLB_TRY(cudaMemcpyAsync(d_aos_q, q + i0 * Q, vec_bytes, cudaMemcpyHostToDevice, s));
+      MLB_TRY(cudaMemcpyAsync(d_aos_p, p + i0 * Q, vec_bytes, cudaMemcpyHostToDevice, s));
+      if ((rc = mlb_aos_to_soa(nc, Q, d_aos_q, d_q, nc, s)) != MLB_OK) break;
+      if ((rc = mlb_aos_to_soa(nc, Q, d_aos_p, d_p, nc, s)) != MLB_OK) break;
+      rc = mlb_leapfrog_steps(m, nc, nc, d_q, d_p, dt, nullptr, n_step, opts, d_status, d_done,
+                              d_itf, d_itr, d_h0, d_h1, s);
+      if (rc != MLB_OK) break;
+      if ((rc = mlb_soa_to_aos(nc, Q, d_q, nc, d_aos_q, s)) != MLB_OK) break;
+      if ((rc = mlb_soa_to_aos(nc, Q, d_p, nc, d_aos_p, s)) != MLB_OK) break;
+      MLB_TRY(cudaMemcpyAsync(q + i0 * Q, d_aos_q, vec_bytes, cudaMemcpyDeviceToHost, s));
+      MLB_TRY(cudaMemcpyAsync(p + i0 * Q, d_aos_p, vec_bytes, cudaMemcpyDeviceToHost, s));
+      MLB_TRY(cudaMemcpyAsync(status + i0, d_status, nc * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+      if (n_done) MLB_TRY(cudaMemcpyAsync(n_done + i0, d_done, nc * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+      if (iters_fwd) MLB_TRY(cudaMemcpyAsync(iters_fwd + i0, d_itf, nc * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+      if (iters_rev) MLB_TRY(cudaMemcpyAsync(iters_rev + i0, d_itr, nc * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+      if (h_init) MLB_TRY(cudaMemcpyAsync(h_init + i0, d_h0, nc * sizeof(double), cudaMemcpyDeviceToHost, s));
+      if (h_final) MLB_TRY(cudaMemcpyAsync(h_final + i0, d_h1, nc * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+  }
+done:
+  for (int k = 0; k < mlb_model::kHostStreams; ++k) {
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t)m->host_streams[k]);
+    if (e != cudaSuccess && rc == MLB_OK) {
+      g_err = std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e);
+      rc = MLB_ERR_CUDA;
+    }
+  }
 #undef MLB_TRY
-  return MLB_OK;
+  return rc;
 }
 
 int mlb_selftest_fast_math(int64_t n, const double* x, double* rcp, double* sqrt_out,

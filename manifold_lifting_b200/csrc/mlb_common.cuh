@@ -15,7 +15,7 @@ namespace mlb {
 // Solver / integrator options in kernel-parameter form (see mlb_solver_opts).
 struct Opts {
   double ctol, ptol, dtol, rev_tol;
-  int max_iters, max_ls, norm, rev_norm;
+  int max_iters, max_ls, norm, rev_norm, flags;
 };
 
 // ---- lean fp64 primitives

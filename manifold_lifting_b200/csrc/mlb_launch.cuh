@@ -29,8 +29,13 @@ struct mlb_model {
   mutable int dev_id = -1;
   int n_steps = 0;
   // mlb_leapfrog_steps_host: grow-only device staging area (no malloc / free per call)
+  mutable std::mutex host_mutex;  // serialises mlb_leapfrog_steps_host calls on the handle
   mutable void* host_ws = nullptr;
   mutable size_t host_ws_bytes = 0;
+  static constexpr int kHostStreams = 4;  // chunk pipeline of the host entry point
+  mutable void* host_streams[kHostStreams] = {nullptr, nullptr, nullptr, nullptr};
+  mutable std::mutex pin_mutex;
+  mutable int* pinned_word = nullptr;  // polled by the host-driven streaming path
 };
 
 namespace mlb {

@@ -24,6 +24,7 @@ template <int PARAM>
 struct FnOde {
   static constexpr int U = 9, ND = 8, NPAIR = ND * (ND + 1) / 2, SIGMA = 6;
   static constexpr int NG = 6, PAIRS_PER_GROUP = NPAIR / NG;  // second-order pass split
+  static constexpr int ROLE_DIRS = 2, N_ROLE = ND / ROLE_DIRS;  // Jacobian sweep split
   static_assert(NPAIR % NG == 0, "pair groups must be equal-sized");
 
   struct Th {
@@ -99,14 +100,17 @@ struct FnOde {
   // bookkeeping: y (state at the step start), acc (running RK4 combination) and ys (the
   // stage state, overwritten IN PLACE in dependency order second-order -> first-order ->
   // primal, so no separate copy of the stage derivative is kept).
+  // S holds the NS1 first-order directions D0 .. D0+NS1-1 (a SUBSET when a Jacobian sweep
+  // is split over several threads; second-order pairs need all of them: D0 = 0, NS1 = ND)
   template <int NS1, int NP, int P0>
   struct Aug {
     double x[2], S[NS1 ? NS1 : 1][2], X[NP ? NP : 1][2];
   };
 
-  template <int NS1, int NP, int P0, bool first, bool last>
+  template <int NS1, int NP, int P0, bool first, bool last, int D0 = 0>
   static MLB_DEV void stage(const Th& t, const Aug<NS1, NP, P0>& y, Aug<NS1, NP, P0>& acc,
                             Aug<NS1, NP, P0>& ys, double w_acc, double c_next) {
+    static_assert(NP == 0 || (D0 == 0 && NS1 == ND), "pairs need every direction");
     // Jacobian of f at the stage state
     const double a00 = fma(-3.0 * t.b * ys.x[0], ys.x[0], t.a), a01 = t.g, a10 = -t.d,
                  a11 = -t.e;
@@ -143,7 +147,7 @@ struct FnOde {
         (
             [&] {
               double p[2];
-              phi<D>(t, ys.x, p);
+              phi<D0 + D>(t, ys.x, p);
               const double k0 = fma(a00, ys.S[D][0], fma(a01, ys.S[D][1], p[0]));
               const double k1 = fma(a10, ys.S[D][0], fma(a11, ys.S[D][1], p[1]));
               acc.S[D][0] = fma(w_acc, k0, first ? y.S[D][0] : acc.S[D][0]);
@@ -166,16 +170,16 @@ struct FnOde {
   }
 
   // Integrates over the schedule; obs(i, state) is called at every observation.
-  // NS1 = 0 (primal only) or ND; NP pairs starting at pair index P0.
-  template <int NS1, int NP, int P0, class F>
+  // NS1 first-order directions starting at D0 (0 = primal only); NP pairs starting at P0.
+  template <int NS1, int NP, int P0, class F, int D0 = 0>
   static MLB_DEV void sweep(const OdeData& D, const double (&u)[U], F&& obs) {
     const Th t = theta(u);
     Aug<NS1, NP, P0> y, acc, ys;
     y.x[0] = u[7], y.x[1] = u[8];
 #pragma unroll
     for (int d = 0; d < (NS1 ? NS1 : 1); ++d) {
-      y.S[d][0] = (d == 6) ? 1.0 : 0.0;
-      y.S[d][1] = (d == 7) ? 1.0 : 0.0;
+      y.S[d][0] = (D0 + d == 6) ? 1.0 : 0.0;
+      y.S[d][1] = (D0 + d == 7) ? 1.0 : 0.0;
     }
 #pragma unroll
     for (int k = 0; k < (NP ? NP : 1); ++k) y.X[k][0] = 0.0, y.X[k][1] = 0.0;
@@ -185,10 +189,10 @@ struct FnOde {
     for (int s = 0; s < D.n_steps; ++s) {
       const double h = __ldg(D.dt_seq + s);
       ys = y;
-      stage<NS1, NP, P0, true, false>(t, y, acc, ys, h * (1.0 / 6.0), 0.5 * h);
-      stage<NS1, NP, P0, false, false>(t, y, acc, ys, h * (1.0 / 3.0), 0.5 * h);
-      stage<NS1, NP, P0, false, false>(t, y, acc, ys, h * (1.0 / 3.0), h);
-      stage<NS1, NP, P0, false, true>(t, y, acc, ys, h * (1.0 / 6.0), 0.0);
+      stage<NS1, NP, P0, true, false, D0>(t, y, acc, ys, h * (1.0 / 6.0), 0.5 * h);
+      stage<NS1, NP, P0, false, false, D0>(t, y, acc, ys, h * (1.0 / 3.0), 0.5 * h);
+      stage<NS1, NP, P0, false, false, D0>(t, y, acc, ys, h * (1.0 / 3.0), h);
+      stage<NS1, NP, P0, false, true, D0>(t, y, acc, ys, h * (1.0 / 6.0), 0.0);
       y = acc;
       while (s == next_step) {
         obs(next, y);

@@ -38,6 +38,7 @@ template <int PARAM>
 struct HhOde {
   static constexpr int U = 7, ND = 6, NPAIR = ND * (ND + 1) / 2, SIGMA = 6;
   static constexpr int NG = 7, PAIRS_PER_GROUP = NPAIR / NG;
+  static constexpr int ROLE_DIRS = 1, N_ROLE = ND / ROLE_DIRS;  // Jacobian sweep split
   static_assert(NPAIR % NG == 0, "pair groups must be equal-sized");
   static MLB_DEV int dir_u(int d) { return d; }
   static __host__ __device__ constexpr int pair_a(int k) { return PairMap<ND>::a(k); }
@@ -73,16 +74,19 @@ struct HhOde {
     T k_tau_p_1, g_Na, g_K, g_M, g_leak, v_t;
   };
 
-  template <class T>
+  // D0: first direction carried by T's gradient (a jet may carry a SUBSET of the six ODE
+  // directions when a Jacobian sweep is split over threads; seeds outside it vanish)
+  template <class T, int D0 = 0>
   static MLB_DEV Par<T> params(const double (&u)[U]) {
     T t[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       if (k < 5) {
-        t[k] = jexp(Ops<T>::seed(u[k] + (PARAM == MLB_PARAM_NORMAL ? loc(k) : 0.0), k, 1.0));
+        t[k] = jexp(Ops<T>::seed(u[k] + (PARAM == MLB_PARAM_NORMAL ? loc(k) : 0.0), k - D0, 1.0));
       } else {
-        t[k] = (PARAM == MLB_PARAM_NORMAL) ? Ops<T>::seed(fma(scale(k), u[k], loc(k)), k, scale(k))
-                                           : Ops<T>::seed(u[k], k, 1.0);
+        t[k] = (PARAM == MLB_PARAM_NORMAL)
+                   ? Ops<T>::seed(fma(scale(k), u[k], loc(k)), k - D0, scale(k))
+                   : Ops<T>::seed(u[k], k - D0, 1.0);
       }
     }
     return Par<T>{t[0], t[1], t[2], t[3], t[4], t[5]};
@@ -114,10 +118,10 @@ struct HhOde {
     return jrecip(1.0 + jexp((K[HH_k_p_infinity_1] - v) * K[HH_r_p_infinity_2]));
   }
 
-  template <class T, class F>
+  template <class T, class F, int D0 = 0>
   static MLB_DEV void integrate(const OdeData& D, const double (&u)[U], F&& obs) {
     const double* K = D.consts;
-    const Par<T> p = params<T>(u);
+    const Par<T> p = params<T, D0>(u);
     T v = Ops<T>::constant(K[HH_E_leak]);
     T n, m, h, pp;
     {  // steady state at v = E_leak (:125-139)
@@ -177,9 +181,11 @@ struct HhOde {
     double x[1], S[NS1 ? NS1 : 1][1], X[NP ? NP : 1][1];
   };
 
-  // same interface as FnOde::sweep (see mlb_stream.cuh)
-  template <int NS1, int NP, int P0, class F>
+  // same interface as FnOde::sweep (see mlb_stream.cuh): NS1 first-order directions
+  // starting at D0 (0 = value only), NP second-order pairs starting at pair index P0
+  template <int NS1, int NP, int P0, class F, int D0 = 0>
   static MLB_DEV void sweep(const OdeData& D, const double (&u)[U], F&& obs) {
+    static_assert(NP == 0 || (D0 == 0 && NS1 == ND), "pairs need every direction");
     if constexpr (NS1 == 0) {
       integrate<double>(D, u, [&](int i, const double& v) {
         ObsView<0, 0> o;
@@ -187,16 +193,17 @@ struct HhOde {
         obs(i, o);
       });
     } else {
-      using T = DJet<ND, NP, P0>;
-      integrate<T>(D, u, [&](int i, const T& v) {
+      using T = DJet<NS1, NP, P0>;
+      auto cb = [&](int i, const T& v) {
         ObsView<NS1, NP> o;
         o.x[0] = v.v;
 #pragma unroll
-        for (int d = 0; d < ND; ++d) o.S[d][0] = v.g[d];
+        for (int d = 0; d < NS1; ++d) o.S[d][0] = v.g[d];
 #pragma unroll
         for (int k = 0; k < NP; ++k) o.X[k][0] = v.h[k];
         obs(i, o);
-      });
+      };
+      integrate<T, decltype(cb)&, D0>(D, u, cb);
     }
   }
 };

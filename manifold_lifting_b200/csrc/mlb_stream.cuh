@@ -114,6 +114,28 @@ struct Stream {
     return norm_finish(acc, norm);
   }
 
+  // One ROLE of a Jacobian sweep split over threads: integrates the state plus the NDR
+  // sensitivity directions D0 .. D0+NDR-1 and writes those dy_du columns; the role with
+  // BASE also writes the residual, the sigma column and dy_dn (systems.py:568-580).
+  template <int D0, int NDR, bool BASE>
+  MLB_DEV static void jacob_role(const OdeData& D, const Col& q, const Col& jac, const Col& c) {
+    double u[U];
+    load_u(q, u);
+    const double sig = M::sigma(u);
+    const int Y = D.Y;
+    auto cb = [&](int i, const auto& st) {
+#pragma unroll
+      for (int d = 0; d < NDR; ++d) jac[i * U + M::dir_u(D0 + d)] = st.S[d][0];
+      if (BASE) {
+        const double ni = q[U + i];
+        if (c) c[i] = fma(sig, ni, st.x[0] - __ldg(D.y_obs + i));
+        jac[i * U + M::SIGMA] = sig * ni;
+        jac[U * Y + i] = sig;
+      }
+    };
+    M::template sweep<NDR, 0, 0, decltype(cb)&, D0>(D, u, cb);
+  }
+
   // ---- block algebra ----------------------------------------------------------------
   struct Chol {
     double L[U][U], rdiag[U];
@@ -322,6 +344,7 @@ struct Stream {
   //   g_u[b]     += sum_i sum_a B_ia d2x_i/du_a du_b        (b an ODE direction)
   //   g_u[sigma] += Y - (U - tr M) + sum_i B_i,sigma sigma n_i
   //   g_n[i]      = n_i + B_i,sigma sigma
+  template <bool WITH_SECOND_ORDER = true>
   MLB_DEV static void grad_logdet(const OdeData& D, const Col& q, const double (&u)[U],
                                   const Col& jac, const Chol& C, const Col& B,
                                   double (&gu)[U], const Col& g, double& nld) {
@@ -362,6 +385,7 @@ struct Stream {
     }
     nld += half_nn;
     gu[M::SIGMA] += gs;
+    if (!WITH_SECOND_ORDER) return;
     // second-order sensitivity sweeps, NG groups of pairs (a <= b)
     [&]<int... G>(std::integer_sequence<int, G...>) {
       (second_order_group<G>(D, u, B, gu), ...);

@@ -336,6 +336,11 @@ struct ScratchBuf {  // stream-ordered scratch allocation
 inline unsigned sgrid(int64_t n) { return (unsigned)((n + kStreamBlock - 1) / kStreamBlock); }
 inline int64_t pad32(int64_t n) { return (n + 31) / 32 * 32; }
 
+// host-driven sub-phase path (mlb_stream_phased.cuh)
+template <class M, int SOLVER>
+int phased_leapfrog_steps(const mlb_model* m, const OdeData& D, int64_t n, int64_t ld,
+                          const Opts& o, const StepsIO& io, cudaStream_t s);
+
 template <class M>
 struct StreamLaunch {
   static constexpr int U = M::U;
@@ -438,6 +443,11 @@ struct StreamLaunch {
     if (solver > MLB_SOLVER_NEWTON_LS) {
       g_err = "Mici's own solvers are not built for ODE models";
       return MLB_ERR_UNSUPPORTED;
+    }
+    if (!(o.flags & MLB_FLAG_SINGLE_KERNEL) && solver != MLB_SOLVER_NEWTON_LS) {
+      if (solver == MLB_SOLVER_QUASI_NEWTON)
+        return phased_leapfrog_steps<M, MLB_SOLVER_QUASI_NEWTON>(m, D, n, ld, o, io, s);
+      return phased_leapfrog_steps<M, MLB_SOLVER_NEWTON>(m, D, n, ld, o, io, s);
     }
     ScratchBuf sb;
     const int64_t lds = pad32(n);

@@ -74,10 +74,47 @@ def fn_counts(Y, n_steps, U=9, ND=8):
     return c
 
 
+def hh_counts(Y, n_steps_used, U=7, ND=6):
+    """Hodgkin-Huxley (streaming family, forward-mode jets).  One exponential-Euler step
+    of the recurrence as written in csrc/mlb_ode_hh.cuh has 21 jet*jet products (M), 21
+    jet additions (A), 36 scalar-jet operations (S) and 24 unary functions exp / expm1 /
+    reciprocal (C).  Per operation: value only M=A=S=C=1; first order (ND directions)
+    M=1+3 ND, A=S=1+ND, C=2+ND; second order (NP=ND(ND+1)/2 pairs, counted ONCE: the
+    kernel's per-group recomputation of the first-order part is not algorithmic work)
+    M=1+3 ND+7 NP, A=S=1+ND+NP, C=3+ND+4 NP."""
+    NP = ND * (ND + 1) // 2
+    nM, nA, nS, nC = 21, 21, 36, 24
+    step0 = nM + nA + nS + nC
+    step1 = nM * (1 + 3 * ND) + (nA + nS) * (1 + ND) + nC * (2 + ND)
+    step2 = (nM * (1 + 3 * ND + 7 * NP) + (nA + nS) * (1 + ND + NP)
+             + nC * (3 + ND + 4 * NP))  # fmt: skip
+    c = {}
+    c["constr"] = n_steps_used * step0 + 3 * Y
+    c["jacob"] = n_steps_used * step1 + 5 * Y
+    c["second_order"] = n_steps_used * step2 + 4 * NP * Y
+    c["decompose"] = Y * (U * (U + 1) + U + 8) + U * U * U // 3 + 20 * U
+    c["inv_gram"] = Y * (2 * U + 8) + 2 * U * U + Y * (2 * U + 8)
+    c["rmult"] = Y * (2 * U + 1)
+    c["lmult"] = Y * (2 * U + 2)
+    c["pinv"] = c["inv_gram"] + c["rmult"]
+    Q = U + Y
+    c["project"] = c["lmult"] + c["pinv"] + Q
+    c["inv_jacprod"] = Y * (2 * U * U + 3 * U + 8) + 2 * U * U * U // 3 + 2 * U * U \
+        + Y * (2 * U + 8)
+    c["newton_iter"] = c["jacob"] + Y + c["inv_jacprod"] + c["rmult"] + 3 * Q
+    c["quasi_newton_iter"] = c["constr"] + Y + c["pinv"] + 3 * Q
+    c["grad_logdet"] = 2 * U * U * U + Y * (2 * U * U + U + 6) + c["second_order"]
+    c["evaluate"] = c["jacob"] + c["decompose"] + (U + 2) * 30 + 3 * Q + c["grad_logdet"]
+    c["step_fixed"] = 3 * c["project"] + 12 * Q + c["evaluate"]
+    return c
+
+
 def step_flops(model, solver, mean_iters_per_step):
     """Algorithmic flops of one constrained leapfrog step for one chain, given the mean
     number of projection iterations (forward + reverse) per step."""
-    if model.model_id == 2:
+    if model.model_id == 3:
+        c = hh_counts(model.dim_y, model.n_steps_used)
+    elif model.model_id == 2:
         c = fn_counts(model.dim_y, int(model.dt_seq.size))
     else:
         c = toy_counts() if model.model_id == 0 else hier_counts(model.dim_u, model.dim_y)

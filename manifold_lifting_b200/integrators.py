@@ -32,6 +32,10 @@ class ConstrainedLeapfrogIntegrator:
             raise NotImplementedError("n_inner_step > 1 is not used by the reference")
         self.system, self.step_size, self.n_inner_step = system, step_size, n_inner_step
         self.reverse_check_tol, self.reverse_check_norm = reverse_check_tol, reverse_check_norm
+        # ODE-constrained models only (include/mlb.h MLB_FLAG_SINGLE_KERNEL): True selects
+        # the asynchronous one-thread-per-chain kernel instead of the host-driven
+        # sub-phase kernels; both compute the same step
+        self.single_kernel = False
         self.projection_solver = projection_solver
         # mutated in place by ToleranceAdapter (adapters.py:45-47, 56-58)
         self.projection_solver_kwargs = ({} if projection_solver_kwargs is None
@@ -48,7 +52,8 @@ class ConstrainedLeapfrogIntegrator:
             solver, int(kw.get("max_iters", 50)), int(kw.get("max_line_search_iters", 10)),
             _norm_code(kw.get("norm", maximum_norm)), kw.get("constraint_tol", 1e-9),
             kw.get("position_tol", 1e-8), kw.get("divergence_tol", 1e10),
-            self.reverse_check_tol, _norm_code(self.reverse_check_norm), 0)  # fmt: skip
+            self.reverse_check_tol, _norm_code(self.reverse_check_norm),
+            _lib.FLAG_SINGLE_KERNEL if self.single_kernel else 0)  # fmt: skip
 
     def step_size_scalar(self):
         ss = self.step_size

@@ -321,6 +321,37 @@ def test_host_buffer_entry_point_matches_device_path():
     assert rel_err(qh, ref["q"]) < TOL and rel_err(ph, ref["p"]) < TOL
 
 
+def test_host_buffer_entry_point_chunk_pipeline():
+    """More chains than one chunk of the host entry point's copy / compute pipeline (8,192
+    chains per chunk, ragged tail): every output array, against the device-pointer path."""
+    import ctypes as C
+
+    mlb = _mlb()
+    _, _, cm, gm, gs, q = make_case("hier", "unbounded", 20000)
+    p = tangent_momentum(cm, q)
+    integ = mlb.integrators.ConstrainedLeapfrogIntegrator(
+        gs, 0.1, projection_solver=mlb.jitted_solve_projection_onto_manifold_newton,
+        projection_solver_kwargs=dict(constraint_tol=1e-9, position_tol=1e-8, max_iters=50))
+    dev = integ.steps(mlb.states.ChainState(q, p), 3, raise_on_failure=False)
+    n = q.shape[0]
+    qh, ph = q.copy(), p.copy()
+    i32 = [np.full(n, -7, np.int32) for _ in range(4)]
+    f64 = [np.full(n, np.nan) for _ in range(2)]
+    opts = mlb._lib.SolverOpts(mlb._lib.SOLVER_NEWTON, 50, 10, 0, 1e-9, 1e-8, 1e10, 2e-8, 0, 0)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    for _ in range(2):  # second call reuses the staging area and the streams
+        qh[:], ph[:] = q, p
+        rc = mlb._lib.lib().mlb_leapfrog_steps_host(
+            gm.handle, C.c_int64(n), vp(qh), vp(ph), C.c_double(0.1), C.c_int32(3),
+            C.byref(opts), vp(i32[0]), vp(i32[1]), vp(i32[2]), vp(i32[3]), vp(f64[0]), vp(f64[1]))
+        assert rc == 0
+        assert (i32[0] == cpu(dev.status)).all() and (i32[1] == cpu(dev.n_done)).all()
+        assert (i32[2] == cpu(dev.iters_fwd)).all() and (i32[3] == cpu(dev.iters_rev)).all()
+        assert np.array_equal(qh, cpu(dev.pos)) and np.array_equal(ph, cpu(dev.mom))
+        assert np.array_equal(f64[0], cpu(dev.h_init))
+        assert np.array_equal(f64[1], cpu(dev.h_final), equal_nan=True)
+
+
 def test_full_size_properties_65536_chains():
     """BASELINE config 3 at full size: size-independent properties (the oracle is not run
     at this size): on-manifold, tangent momentum, energy error O(dt^2), reversibility."""

@@ -341,3 +341,73 @@ def test_fn_hmc_transitions_match_oracle_decisions():
     qg2 = mlb._lib.soa_clone(mlb._lib.to_soa(q))
     sampler2._launch(qg2, 1, chain_offset=100)
     assert scaled_err(cpu(qg2), qo2) < 1e-8
+
+
+def test_fn_host_buffer_entry_point():
+    """mlb_leapfrog_steps_host for an ODE model (it drives the sub-phase kernels while
+    holding the handle's host-entry lock) against the device-pointer call."""
+    import ctypes as C
+
+    mlb, g, cm, gm, gs = fn_case()
+    q = fn_states(cm, 48)
+    p = tangent_momentum(cm, q)
+    integ = mlb.integrators.ConstrainedLeapfrogIntegrator(
+        gs, 0.01, projection_solver=mlb.jitted_solve_projection_onto_manifold_newton,
+        projection_solver_kwargs=dict(constraint_tol=1e-9, position_tol=1e-8, max_iters=50))
+    dev = integ.steps(mlb.states.ChainState(q, p), 1, raise_on_failure=False)
+    qh, ph = q.copy(), p.copy()
+    status = np.full(q.shape[0], -7, np.int32)
+    opts = integ.solver_opts()
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    rc = mlb._lib.lib().mlb_leapfrog_steps_host(
+        gm.handle, C.c_int64(q.shape[0]), vp(qh), vp(ph), C.c_double(0.01), C.c_int32(1),
+        C.byref(opts), vp(status), None, None, None, None, None)
+    assert rc == 0
+    assert (status == cpu(dev.status)).all()
+    assert np.array_equal(qh, cpu(dev.pos)) and np.array_equal(ph, cpu(dev.mom))
+
+
+# ------------------------------------------------- host-driven sub-phase path vs one kernel
+@pytest.mark.parametrize("model", ["fn", "hh"])
+@pytest.mark.parametrize("solver", [co.SOLVER_QUASI_NEWTON, co.SOLVER_NEWTON])
+def test_phased_path_matches_single_kernel(model, solver):
+    """mlb_leapfrog_steps runs the ODE family as a sequence of sub-phase kernels with the
+    sweeps split over sensitivity directions / pair groups (default) or as one kernel
+    (MLB_FLAG_SINGLE_KERNEL).  Same device functions, same order of operations per chain:
+    statuses and iteration counts are identical and the states agree to rounding of the
+    few expressions the two drivers contract differently."""
+    if model == "fn":
+        mlb, g, cm, gm, gs = fn_case()
+        q = fn_states(cm, 96)
+        dt, n_step, tol_q, tol_p = 0.01, 2, 1e-11, 1e-7
+    else:
+        mlb, g, cm, gm, gs = hh_case()
+        q = hh_states(cm, g, 40, spread=0.01)
+        dt, n_step, tol_q, tol_p = 0.005, 2, 1e-9, 1e-3
+    p = tangent_momentum(cm, q)
+    outs = []
+    for single in (False, True):
+        integ = mlb.integrators.ConstrainedLeapfrogIntegrator(
+            gs, dt, projection_solver={v: k for k, v in mlb.solvers.SOLVER_IDS.items()}[solver],
+            projection_solver_kwargs=dict(constraint_tol=1e-9, position_tol=1e-8, max_iters=50))
+        integ.single_kernel = single
+        outs.append(integ.steps(mlb.states.ChainState(q, p), n_step, raise_on_failure=False))
+    a, b = outs
+    assert (cpu(a.status) == cpu(b.status)).all()
+    assert (cpu(a.n_done) == cpu(b.n_done)).all()
+    # ill-conditioned HH quasi-Newton solves sit near the tolerance for several iterations:
+    # counts may differ by rounding there, and such chains are left out of the comparison
+    same_frac = 0.95 if model == "fn" else 0.6
+    assert (cpu(a.iters_fwd) == cpu(b.iters_fwd)).mean() > same_frac
+    assert (cpu(a.iters_rev) == cpu(b.iters_rev)).mean() > same_frac
+    ok = (cpu(a.status) == 0) & (cpu(a.iters_fwd) == cpu(b.iters_fwd)) \
+        & (cpu(a.iters_rev) == cpu(b.iters_rev))
+    assert ok.mean() > 0.5
+    assert scaled_err(cpu(a.pos)[ok], cpu(b.pos)[ok]) < tol_q
+    assert scaled_err(cpu(a.mom)[ok], cpu(b.mom)[ok]) < tol_p
+    assert rel_err(cpu(a.h_init), cpu(b.h_init)) < 1e-12
+    assert rel_err(cpu(a.h_final)[ok], cpu(b.h_final)[ok]) < 1e-8
+    # failed chains are handed back at their last committed state by both paths
+    bad = cpu(a.status) != 0
+    if bad.any():
+        assert scaled_err(cpu(a.pos)[bad], cpu(b.pos)[bad]) < tol_q
