@@ -393,17 +393,21 @@ int mlb_leapfrog_steps_host(const mlb_model* m, int64_t n, double* q, double* p,
   if (n == 0) return MLB_OK;
   const int Q = m->Q;
   // Chains are independent, so the batch is cut into chunks that flow through
-  // H2D copy -> transpose -> fused kernel -> transpose -> D2H copy on a few streams: the
-  // copies of one chunk overlap the kernel of another (PCIe is full duplex), and the
-  // call costs about max(copy time, kernel time) instead of their sum.  The streaming
-  // (ODE) family keeps one chunk: its batches are small and its kernels long.
+  // H2D copy -> fused kernel -> D2H copy on a few streams: the copies of one chunk overlap
+  // the kernel of another (PCIe is full duplex), and the call costs about
+  // max(copy time, kernel time) instead of their sum.  The register-resident family reads
+  // and writes the reference's [n][Q] rows directly (it touches the state once per launch),
+  // so a chunk is 2 + 1 + 2 API calls plus one per requested per-chain output; the
+  // streaming (ODE) family keeps one chunk and transposes on the device: its batches are
+  // small and its kernels long.
   const bool small_state = m->model == MLB_MODEL_TOY || m->model == MLB_MODEL_HIER;
-  const int64_t chunk = small_state ? 8192 : n;
+  const int64_t chunk = small_state ? 16384 : n;
   const int n_chunk = (int)((n + chunk - 1) / chunk);
-  // per chunk: aos staging (2 vec), soa state (2 vec), per-chain outputs; the staging area
-  // lives in the model handle and only grows: no cudaMalloc / cudaFree (both synchronise
-  // the device) on the steady-state path.  Calls on one handle are serialised.
-  const size_t per_chain = (size_t)4 * Q * sizeof(double) + 2 * sizeof(double) + 4 * sizeof(int32_t);
+  // per chunk: row-major state (2 vec), component-major state (2 vec, ODE family only),
+  // per-chain outputs; the staging area lives in the model handle and only grows: no
+  // cudaMalloc / cudaFree (both synchronise the device) on the steady-state path.
+  const size_t per_chain = (size_t)(small_state ? 2 : 4) * Q * sizeof(double) +
+                           2 * sizeof(double) + 4 * sizeof(int32_t);
   const size_t need = per_chain * (size_t)n + 256 * (size_t)n_chunk;
   std::lock_guard<std::mutex> lock(m->host_mutex);
   if (m->host_ws_bytes < need) {
@@ -419,6 +423,7 @@ int mlb_leapfrog_steps_host(const mlb_model* m, int64_t n, double* q, double* p,
 #define MLB_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { g_err = std::string(#expr) + ": " + cudaGetErrorString(e_); rc = MLB_ERR_CUDA; goto done; } } while (0)
   int rc = MLB_OK;
   {
+    const Opts o = to_opts(opts);
     char* base = static_cast<char*>(m->host_ws);
     for (int k = 0; k < n_chunk && rc == MLB_OK; ++k) {
       const int64_t i0 = k * chunk, nc = std::min(chunk, n - i0);
@@ -427,21 +432,25 @@ int mlb_leapfrog_steps_host(const mlb_model* m, int64_t n, double* q, double* p,
       const size_t vec_bytes = (size_t)nc * Q * sizeof(double);
       double* d_aos_q = (double*)dev;
       double* d_aos_p = d_aos_q + (size_t)nc * Q;
-      double* d_q = d_aos_p + (size_t)nc * Q;
-      double* d_p = d_q + (size_t)nc * Q;
+      double* d_q = small_state ? d_aos_q : d_aos_p + (size_t)nc * Q;
+      double* d_p = small_state ? d_aos_p : d_q + (size_t)nc * Q;
       double* d_h0 = d_p + (size_t)nc * Q;
       double* d_h1 = d_h0 + nc;
       int32_t* d_status = (int32_t*)(d_h1 + nc);
       int32_t *d_done = d_status + nc, *d_itf = d_done + nc, *d_itr = d_itf + nc;
       MLB_TRY(cudaMemcpyAsync(d_aos_q, q + i0 * Q, vec_bytes, cudaMemcpyHostToDevice, s));
       MLB_TRY(cudaMemcpyAsync(d_aos_p, p + i0 * Q, vec_bytes, cudaMemcpyHostToDevice, s));
-      if ((rc = mlb_aos_to_soa(nc, Q, d_aos_q, d_q, nc, s)) != MLB_OK) break;
-      if ((rc = mlb_aos_to_soa(nc, Q, d_aos_p, d_p, nc, s)) != MLB_OK) break;
-      rc = mlb_leapfrog_steps(m, nc, nc, d_q, d_p, dt, nullptr, n_step, opts, d_status, d_done,
-                              d_itf, d_itr, d_h0, d_h1, s);
-      if (rc != MLB_OK) break;
-      if ((rc = mlb_soa_to_aos(nc, Q, d_q, nc, d_aos_q, s)) != MLB_OK) break;
-      if ((rc = mlb_soa_to_aos(nc, Q, d_p, nc, d_aos_p, s)) != MLB_OK) break;
+      if (!small_state) {
+        if ((rc = mlb_aos_to_soa(nc, Q, d_aos_q, d_q, nc, s)) != MLB_OK) break;
+        if ((rc = mlb_aos_to_soa(nc, Q, d_aos_p, d_p, nc, s)) != MLB_OK) break;
+      }
+      StepsIO io{d_q, d_p, dt, nullptr, n_step, d_status, d_done, d_itf, d_itr, d_h0, d_h1};
+      io.row_major = small_state;
+      if ((rc = m->ops->steps(m, opts->solver, nc, nc, o, io, s)) != MLB_OK) break;
+      if (!small_state) {
+        if ((rc = mlb_soa_to_aos(nc, Q, d_q, nc, d_aos_q, s)) != MLB_OK) break;
+        if ((rc = mlb_soa_to_aos(nc, Q, d_p, nc, d_aos_p, s)) != MLB_OK) break;
+      }
       MLB_TRY(cudaMemcpyAsync(q + i0 * Q, d_aos_q, vec_bytes, cudaMemcpyDeviceToHost, s));
       MLB_TRY(cudaMemcpyAsync(p + i0 * Q, d_aos_p, vec_bytes, cudaMemcpyDeviceToHost, s));
       MLB_TRY(cudaMemcpyAsync(status + i0, d_status, nc * sizeof(int32_t), cudaMemcpyDeviceToHost, s));

@@ -59,10 +59,7 @@ struct Blocks {
   static MLB_DEV void rmult_jacob(const Jac& J, const double (&w)[Y], double (&out)[Q]) {
 #pragma unroll
     for (int a = 0; a < U; ++a) {
-      double s = 0.0;
-#pragma unroll
-      for (int i = 0; i < Y; ++i) s = fma(w[i], J.du[i][a], s);
-      out[a] = s;
+      out[a] = dot_acc<Y>(0.0, [&](int i) { return w[i]; }, [&](int i) { return J.du[i][a]; });
     }
 #pragma unroll
     for (int i = 0; i < Y; ++i) {
@@ -98,9 +95,8 @@ struct Blocks {
       for (int a = 0; a < U; ++a)
 #pragma unroll
         for (int b = 0; b <= a; ++b) {
-          double s = (a == b) ? 1.0 : 0.0;
-#pragma unroll
-          for (int i = 0; i < Y; ++i) s = fma(J.du[i][a], J.du[i][b] * G.rd[i], s);
+          const double s = dot_acc<Y>((a == b) ? 1.0 : 0.0, [&](int i) { return J.du[i][a]; },
+                                      [&](int i) { return J.du[i][b] * G.rd[i]; });
           G.chol[a][b] = s;
           G.chol[b][a] = s;
         }
@@ -122,10 +118,8 @@ struct Blocks {
       double t[K];
 #pragma unroll
       for (int a = 0; a < U; ++a) {
-        double s = 0.0;
-#pragma unroll
-        for (int i = 0; i < Y; ++i) s = fma(J.du[i][a], w[i] * G.rd[i], s);
-        t[a] = s;
+        t[a] = dot_acc<Y>(0.0, [&](int i) { return J.du[i][a]; },
+                          [&](int i) { return w[i] * G.rd[i]; });
       }
       chol_solve<K>(G.chol, G.rdiag, t);
 #pragma unroll
@@ -172,15 +166,11 @@ struct Blocks {
       for (int a = 0; a < U; ++a) {
 #pragma unroll
         for (int b = 0; b < U; ++b) {
-          double s = (a == b) ? 1.0 : 0.0;
-#pragma unroll
-          for (int i = 0; i < Y; ++i) s = fma(Jr.du[i][a], Jl.du[i][b] * rd[i], s);
-          mat[a][b] = s;
+          mat[a][b] = dot_acc<Y>((a == b) ? 1.0 : 0.0, [&](int i) { return Jr.du[i][a]; },
+                                 [&](int i) { return Jl.du[i][b] * rd[i]; });
         }
-        double s = 0.0;
-#pragma unroll
-        for (int i = 0; i < Y; ++i) s = fma(Jr.du[i][a], w[i] * rd[i], s);
-        t[a] = s;
+        t[a] = dot_acc<Y>(0.0, [&](int i) { return Jr.du[i][a]; },
+                          [&](int i) { return w[i] * rd[i]; });
       }
       ok = lu_solve<K>(mat, t);
 #pragma unroll

@@ -52,6 +52,27 @@ MLB_DEV double sqrt_rsqrt_fast(double s, double& rs) {
 // numpy / jax `max`: for non-negative doubles the IEEE bit patterns order like unsigned
 // integers and every NaN pattern is above +inf, so an integer max of |v| does both jobs
 // off the fp64 pipe.
+// sum_{i<N} a(i) * b(i) (+ init) with MLB_NACC independent accumulators: a reduction over
+// dim_y as ONE dependent FMA chain leaves the fp64 pipe idle for most of its latency when
+// only two warps share a scheduler
+#ifndef MLB_NACC
+#define MLB_NACC 1
+#endif
+template <int N, class FA, class FB>
+MLB_DEV double dot_acc(double init, FA&& a, FB&& b) {
+  constexpr int NA = MLB_NACC < N ? MLB_NACC : N;
+  double acc[NA];
+#pragma unroll
+  for (int k = 0; k < NA; ++k) acc[k] = k == 0 ? init : 0.0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) acc[i % NA] = fma(a(i), b(i), acc[i % NA]);
+#pragma unroll
+  for (int w = 1; w < NA; w *= 2)
+#pragma unroll
+    for (int k = 0; k + w < NA; k += 2 * w) acc[k] += acc[k + w];
+  return acc[0];
+}
+
 template <int N>
 MLB_DEV double vec_norm(const double (&v)[N], int kind) {
   if (kind == MLB_NORM_MAX) {

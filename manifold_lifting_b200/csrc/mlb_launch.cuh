@@ -73,6 +73,19 @@ MLB_DEV void store_vec(const double (&v)[D], double* a, int64_t ld, int64_t i) {
   for (int k = 0; k < D; ++k) a[(int64_t)k * ld + i] = v[k];
 }
 
+// element (k, chain i) at a[k * es + i * cs]: component-major (es = ld, cs = 1) or the
+// reference's chain-major rows (es = 1, cs = D)
+template <int D>
+MLB_DEV void load_vec(double (&v)[D], const double* a, int64_t es, int64_t cs, int64_t i) {
+#pragma unroll
+  for (int k = 0; k < D; ++k) v[k] = a[(int64_t)k * es + i * cs];
+}
+template <int D>
+MLB_DEV void store_vec(const double (&v)[D], double* a, int64_t es, int64_t cs, int64_t i) {
+#pragma unroll
+  for (int k = 0; k < D; ++k) a[(int64_t)k * es + i * cs] = v[k];
+}
+
 constexpr int kBlock = 64;  // threads per CTA for the heavy per-chain kernels
 #ifndef MLB_LF_MIN_BLOCKS
 #define MLB_LF_MIN_BLOCKS 1  // min resident CTAs per SM asked of the fused kernels
@@ -268,21 +281,21 @@ __global__ void __launch_bounds__(kBlock)
 
 template <class M, int SOLVER>
 __global__ void __launch_bounds__(kBlock, MLB_LF_MIN_BLOCKS)
-    k_leapfrog_steps(const __grid_constant__ typename M::Params P, int64_t n, int64_t ld,
-                     double* q, double* p, double dt, const double* dt_pc, int n_step,
+    k_leapfrog_steps(const __grid_constant__ typename M::Params P, int64_t n, int64_t es,
+                     int64_t cs, double* q, double* p, double dt, const double* dt_pc, int n_step,
                      Opts o, int32_t* status, int32_t* n_done, int32_t* iters_fwd,
                      int32_t* iters_rev, double* h_init, double* h_final) {
   constexpr int Q = M::Q;
   __shared__ double commit[2 * Q][kBlock];  // last committed (q, p) of each chain
   MLB_CHAIN_INDEX();
   double qv[Q], pv[Q];
-  load_vec<Q>(qv, q, ld, i);
-  load_vec<Q>(pv, p, ld, i);
+  load_vec<Q>(qv, q, es, cs, i);
+  load_vec<Q>(pv, p, es, cs, i);
   const double dti = dt_pc ? dt_pc[i] : dt;
   const TrajOut t = run_trajectory<M, SOLVER, false, false, kBlock>(
       P, qv, pv, &commit[0][threadIdx.x], &commit[Q][threadIdx.x], n_step, dti, o, 0.0);
-  store_vec<Q>(qv, q, ld, i);
-  store_vec<Q>(pv, p, ld, i);
+  store_vec<Q>(qv, q, es, cs, i);
+  store_vec<Q>(pv, p, es, cs, i);
   status[i] = t.status;
   if (n_done) n_done[i] = t.done;
   if (iters_fwd) iters_fwd[i] = t.it_fwd;
@@ -417,6 +430,9 @@ struct StepsIO {
   int n_step;
   int32_t *status, *n_done, *iters_fwd, *iters_rev;
   double *h_init, *h_final;
+  // q, p given as chain-major rows [n][Q] (the reference's layout) instead of [Q][ld];
+  // only the register-resident family reads it (it touches q, p once per launch)
+  bool row_major = false;
 };
 
 // Table of launchers for one compiled-in model; one translation unit per model so the
@@ -547,7 +563,8 @@ struct Launch {
                    const StepsIO& io, cudaStream_t s) {
     return dispatch_solver(solver, [&]<int S>() {
       k_leapfrog_steps<M, S><<<grid_for(n), kBlock, 0, s>>>(
-          P(m), n, ld, io.q, io.p, io.dt, io.dt_pc, io.n_step, o, io.status, io.n_done,
+          P(m), n, io.row_major ? 1 : ld, io.row_major ? (int64_t)M::Q : 1, io.q, io.p, io.dt,
+          io.dt_pc, io.n_step, o, io.status, io.n_done,
           io.iters_fwd, io.iters_rev, io.h_init, io.h_final);
       return finish_launch();
     });

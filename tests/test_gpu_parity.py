@@ -322,12 +322,12 @@ def test_host_buffer_entry_point_matches_device_path():
 
 
 def test_host_buffer_entry_point_chunk_pipeline():
-    """More chains than one chunk of the host entry point's copy / compute pipeline (8,192
+    """More chains than one chunk of the host entry point's copy / compute pipeline (16,384
     chains per chunk, ragged tail): every output array, against the device-pointer path."""
     import ctypes as C
 
     mlb = _mlb()
-    _, _, cm, gm, gs, q = make_case("hier", "unbounded", 20000)
+    _, _, cm, gm, gs, q = make_case("hier", "unbounded", 40000)
     p = tangent_momentum(cm, q)
     integ = mlb.integrators.ConstrainedLeapfrogIntegrator(
         gs, 0.1, projection_solver=mlb.jitted_solve_projection_onto_manifold_newton,
