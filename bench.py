@@ -367,7 +367,11 @@ class ClockSampler:
     REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20),
                ("hw_thermal_slowdown", 0x40), ("hw_power_brake", 0x80))  # fmt: skip
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.002):
+        # the ODE workloads are driven from the host (hundreds of launches and a few
+        # stream synchronisations per step) and NVML queries contend with those calls
+        # inside the driver: they are polled every 25 ms instead of every 2 ms
+        self.period = period
         self.index, self.rows, self.stop_flag, self.thread, self.err = index, [], False, None, None
         try:
             import pynvml
@@ -394,7 +398,7 @@ class ClockSampler:
             except Exception as e:  # noqa: BLE001
                 self.err = repr(e)
                 return
-            time.sleep(0.002)
+            time.sleep(self.period)
 
     def start(self):
         if self.nv is not None:
@@ -498,7 +502,7 @@ def run_mlb(args, emit):
     for _ in range(W):
         reset(), launch(n_step)
     barrier()
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(local, 0.025 if args.workload in ("fn", "hh") else 0.002)
     clocks.start()
     launches0 = L.mlb_launch_count()
     barrier()

@@ -280,6 +280,11 @@ double mlb_measure_fp64_tflops(int32_t repeats);
 int mlb_selftest_fast_math(int64_t n, const double* x, double* rcp, double* sqrt_out,
                            double* rsqrt_out, void* stream);
 
+/* Same for the branch-free exp / expm1 of the Hodgkin-Huxley recurrence: x [n] device in;
+ * exp_out, expm1_out [n] device out (arguments are clamped to [-700, 700]). */
+int mlb_selftest_exp(int64_t n, const double* x, double* exp_out, double* expm1_out,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

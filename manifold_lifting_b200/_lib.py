@@ -33,7 +33,7 @@ EXPORTS = (
     "mlb_project_onto_cotangent_space", "mlb_leapfrog_steps", "mlb_hmc_sample",
     "mlb_philox_normals_host", "mlb_philox_uniform_host", "mlb_leapfrog_steps_host",
     "mlb_aos_to_soa", "mlb_soa_to_aos", "mlb_launch_count", "mlb_measure_fp64_tflops",
-    "mlb_selftest_fast_math",
+    "mlb_selftest_fast_math", "mlb_selftest_exp",
 )  # fmt: skip
 
 

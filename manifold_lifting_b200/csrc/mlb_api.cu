@@ -130,6 +130,13 @@ __global__ void k_selftest_fast_math(int64_t n, const double* x, double* r, doub
   rs[i] = t;
 }
 
+__global__ void k_selftest_exp(int64_t n, const double* x, double* e, double* em1) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  e[i] = exp_bl(x[i]);
+  em1[i] = expm1_bl(x[i]);
+}
+
 }  // namespace mlb
 
 using namespace mlb;
@@ -479,6 +486,15 @@ int mlb_selftest_fast_math(int64_t n, const double* x, double* rcp, double* sqrt
   if (n == 0) return MLB_OK;
   k_selftest_fast_math<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       n, x, rcp, sqrt_out, rsqrt_out);
+  return finish_launch();
+}
+
+int mlb_selftest_exp(int64_t n, const double* x, double* exp_out, double* expm1_out,
+                     void* stream) {
+  MLB_ARG(n >= 0 && x && exp_out && expm1_out);
+  if (n == 0) return MLB_OK;
+  k_selftest_exp<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, x, exp_out,
+                                                                                 expm1_out);
   return finish_launch();
 }
 

@@ -123,11 +123,11 @@ MLB_JET_T MLB_DEV MLB_JET jchain(const MLB_JET& x, double f, double df, double d
   return r;
 }
 MLB_JET_T MLB_DEV MLB_JET jexp(const MLB_JET& x) {
-  const double e = exp(x.v);
+  const double e = exp_bl(x.v);
   return jchain(x, e, e, e);
 }
 MLB_JET_T MLB_DEV MLB_JET jexpm1(const MLB_JET& x) {
-  const double e = expm1(x.v);
+  const double e = expm1_bl(x.v);
   return jchain(x, e, e + 1.0, e + 1.0);
 }
 MLB_JET_T MLB_DEV MLB_JET jrecip(const MLB_JET& x) {
@@ -138,8 +138,8 @@ MLB_JET_T MLB_DEV MLB_JET operator/(const MLB_JET& x, const MLB_JET& y) { return
 MLB_JET_T MLB_DEV MLB_JET operator/(double c, const MLB_JET& y) { return c * jrecip(y); }
 
 // order-0 versions so that model code can be written once
-MLB_DEV double jexp(double x) { return exp(x); }
-MLB_DEV double jexpm1(double x) { return expm1(x); }
+MLB_DEV double jexp(double x) { return exp_bl(x); }
+MLB_DEV double jexpm1(double x) { return expm1_bl(x); }
 MLB_DEV double jrecip(double x) { return rcp_fast(x); }
 
 // constants / seeded variables of either scalar type

@@ -36,6 +36,7 @@ struct FnOde {
   }
   static MLB_DEV double off(int k) { return PARAM == MLB_PARAM_NORMAL ? loc(k) : 0.0; }
   static MLB_DEV int dir_u(int d) { return d < 6 ? d : d + 1; }
+  static MLB_DEV int u_dir(int a) { return a < 6 ? a : (a == 6 ? -1 : a - 1); }  // inverse
   static MLB_DEV Th theta(const double (&u)[U]) {
     Th t;
     t.a = exp(u[0] + off(0)), t.b = exp(u[1] + off(1)), t.g = exp(u[2] + off(2));

@@ -41,6 +41,7 @@ struct HhOde {
   static constexpr int ROLE_DIRS = 1, N_ROLE = ND / ROLE_DIRS;  // Jacobian sweep split
   static_assert(NPAIR % NG == 0, "pair groups must be equal-sized");
   static MLB_DEV int dir_u(int d) { return d; }
+  static MLB_DEV int u_dir(int a) { return a < ND ? a : -1; }  // inverse (-1: sigma)
   static __host__ __device__ constexpr int pair_a(int k) { return PairMap<ND>::a(k); }
   static __host__ __device__ constexpr int pair_b(int k) { return PairMap<ND>::b(k); }
 

@@ -58,6 +58,84 @@ struct PhasedLayout {
   }
 };
 
+// ---- observation-chunked kernels --------------------------------------------------------
+// The Y-sized streaming phases (capacitance accumulation, Woodbury apply, cotangent
+// projection, B = Gram^-1 A) are sums over observations followed by a U x U solve and a
+// second pass over the observations.  A CTA of NCH warps works on one batch of 32 chains:
+// warp j streams observations [j CH, (j+1) CH), the partial sums are combined in shared
+// memory IN WARP ORDER (deterministic), warp 0 does the U x U factorisation / solve and
+// hands the result back through shared memory.  NCH times more loads in flight per chain
+// than the one-thread-per-chain form, which ran at ~5 % of the HBM rate.
+constexpr int kChunkWarps = 8;
+
+struct ChunkCtx {
+  int lane, wj, k0, k1;
+  int64_t i;
+  bool in_range;
+};
+template <int NCH>
+MLB_DEV ChunkCtx chunk_ctx(int64_t n, int Y) {
+  ChunkCtx c;
+  c.lane = threadIdx.x, c.wj = threadIdx.y;
+  c.i = (int64_t)blockIdx.x * 32 + c.lane;
+  c.in_range = c.i < n;
+  const int CH = (Y + NCH - 1) / NCH;
+  c.k0 = c.wj * CH;
+  c.k1 = c.k0 + CH < Y ? c.k0 + CH : Y;
+  if (c.k0 > Y) c.k0 = Y;
+  return c;
+}
+// v <- sum over the CTA's warps of v (added in warp order); the total is returned to warp 0
+// only.  sh: [R][32] doubles.  Every thread of the CTA must call it.
+template <int R, int NCH>
+MLB_DEV void cta_sum_to_warp0(double (&v)[R], double* sh) {
+  const int lane = threadIdx.x, wj = threadIdx.y;
+#pragma unroll 1
+  for (int j = 1; j < NCH; ++j) {
+    if (wj == j) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) sh[r * 32 + lane] = v[r];
+    }
+    __syncthreads();
+    if (wj == 0) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[r] += sh[r * 32 + lane];
+    }
+    __syncthreads();
+  }
+}
+// same for a running norm (max for the maximum norm, sum of squares for the Euclidean norm)
+template <int NCH>
+MLB_DEV double cta_norm_to_warp0(double acc, int kind, double* sh) {
+  const int lane = threadIdx.x, wj = threadIdx.y;
+  if (wj > 0) sh[(wj - 1) * 32 + lane] = acc;
+  __syncthreads();
+  if (wj == 0) {
+#pragma unroll 1
+    for (int j = 1; j < NCH; ++j) {
+      const double o = sh[(j - 1) * 32 + lane];
+      acc = kind == MLB_NORM_MAX ? (o > acc ? o : acc) : acc + o;
+    }
+  }
+  __syncthreads();
+  return acc;
+}
+// warp 0 publishes R values per chain to every warp of the CTA
+template <int R>
+MLB_DEV void cta_bcast_from_warp0(double (&v)[R], double* sh) {
+  const int lane = threadIdx.x;
+  if (threadIdx.y == 0) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) sh[r * 32 + lane] = v[r];
+  }
+  __syncthreads();
+  if (threadIdx.y != 0) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = sh[r * 32 + lane];
+  }
+  __syncthreads();
+}
+
 #define MLB_PH_INDEX()                                              \
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; \
   if (i >= n) return;                                               \
@@ -109,32 +187,121 @@ __global__ void __launch_bounds__(kStreamBlock)
 }
 
 // after the Jacobian sweep of an evaluation: Gram factor, log det, prior, and everything
-// of grad 0.5 log det(J J^T) that does not need second-order sensitivities
-template <class M>
-__global__ void __launch_bounds__(kStreamBlock)
+// of grad 0.5 log det(J J^T) that does not need second-order sensitivities (the arithmetic
+// of Stream::decompose / logdet / grad_logdet<false>, observation-chunked)
+template <class M, int NCH>
+__global__ void __launch_bounds__(32 * NCH)
     kp_eval_mid(const __grid_constant__ OdeData D, PhasedLayout L, int64_t n, int64_t ld,
                 double* q, double* p) {
-  MLB_PH_INDEX();
-  if (!P.I(CT_ALIVE, i)) return;
   using S = Stream<M>;
-  constexpr int U = M::U;
-  const Col qw = col(q, ld, i);
-  typename S::Chol C;
-  const bool ok = S::decompose(D.Y, P.S.Jc, P.S.Gc, C);
-  const double ldv = S::logdet(D.Y, P.S.Gc, C);
-  double u[U], gu[U];
-  S::load_u(qw, u);
-  double nld = M::nld_u(u, gu);
-  S::template grad_logdet<false>(D, qw, u, P.S.Jc, C, P.S.Jt, gu, P.S.g, nld);
+  constexpr int U = M::U, NT = U * (U + 1) / 2;
+  extern __shared__ double sh[];
+  const int Y = L.Y;
+  const ChunkCtx cx = chunk_ctx<NCH>(n, Y);
+  const int64_t i = cx.in_range ? cx.i : 0;
+  const Phased P = L.at(i);
+  const bool live = cx.in_range && P.I(CT_ALIVE, i);
+  const Col qw = col(q, ld, i), jac = P.S.Jc, gram = P.S.Gc, B = P.S.Jt, g = P.S.g;
+  // pass 1: capacitance matrix (lower triangle) and sum log d over the chunk
+  double acc[NT + 1];
 #pragma unroll
-  for (int a = 0; a < U; ++a) P.S.g[a] = gu[a];
-  P.Dv(CD_NLD, i) = nld, P.Dv(CD_LOGDET, i) = ldv;
-  if (!ok) {  // hand the chain back at its last committed state
-    P.I(CT_STATUS, i) = MLB_ST_LINALG, P.I(CT_ALIVE, i) = 0;
-    const Col pw = col(p, ld, i);
-    const int Q = U + D.Y;
+  for (int r = 0; r < NT + 1; ++r) acc[r] = 0.0;
+  if (live && cx.k0 < cx.k1) {
+    double prev = jac[U * Y + cx.k0], lp;
+    prev *= prev, lp = log(prev);
 #pragma unroll 4
-    for (int k = 0; k < Q; ++k) qw[k] = P.S.cq[k], pw[k] = P.S.cp[k];
+    for (int k = cx.k0; k < cx.k1; ++k) {
+      const double dn = jac[U * Y + k], d = dn * dn, rd = rcp_fast(d);
+      gram[U * U + k] = d;
+      if (d != prev) prev = d, lp = log(d);
+      acc[NT] += lp;
+      double row[U];
+#pragma unroll
+      for (int a = 0; a < U; ++a) row[a] = jac[k * U + a];
+      int t = 0;
+#pragma unroll
+      for (int a = 0; a < U; ++a) {
+        const double ra = row[a] * rd;
+#pragma unroll
+        for (int b = 0; b <= a; ++b, ++t) acc[t] = fma(ra, row[b], acc[t]);
+      }
+    }
+  }
+  cta_sum_to_warp0<NT + 1, NCH>(acc, sh);
+  // warp 0: Cholesky, log det, prior, M = C^-1
+  double Minv[U * U + 1];  // + the factorisation flag
+  double u[U], gu[U], nld = 0.0, ldv = 0.0, trM = 0.0;
+#pragma unroll
+  for (int r = 0; r < U * U + 1; ++r) Minv[r] = 0.0;
+  if (live && cx.wj == 0) {
+    typename S::Chol C;
+    int t = 0;
+#pragma unroll
+    for (int a = 0; a < U; ++a)
+#pragma unroll
+      for (int b = 0; b <= a; ++b, ++t) C.L[a][b] = acc[t] + (a == b ? 1.0 : 0.0), C.L[b][a] = C.L[a][b];
+    C.ok = chol_lower<U>(C.L, C.rdiag);
+#pragma unroll
+    for (int a = 0; a < U; ++a)
+#pragma unroll
+      for (int b = 0; b < U; ++b) gram[a * U + b] = C.L[a][b];
+    double sl = 0.0;
+#pragma unroll
+    for (int a = 0; a < U; ++a) sl += log(C.L[a][a]);
+    ldv = fma(0.5, acc[NT], sl);
+    S::load_u(qw, u);
+    nld = M::nld_u(u, gu);
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      double cj[U];
+#pragma unroll
+      for (int a = 0; a < U; ++a) cj[a] = (a == j) ? 1.0 : 0.0;
+      chol_solve<U>(C.L, C.rdiag, cj);
+#pragma unroll
+      for (int a = 0; a < U; ++a) Minv[a * U + j] = cj[a];
+    }
+#pragma unroll
+    for (int a = 0; a < U; ++a) trM += Minv[a * U + a];
+    Minv[U * U] = C.ok ? 1.0 : 0.0;
+  }
+  cta_bcast_from_warp0<U * U + 1>(Minv, sh);
+  // pass 2: B = Gram^-1 A rows, noise part of the gradient
+  double part[2] = {0.0, 0.0};  // sigma-column sum, 0.5 |n|^2
+  if (live) {
+#pragma unroll 4
+    for (int k = cx.k0; k < cx.k1; ++k) {
+      const double dn = jac[U * Y + k], rd = rcp_fast(dn * dn), ni = qw[U + k];
+      double row[U];
+#pragma unroll
+      for (int a = 0; a < U; ++a) row[a] = jac[k * U + a];
+#pragma unroll
+      for (int a = 0; a < U; ++a) {
+        double t = 0.0;
+#pragma unroll
+        for (int b = 0; b < U; ++b) t = fma(row[b], Minv[b * U + a], t);
+        t *= rd;
+        B[k * U + a] = t;
+        if (a == M::SIGMA) {
+          part[0] = fma(t, dn * ni, part[0]);
+          g[U + k] = fma(t, dn, ni);
+        }
+      }
+      part[1] = fma(0.5 * ni, ni, part[1]);
+    }
+  }
+  cta_sum_to_warp0<2, NCH>(part, sh);
+  if (live && cx.wj == 0) {
+    gu[M::SIGMA] += (double)Y - ((double)U - trM) + part[0];
+#pragma unroll
+    for (int a = 0; a < U; ++a) g[a] = gu[a];
+    P.Dv(CD_NLD, i) = nld + part[1], P.Dv(CD_LOGDET, i) = ldv;
+    if (Minv[U * U] == 0.0) {  // hand the chain back at its last committed state
+      P.I(CT_STATUS, i) = MLB_ST_LINALG, P.I(CT_ALIVE, i) = 0;
+      const Col pw = col(p, ld, i);
+      const int Q = U + Y;
+#pragma unroll 4
+      for (int k = 0; k < Q; ++k) qw[k] = P.S.cq[k], pw[k] = P.S.cp[k];
+    }
   }
 }
 
@@ -159,45 +326,100 @@ __global__ void __launch_bounds__(kStreamBlock)
 }
 
 // [finish a fresh evaluation: add the second-order partials] [half kick] cotangent
-// projection [commit the step / record h_init]
-template <class M>
-__global__ void __launch_bounds__(kStreamBlock)
+// projection p -= J^T Gram^-1 J p [commit the step / record h_init]; observation-chunked
+template <class M, int NCH>
+__global__ void __launch_bounds__(32 * NCH)
     kp_kick_project(PhasedLayout L, int64_t n, int64_t ld, double* p, double* q, double dt,
                     const double* dt_pc, int fresh, int kick, int first, int commit) {
-  MLB_PH_INDEX();
-  if (!P.I(CT_ALIVE, i)) return;
   using S = Stream<M>;
   constexpr int U = M::U;
-  const int Y = L.Y, Q = U + Y;
-  const Col pw = col(p, ld, i), qw = col(q, ld, i);
-  if (fresh) {
+  extern __shared__ double sh[];
+  const int Y = L.Y;
+  const ChunkCtx cx = chunk_ctx<NCH>(n, Y);
+  const int64_t i = cx.in_range ? cx.i : 0;
+  const Phased P = L.at(i);
+  const bool live = cx.in_range && P.I(CT_ALIVE, i);
+  const Col pw = col(p, ld, i), qw = col(q, ld, i), jac = P.S.Jc, g = P.S.g, w = P.S.w;
+  double gfin[U], vu[U], acc[U + 1];  // acc: A^T D^-1 (J p) partial, |p|^2 partial (first)
 #pragma unroll
-    for (int d = 0; d < M::ND; ++d) {
-      double s = P.S.g[M::dir_u(d)];
-      for (int g = 0; g < M::NG; ++g) s += P.hpart[g * M::ND + d];
-      P.S.g[M::dir_u(d)] = s;
+  for (int r = 0; r < U + 1; ++r) acc[r] = 0.0;
+  const double hk = kick ? -0.5 * (dt_pc ? dt_pc[i] : dt) : 0.0;
+  if (live) {
+#pragma unroll
+    for (int a = 0; a < U; ++a) {
+      double t = g[a];
+      if (fresh) {
+        const int d = M::u_dir(a);
+        if (d >= 0)
+          for (int gi = 0; gi < M::NG; ++gi) t += P.hpart[gi * M::ND + d];
+      }
+      gfin[a] = t;
+      const double pa = pw[a];
+      if (first && cx.wj == 0) acc[U] = fma(pa, pa, acc[U]);
+      vu[a] = kick ? fma(hk, t, pa) : pa;
+    }
+#pragma unroll 4
+    for (int k = cx.k0; k < cx.k1; ++k) {
+      double pk = pw[U + k];
+      if (first) acc[U] = fma(pk, pk, acc[U]);
+      if (kick) pk = fma(hk, g[U + k], pk), pw[U + k] = pk;
+      const double dn = jac[U * Y + k];
+      double t = dn * pk, row[U];
+#pragma unroll
+      for (int a = 0; a < U; ++a) row[a] = jac[k * U + a], t = fma(row[a], vu[a], t);
+      w[k] = t;
+      const double wr = t * rcp_fast(dn * dn);
+#pragma unroll
+      for (int a = 0; a < U; ++a) acc[a] = fma(row[a], wr, acc[a]);
     }
   }
-  auto hamiltonian = [&]() {
-    double s = 0.0;
-#pragma unroll 4
-    for (int k = 0; k < Q; ++k) s = fma(pw[k], pw[k], s);
-    return P.Dv(CD_NLD, i) + P.Dv(CD_LOGDET, i) + 0.5 * s;
-  };
-  if (first) P.Dv(CD_HINIT, i) = P.Dv(CD_HLAST, i) = hamiltonian();
-  const double dti = dt_pc ? dt_pc[i] : dt;
-  if (kick) {
-#pragma unroll 4
-    for (int k = 0; k < Q; ++k) pw[k] = fma(-0.5 * dti, P.S.g[k], pw[k]);
+  cta_sum_to_warp0<U + 1, NCH>(acc, sh);
+  double tt[U];
+#pragma unroll
+  for (int a = 0; a < U; ++a) tt[a] = acc[a];
+  if (live && cx.wj == 0) {
+    if (first)
+      P.Dv(CD_HINIT, i) = P.Dv(CD_HLAST, i) = P.Dv(CD_NLD, i) + P.Dv(CD_LOGDET, i) + 0.5 * acc[U];
+    typename S::Chol C;
+    S::load_chol(P.S.Gc, C);
+    chol_solve<U>(C.L, C.rdiag, tt);
   }
-  typename S::Chol C;
-  S::load_chol(P.S.Gc, C);
-  S::project(Y, P.S.Jc, C, pw, P.S.w);
-  if (commit) {
+  cta_bcast_from_warp0<U>(tt, sh);
+  double su[U + 1];  // J^T x latent part, |p|^2 partial of the projected momentum
+#pragma unroll
+  for (int r = 0; r < U + 1; ++r) su[r] = 0.0;
+  if (live) {
 #pragma unroll 4
-    for (int k = 0; k < Q; ++k) P.S.cq[k] = qw[k], P.S.cp[k] = pw[k];
-    P.Dv(CD_HLAST, i) = hamiltonian();
-    P.I(CT_DONE, i) += 1;
+    for (int k = cx.k0; k < cx.k1; ++k) {
+      const double dn = jac[U * Y + k];
+      double t = w[k], row[U];
+#pragma unroll
+      for (int a = 0; a < U; ++a) row[a] = jac[k * U + a], t = fma(-row[a], tt[a], t);
+      const double x = t * rcp_fast(dn * dn);
+#pragma unroll
+      for (int a = 0; a < U; ++a) su[a] = fma(row[a], x, su[a]);
+      const double pk = fma(-dn, x, pw[U + k]);
+      pw[U + k] = pk;
+      if (commit) {
+        P.S.cq[U + k] = qw[U + k], P.S.cp[U + k] = pk;
+        su[U] = fma(pk, pk, su[U]);
+      }
+    }
+  }
+  cta_sum_to_warp0<U + 1, NCH>(su, sh);
+  if (live && cx.wj == 0) {
+    double hs = su[U];
+#pragma unroll
+    for (int a = 0; a < U; ++a) {
+      const double pa = vu[a] - su[a];
+      pw[a] = pa;
+      if (fresh) g[a] = gfin[a];
+      if (commit) P.S.cq[a] = qw[a], P.S.cp[a] = pa, hs = fma(pa, pa, hs);
+    }
+    if (commit) {
+      P.Dv(CD_HLAST, i) = P.Dv(CD_NLD, i) + P.Dv(CD_LOGDET, i) + 0.5 * hs;
+      P.I(CT_DONE, i) += 1;
+    }
   }
 }
 
@@ -220,65 +442,108 @@ __global__ void __launch_bounds__(kStreamBlock)
 }
 
 // one solver iteration after its sweep: |c|, direction, update, new |dq|, and whether the
-// chain iterates again (the loop condition of systems.py:215-227 for the NEXT pass)
-template <class M, int SOLVER>
-__global__ void __launch_bounds__(kStreamBlock)
+// chain iterates again (the loop condition of systems.py:215-227 for the NEXT pass);
+// observation-chunked
+template <class M, int SOLVER, int NCH>
+__global__ void __launch_bounds__(32 * NCH)
     kp_update(PhasedLayout L, int64_t n, Opts o, int* counter) {
-  MLB_PH_INDEX();
-  if (!P.I(CT_ACTIVE, i)) return;
   using S = Stream<M>;
   constexpr int U = M::U;
+  constexpr bool QN = SOLVER == MLB_SOLVER_QUASI_NEWTON;
+  constexpr int NA = QN ? U : U * U + U;  // [mat U x U,] rhs U
+  extern __shared__ double sh[];
   const int Y = L.Y;
+  const ChunkCtx cx = chunk_ctx<NCH>(n, Y);
+  const int64_t i = cx.in_range ? cx.i : 0;
+  const Phased P = L.at(i);
+  const bool live = cx.in_range && P.I(CT_ACTIVE, i);
   const Col q = P.S.qs, mu = P.S.mu, c = P.S.c, jp = P.S.Jc;
-  const Col jl = SOLVER == MLB_SOLVER_QUASI_NEWTON ? P.S.Jc : P.S.Jt;
-  double s[U], du[U], u[U];
-  S::load_u(q, u);
-  double eacc = 0.0;
-#pragma unroll 4
-  for (int k = 0; k < Y; ++k) eacc = norm_accum(eacc, c[k], o.norm);
-  const double err = norm_finish(eacc, o.norm);
-  if (SOLVER == MLB_SOLVER_QUASI_NEWTON) {
-    typename S::Chol Cp;
-    S::load_chol(P.S.Gc, Cp);
+  const Col jl = QN ? P.S.Jc : P.S.Jt;
+  // pass 1: |c|, capacitance matrix of (J_l, J_prev) and right-hand side over the chunk
+  double acc[NA], eacc = 0.0;
 #pragma unroll
-    for (int a = 0; a < U; ++a) s[a] = 0.0;
-#pragma unroll 4
-    for (int k = 0; k < Y; ++k) {
-      const double dn = jp[U * Y + k], cr = c[k] * rcp_fast(dn * dn);
+  for (int r = 0; r < NA; ++r) acc[r] = 0.0;
+  if (live) {
+#pragma unroll 2
+    for (int k = cx.k0; k < cx.k1; ++k) {
+      const double ck = c[k];
+      eacc = norm_accum(eacc, ck, o.norm);
+      const double rd = rcp_fast(jl[U * Y + k] * jp[U * Y + k]), wr = ck * rd;
+      if (QN) {
 #pragma unroll
-      for (int a = 0; a < U; ++a) s[a] = fma(jp[k * U + a], cr, s[a]);
-    }
-    chol_solve<U>(Cp.L, Cp.rdiag, s);
-  } else {
-    if (!S::inv_jacprod_core(Y, jl, jp, c, s)) {
+        for (int a = 0; a < U; ++a) acc[a] = fma(jp[k * U + a], wr, acc[a]);
+      } else {
+        double rl[U];
 #pragma unroll
-      for (int a = 0; a < U; ++a) s[a] = nan("");
+        for (int b = 0; b < U; ++b) rl[b] = jl[k * U + b] * rd;
+#pragma unroll
+        for (int a = 0; a < U; ++a) {
+          const double ra = jp[k * U + a];
+          acc[U * U + a] = fma(ra, wr, acc[U * U + a]);
+#pragma unroll
+          for (int b = 0; b < U; ++b) acc[a * U + b] = fma(ra, rl[b], acc[a * U + b]);
+        }
+      }
     }
   }
+  cta_sum_to_warp0<NA, NCH>(acc, sh);
+  eacc = cta_norm_to_warp0<NCH>(eacc, o.norm, sh);
+  double s[U];
+#pragma unroll
+  for (int a = 0; a < U; ++a) s[a] = 0.0;
+  if (live && cx.wj == 0) {
+    if (QN) {
+      typename S::Chol Cp;
+      S::load_chol(P.S.Gc, Cp);
+#pragma unroll
+      for (int a = 0; a < U; ++a) s[a] = acc[a];
+      chol_solve<U>(Cp.L, Cp.rdiag, s);
+    } else {
+      double mat[U][U];
+#pragma unroll
+      for (int a = 0; a < U; ++a) {
+        s[a] = acc[U * U + a];
+#pragma unroll
+        for (int b = 0; b < U; ++b) mat[a][b] = acc[a * U + b] + (a == b ? 1.0 : 0.0);
+      }
+      if (!lu_solve<U>(mat, s)) {
+#pragma unroll
+        for (int a = 0; a < U; ++a) s[a] = nan("");
+      }
+    }
+  }
+  cta_bcast_from_warp0<U>(s, sh);
+  // pass 2: x = (c - A_l s) / D, update of the noise coordinates, J_prev^T x latent part
+  double du[U], nacc = 0.0;
 #pragma unroll
   for (int a = 0; a < U; ++a) du[a] = 0.0;
-  double nacc = 0.0;
+  if (live) {
 #pragma unroll 4
-  for (int k = 0; k < Y; ++k) {
-    const double x = S::inv_jacprod_x(Y, k, jl, jp, c[k], s);
+    for (int k = cx.k0; k < cx.k1; ++k) {
+      const double x = S::inv_jacprod_x(Y, k, jl, jp, c[k], s);
 #pragma unroll
-    for (int a = 0; a < U; ++a) du[a] = fma(jp[k * U + a], x, du[a]);
-    const double dni = jp[U * Y + k] * x;
-    q[U + k] -= dni, mu[U + k] += dni;
-    nacc = norm_accum(nacc, dni, o.norm);
+      for (int a = 0; a < U; ++a) du[a] = fma(jp[k * U + a], x, du[a]);
+      const double dni = jp[U * Y + k] * x;
+      q[U + k] -= dni, mu[U + k] += dni;
+      nacc = norm_accum(nacc, dni, o.norm);
+    }
   }
+  cta_sum_to_warp0<U, NCH>(du, sh);
+  nacc = cta_norm_to_warp0<NCH>(nacc, o.norm, sh);
+  if (live && cx.wj == 0) {
 #pragma unroll
-  for (int a = 0; a < U; ++a) {
-    q[a] = u[a] - du[a];
-    mu[a] += du[a];
-    nacc = norm_accum(nacc, du[a], o.norm);
+    for (int a = 0; a < U; ++a) {
+      q[a] -= du[a];
+      mu[a] += du[a];
+      nacc = norm_accum(nacc, du[a], o.norm);
+    }
+    const double ndq = norm_finish(nacc, o.norm), err = norm_finish(eacc, o.norm);
+    const int iters = P.I(CT_ITERS, i) + 1;
+    P.I(CT_ITERS, i) = iters, P.Dv(CD_NDQ, i) = ndq, P.Dv(CD_ERR, i) = err;
+    const bool again = keep_iterating(iters, ndq, err, o);
+    P.I(CT_ACTIVE, i) = again;
+    if (again) atomicAdd(counter, 1);
   }
-  const double ndq = norm_finish(nacc, o.norm);
-  const int iters = P.I(CT_ITERS, i) + 1;
-  P.I(CT_ITERS, i) = iters, P.Dv(CD_NDQ, i) = ndq, P.Dv(CD_ERR, i) = err;
-  const bool again = keep_iterating(iters, ndq, err, o);
-  P.I(CT_ACTIVE, i) = again;
-  if (again) atomicAdd(counter, 1);
 }
 
 // close a solve: mu / dt, classification (solvers.py:81-95), then either accept the
@@ -347,6 +612,12 @@ int phased_leapfrog_steps(const mlb_model* m, const OdeData& D, int64_t n, int64
   }
   int* host_count = m->pinned_word;
   const dim3 blk(kStreamBlock), g1(sgrid(n)), g_role(sgrid(n), M::N_ROLE), g_grp(sgrid(n), M::NG);
+  constexpr int NCH = kChunkWarps;
+  const dim3 cblk(32, NCH);
+  // dynamic shared memory of the chunked kernels: [rows][32] doubles
+  constexpr size_t sh_eval = sizeof(double) * 32 * (U * U + 1);
+  constexpr size_t sh_proj = sizeof(double) * 32 * (U + 1 > NCH ? U + 1 : NCH);
+  constexpr size_t sh_upd = sizeof(double) * 32 * (U * U + U > NCH ? U * U + U : NCH);
   auto launched = [&]() { return finish_launch(); };
 #define MLB_KP(call)                    \
   do {                                  \
@@ -367,17 +638,17 @@ int phased_leapfrog_steps(const mlb_model* m, const OdeData& D, int64_t n, int64
       const bool fresh = first || sub == 1;
       if (fresh) {  // evaluate at the working position
         MLB_KP((kp_jacob<M, true><<<g_role, blk, 0, s>>>(D, L, n, ld, io.q)));
-        MLB_KP((kp_eval_mid<M><<<g1, blk, 0, s>>>(D, L, n, ld, io.q, io.p)));
+        MLB_KP((kp_eval_mid<M, NCH><<<g1, cblk, sh_eval, s>>>(D, L, n, ld, io.q, io.p)));
         MLB_KP((kp_second_order<M><<<g_grp, blk, 0, s>>>(D, L, n, ld, io.q)));
       }
       if (io.n_step <= 0) {  // only h_init is wanted
-        MLB_KP((kp_kick_project<M><<<g1, blk, 0, s>>>(L, n, ld, io.p, io.q, io.dt, io.dt_pc,
+        MLB_KP((kp_kick_project<M, NCH><<<g1, cblk, sh_proj, s>>>(L, n, ld, io.p, io.q, io.dt, io.dt_pc,
                                                       1, 0, 1, 0)));
         first = false;
         break;
       }
       // note: with first == true the Hamiltonian is recorded BEFORE the kick
-      MLB_KP((kp_kick_project<M><<<g1, blk, 0, s>>>(L, n, ld, io.p, io.q, io.dt, io.dt_pc,
+      MLB_KP((kp_kick_project<M, NCH><<<g1, cblk, sh_proj, s>>>(L, n, ld, io.p, io.q, io.dt, io.dt_pc,
                                                     fresh, sub != 1, first, sub == 2)));
       first = false;
       if (sub == 2) break;
@@ -390,7 +661,7 @@ int phased_leapfrog_steps(const mlb_model* m, const OdeData& D, int64_t n, int64
           MLB_KP((kp_constr<M><<<g1, blk, 0, s>>>(D, L, n)));
         else
           MLB_KP((kp_jacob<M, false><<<g_role, blk, 0, s>>>(D, L, n, ld, io.q)));
-        MLB_KP((kp_update<M, SOLVER><<<g1, blk, 0, s>>>(L, n, o, counter)));
+        MLB_KP((kp_update<M, SOLVER, NCH><<<g1, cblk, sh_upd, s>>>(L, n, o, counter)));
         active = read_counter();
       }
       if (active < 0) {

@@ -408,3 +408,36 @@ def test_fast_math_primitives():
         C.c_int64(x.size), C.c_void_p((-xd).data_ptr()), C.c_void_p(r.data_ptr()),
         C.c_void_p(s.data_ptr()), C.c_void_p(rs.data_ptr()), mlb._lib.stream_ptr()))
     assert np.array_equal(cpu(r), neg)
+
+
+def test_branch_free_exp_expm1():
+    """Straight-line exp / expm1 used by the Hodgkin-Huxley recurrence
+    (csrc/mlb_common.cuh) against mpmath-grade references (numpy long double where
+    available, else float64 libm): <= 2 ulp (exp), <= 3 ulp (expm1) on [-700, 700], dense
+    sampling around 0 where expm1 cancels, NaN propagated."""
+    import ctypes as C
+
+    mlb = _mlb()
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.uniform(-700, 700, 200000), rng.uniform(-40, 40, 200000),
+                        rng.uniform(-1, 1, 200000), 10.0 ** rng.uniform(-300, 0, 50000),
+                        -(10.0 ** rng.uniform(-300, 0, 50000)),
+                        [0.0, -0.0, 0.5 * np.log(2), -0.5 * np.log(2), 700.0, -700.0]])  # fmt: skip
+    xd = torch.as_tensor(x, device="cuda")
+    e, em1 = torch.empty_like(xd), torch.empty_like(xd)
+    mlb._lib.check(mlb._lib.lib().mlb_selftest_exp(
+        C.c_int64(x.size), C.c_void_p(xd.data_ptr()), C.c_void_p(e.data_ptr()),
+        C.c_void_p(em1.data_ptr()), mlb._lib.stream_ptr()))
+    xl = x.astype(np.longdouble)
+    ref_e, ref_m = np.exp(xl), np.expm1(xl)
+    eps = np.finfo(np.float64).eps
+    assert np.abs((cpu(e).astype(np.longdouble) - ref_e) / ref_e).max() < 2 * eps
+    nz = x != 0.0
+    assert np.abs((cpu(em1)[nz].astype(np.longdouble) - ref_m[nz]) / ref_m[nz]).max() < 3 * eps
+    assert (cpu(em1)[~nz] == 0.0).all()
+    bad = torch.tensor([float("nan")], dtype=torch.float64, device="cuda")
+    mlb._lib.check(mlb._lib.lib().mlb_selftest_exp(
+        C.c_int64(1), C.c_void_p(bad.data_ptr()), C.c_void_p(e.data_ptr()),
+        C.c_void_p(em1.data_ptr()), mlb._lib.stream_ptr()))
+    assert np.isnan(cpu(e)[0]) and np.isnan(cpu(em1)[0])
+

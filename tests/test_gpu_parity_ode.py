@@ -131,7 +131,8 @@ def test_fn_fused_leapfrog_steps_match_oracle(solver):
     assert ok.mean() > 0.8
     assert scaled_err(cpu(out.pos)[ok], ref["q"][ok]) < 1e-9
     assert scaled_err(cpu(out.mom)[ok], ref["p"][ok]) < 1e-6  # cond(C) ~ 1e10 projections
-    assert rel_err(cpu(out.h_init), ref["h_init"]) < TOL
+    # h = nld + 0.5 log det + 0.5 |p|^2 cancels terms of size 1e3-1e4 down to O(1)
+    assert rel_err(cpu(out.h_init), ref["h_init"]) < 1e-9
     assert rel_err(cpu(out.h_final)[ok], ref["h_final"][ok]) < 1e-9
 
 
@@ -373,9 +374,9 @@ def test_fn_host_buffer_entry_point():
 def test_phased_path_matches_single_kernel(model, solver):
     """mlb_leapfrog_steps runs the ODE family as a sequence of sub-phase kernels with the
     sweeps split over sensitivity directions / pair groups (default) or as one kernel
-    (MLB_FLAG_SINGLE_KERNEL).  Same device functions, same order of operations per chain:
-    statuses and iteration counts are identical and the states agree to rounding of the
-    few expressions the two drivers contract differently."""
+    (MLB_FLAG_SINGLE_KERNEL).  Same model sweeps; the Y-sized reductions are summed per
+    observation chunk in the sub-phase kernels, so the two agree to rounding: statuses
+    and (away from tolerance ties) iteration counts are identical."""
     if model == "fn":
         mlb, g, cm, gm, gs = fn_case()
         q = fn_states(cm, 96)
@@ -405,7 +406,9 @@ def test_phased_path_matches_single_kernel(model, solver):
     assert ok.mean() > 0.5
     assert scaled_err(cpu(a.pos)[ok], cpu(b.pos)[ok]) < tol_q
     assert scaled_err(cpu(a.mom)[ok], cpu(b.mom)[ok]) < tol_p
-    assert rel_err(cpu(a.h_init), cpu(b.h_init)) < 1e-12
+    # the observation-chunked kernels add the same terms in a different order, and h
+    # cancels terms of size 1e3-1e4 down to O(1)
+    assert rel_err(cpu(a.h_init), cpu(b.h_init)) < 1e-9
     assert rel_err(cpu(a.h_final)[ok], cpu(b.h_final)[ok]) < 1e-8
     # failed chains are handed back at their last committed state by both paths
     bad = cpu(a.status) != 0
