@@ -54,8 +54,8 @@ MLB_DEV double sqrt_rsqrt_fast(double s, double& rs) {
 // ends the basic block and makes the thread run them back to back (~200 cycles of
 // dependent latency apiece, measured 4300 cycles per ODE step for one warp).  These are
 // straight-line (Cody-Waite reduction to |r| <= ln2/2, degree-13 Taylor polynomial
-// (remainder < 5e-18), scaling by a constructed power of two), so the compiler's
-// scheduler interleaves the independent evaluations.  Arguments are clamped to
+// (remainder < 5e-18), scaling by a constructed power of two) and short (~12 dependent
+// fp64 operations).  Arguments are clamped to
 // [-700, 700] (no overflow / subnormal handling); NaN propagates, +-inf gives NaN.  Error <= ~1 ulp (exp),
 // <= ~2 ulp (expm1), checked against the libdevice functions by
 // tests/test_gpu_parity.py::test_fast_math_primitives.
@@ -69,20 +69,18 @@ MLB_DEV void exp_reduce(double x, double& r, double& scale) {
   const int k = __double2loint(t);
   scale = __hiloint2double((k + 1023) << 20, 0);
 }
-MLB_DEV double exp_poly_tail(double r) {  // (exp(r) - 1 - r) / r^2
-  double q = 1.0 / 6227020800.0;          // 1/13!
-  q = fma(q, r, 1.0 / 479001600.0);
-  q = fma(q, r, 1.0 / 39916800.0);
-  q = fma(q, r, 1.0 / 3628800.0);
-  q = fma(q, r, 1.0 / 362880.0);
-  q = fma(q, r, 1.0 / 40320.0);
-  q = fma(q, r, 1.0 / 5040.0);
-  q = fma(q, r, 1.0 / 720.0);
-  q = fma(q, r, 1.0 / 120.0);
-  q = fma(q, r, 1.0 / 24.0);
-  q = fma(q, r, 1.0 / 6.0);
-  q = fma(q, r, 0.5);
-  return q;
+// (exp(r) - 1 - r) / r^2 = sum_{k<12} r^k / (k+2)!, Estrin's scheme: 5 dependent levels
+// instead of Horner's 12 (the evaluation sits on the critical path of the recurrence)
+MLB_DEV double exp_poly_tail(double r) {
+  const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+  const double p01 = fma(r, 1.0 / 6.0, 0.5);
+  const double p23 = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+  const double p45 = fma(r, 1.0 / 5040.0, 1.0 / 720.0);
+  const double p67 = fma(r, 1.0 / 362880.0, 1.0 / 40320.0);
+  const double p89 = fma(r, 1.0 / 39916800.0, 1.0 / 3628800.0);
+  const double pab = fma(r, 1.0 / 6227020800.0, 1.0 / 479001600.0);
+  const double q0 = fma(r2, p23, p01), q1 = fma(r2, p67, p45), q2 = fma(r2, pab, p89);
+  return fma(r8, q2, fma(r4, q1, q0));
 }
 MLB_DEV double exp_bl(double x) {
   double r, s;

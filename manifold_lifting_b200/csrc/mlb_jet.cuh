@@ -142,6 +142,32 @@ MLB_DEV double jexp(double x) { return exp_bl(x); }
 MLB_DEV double jexpm1(double x) { return expm1_bl(x); }
 MLB_DEV double jrecip(double x) { return rcp_fast(x); }
 
+// A scalar / jet as JetSize<T>::value doubles at base[j * stride] (exchange of recurrence
+// state between the warps that share a chain batch)
+template <class T>
+struct JetSize {
+  static constexpr int value = 1;
+};
+MLB_JET_T struct JetSize<MLB_JET> {
+  static constexpr int value = 1 + N + NP;
+};
+MLB_DEV void jet_store(const double& x, double* base, int) { base[0] = x; }
+MLB_DEV void jet_load(double& x, const double* base, int) { x = base[0]; }
+MLB_JET_T MLB_DEV void jet_store(const MLB_JET& x, double* base, int stride) {
+  base[0] = x.v;
+#pragma unroll
+  for (int a = 0; a < N; ++a) base[(1 + a) * stride] = x.g[a];
+#pragma unroll
+  for (int k = 0; k < NP; ++k) base[(1 + N + k) * stride] = x.h[k];
+}
+MLB_JET_T MLB_DEV void jet_load(MLB_JET& x, const double* base, int stride) {
+  x.v = base[0];
+#pragma unroll
+  for (int a = 0; a < N; ++a) x.g[a] = base[(1 + a) * stride];
+#pragma unroll
+  for (int k = 0; k < NP; ++k) x.h[k] = base[(1 + N + k) * stride];
+}
+
 // constants / seeded variables of either scalar type
 template <class T>
 struct JetOps;

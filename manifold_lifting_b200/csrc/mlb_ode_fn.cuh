@@ -25,6 +25,9 @@ struct FnOde {
   static constexpr int U = 9, ND = 8, NPAIR = ND * (ND + 1) / 2, SIGMA = 6;
   static constexpr int NG = 6, PAIRS_PER_GROUP = NPAIR / NG;  // second-order pass split
   static constexpr int ROLE_DIRS = 2, N_ROLE = ND / ROLE_DIRS;  // Jacobian sweep split
+  static constexpr int GATE_WARPS = 1;  // no cooperative sweep: the RK4 stages are short
+  template <int NS1, int NP>
+  static constexpr int xch_doubles() { return 0; }
   static_assert(NPAIR % NG == 0, "pair groups must be equal-sized");
 
   struct Th {
@@ -172,8 +175,9 @@ struct FnOde {
 
   // Integrates over the schedule; obs(i, state) is called at every observation.
   // NS1 first-order directions starting at D0 (0 = primal only); NP pairs starting at P0.
-  template <int NS1, int NP, int P0, class F, int D0 = 0>
-  static MLB_DEV void sweep(const OdeData& D, const double (&u)[U], F&& obs) {
+  template <int NS1, int NP, int P0, class F, int D0 = 0, int GW = 1>
+  static MLB_DEV void sweep(const OdeData& D, const double (&u)[U], F&& obs, double* = nullptr) {
+    static_assert(GW == 1, "FitzHugh-Nagumo sweeps are not cooperative");
     const Th t = theta(u);
     Aug<NS1, NP, P0> y, acc, ys;
     y.x[0] = u[7], y.x[1] = u[8];

@@ -39,6 +39,7 @@ struct HhOde {
   static constexpr int U = 7, ND = 6, NPAIR = ND * (ND + 1) / 2, SIGMA = 6;
   static constexpr int NG = 7, PAIRS_PER_GROUP = NPAIR / NG;
   static constexpr int ROLE_DIRS = 1, N_ROLE = ND / ROLE_DIRS;  // Jacobian sweep split
+  static constexpr int GATE_WARPS = 4;  // warps sharing one chain batch in a cooperative sweep
   static_assert(NPAIR % NG == 0, "pair groups must be equal-sized");
   static MLB_DEV int dir_u(int d) { return d; }
   static MLB_DEV int u_dir(int a) { return a < ND ? a : -1; }  // inverse (-1: sigma)
@@ -100,17 +101,28 @@ struct HhOde {
   struct Rates {
     T an, bn, am, bm, ah, bh;
   };
-  template <class T>
-  static MLB_DEV Rates<T> rates(const OdeData& D, const T& v, const Par<T>& p) {
+  // opening / closing rates of one gate (GATE 0: n, 1: m, 2: h) at potential v
+  template <int GATE, class T>
+  static MLB_DEV void gate_rates(const OdeData& D, const T& v, const Par<T>& p, T& a, T& b) {
     const double* K = D.consts;
     const T w = v - p.v_t;
+    if constexpr (GATE == 0) {
+      a = (K[HH_k_alpha_n_1] * K[HH_k_alpha_n_3]) * xoe((w - K[HH_k_alpha_n_2]) * (-K[HH_r_alpha_n_3]));
+      b = K[HH_k_beta_n_1] * jexp((w - K[HH_k_beta_n_2]) * (-K[HH_r_beta_n_3]));
+    } else if constexpr (GATE == 1) {
+      a = (K[HH_k_alpha_m_1] * K[HH_k_alpha_m_3]) * xoe((w - K[HH_k_alpha_m_2]) * (-K[HH_r_alpha_m_3]));
+      b = (K[HH_k_beta_m_1] * K[HH_k_beta_m_3]) * xoe((w - K[HH_k_beta_m_2]) * K[HH_r_beta_m_3]);
+    } else {
+      a = K[HH_k_alpha_h_1] * jexp((w - K[HH_k_alpha_h_2]) * (-K[HH_r_alpha_h_3]));
+      b = K[HH_k_beta_h_1] * jrecip(jexp((w - K[HH_k_beta_h_2]) * (-K[HH_r_beta_h_3])) + 1.0);
+    }
+  }
+  template <class T>
+  static MLB_DEV Rates<T> rates(const OdeData& D, const T& v, const Par<T>& p) {
     Rates<T> r;
-    r.an = (K[HH_k_alpha_n_1] * K[HH_k_alpha_n_3]) * xoe((w - K[HH_k_alpha_n_2]) * (-K[HH_r_alpha_n_3]));
-    r.bn = K[HH_k_beta_n_1] * jexp((w - K[HH_k_beta_n_2]) * (-K[HH_r_beta_n_3]));
-    r.am = (K[HH_k_alpha_m_1] * K[HH_k_alpha_m_3]) * xoe((w - K[HH_k_alpha_m_2]) * (-K[HH_r_alpha_m_3]));
-    r.bm = (K[HH_k_beta_m_1] * K[HH_k_beta_m_3]) * xoe((w - K[HH_k_beta_m_2]) * K[HH_r_beta_m_3]);
-    r.ah = K[HH_k_alpha_h_1] * jexp((w - K[HH_k_alpha_h_2]) * (-K[HH_r_alpha_h_3]));
-    r.bh = K[HH_k_beta_h_1] * jrecip(jexp((w - K[HH_k_beta_h_2]) * (-K[HH_r_beta_h_3])) + 1.0);
+    gate_rates<0>(D, v, p, r.an, r.bn);
+    gate_rates<1>(D, v, p, r.am, r.bm);
+    gate_rates<2>(D, v, p, r.ah, r.bh);
     return r;
   }
   template <class T>
@@ -119,10 +131,20 @@ struct HhOde {
     return jrecip(1.0 + jexp((K[HH_k_p_infinity_1] - v) * K[HH_r_p_infinity_2]));
   }
 
-  template <class T, class F, int D0 = 0>
-  static MLB_DEV void integrate(const OdeData& D, const double (&u)[U], F&& obs) {
+  // GW = 1: one thread advances the whole recurrence.  GW = GATE_WARPS (= 4): the CTA is
+  // (32 chains) x (4 warps); every warp advances the membrane potential (it needs all four
+  // gating variables) but only ITS OWN gate (threadIdx.y: n, m, h, p), whose new value it
+  // publishes through shared memory `xch` ([2][4][JetSize][32] doubles, double-buffered:
+  // one __syncthreads per step).  A step's critical path drops from 10 exp + 3 expm1 + 11
+  // reciprocals to those of the potential plus one gate (sweeps of a 1,024-chain batch are
+  // latency-bound: 32 warps x roles on 592 schedulers).  obs is called by warp 0 only.
+  template <class T, class F, int D0 = 0, int GW = 1>
+  static MLB_DEV void integrate(const OdeData& D, const double (&u)[U], F&& obs,
+                                double* xch = nullptr) {
     const double* K = D.consts;
     const Par<T> p = params<T, D0>(u);
+    const int gate = GW > 1 ? (int)threadIdx.y : 0;
+    constexpr int JS = JetSize<T>::value;
     T v = Ops<T>::constant(K[HH_E_leak]);
     T n, m, h, pp;
     {  // steady state at v = E_leak (:125-139)
@@ -132,7 +154,7 @@ struct HhOde {
       h = r.ah * jrecip(r.ah + r.bh);
       pp = p_infinity<T>(D, v);
     }
-    int next = 0;
+    int next = 0, buf = 0;
     int next_step = D.Y > 0 ? __ldg(D.obs_step) : -1;
 #pragma unroll 1
     for (int s = 0; s < D.n_steps && next < D.Y; ++s) {
@@ -148,29 +170,48 @@ struct HhOde {
                       tau_v * K[HH_r_c_m];
       const T v_ = v_inf + (v - v_inf) * jexp(g_tot * (-dt * K[HH_r_c_m]));  // exp(-dt / tau_v)
       // :161-173  gates, rates evaluated at the NEW potential
-      const Rates<T> r = rates<T>(D, v_, p);
-      {
-        const T sn = r.an + r.bn, n_inf = r.an * jrecip(sn);
+      if (GW == 1 || gate == 0) {
+        T a, b;
+        gate_rates<0>(D, v_, p, a, b);
+        const T sn = a + b, n_inf = a * jrecip(sn);
         n = n_inf + (n - n_inf) * jexp(sn * (-dt));  // tau_n = 1 / (a_n + b_n)
       }
-      {
-        const T sm = r.am + r.bm, m_inf = r.am * jrecip(sm);
+      if (GW == 1 || gate == 1) {
+        T a, b;
+        gate_rates<1>(D, v_, p, a, b);
+        const T sm = a + b, m_inf = a * jrecip(sm);
         m = m_inf + (m - m_inf) * jexp(sm * (-dt));
       }
-      {
-        const T sh = r.ah + r.bh, h_inf = r.ah * jrecip(sh);
+      if (GW == 1 || gate == 2) {
+        T a, b;
+        gate_rates<2>(D, v_, p, a, b);
+        const T sh = a + b, h_inf = a * jrecip(sh);
         h = h_inf + (h - h_inf) * jexp(sh * (-dt));
       }
-      {
+      if (GW == 1 || gate == 3) {
         const T p_inf = p_infinity<T>(D, v_);
         // tau_p = k_tau_p_1 / (k2 e + 1 / e), e = exp((v + k3) / k4)   (:104-114)
         const T e = jexp((v_ + K[HH_k_tau_p_3]) * K[HH_r_tau_p_4]);
         const T rate = (K[HH_k_tau_p_2] * e + jrecip(e)) * jrecip(p.k_tau_p_1);
         pp = p_inf + (pp - p_inf) * jexp(rate * (-dt));
       }
+      if constexpr (GW > 1) {
+        double* mine = xch + ((buf * GW + gate) * JS) * 32 + threadIdx.x;
+        if (gate == 0) jet_store(n, mine, 32);
+        else if (gate == 1) jet_store(m, mine, 32);
+        else if (gate == 2) jet_store(h, mine, 32);
+        else jet_store(pp, mine, 32);
+        __syncthreads();
+        const double* all = xch + (buf * GW * JS) * 32 + threadIdx.x;
+        if (gate != 0) jet_load(n, all + 0 * JS * 32, 32);
+        if (gate != 1) jet_load(m, all + 1 * JS * 32, 32);
+        if (gate != 2) jet_load(h, all + 2 * JS * 32, 32);
+        if (gate != 3) jet_load(pp, all + 3 * JS * 32, 32);
+        buf ^= 1;
+      }
       v = v_;
       while (s == next_step) {
-        obs(next, v);
+        if (GW == 1 || gate == 0) obs(next, v);
         ++next;
         next_step = next < D.Y ? __ldg(D.obs_step + next) : -1;
       }
@@ -184,15 +225,23 @@ struct HhOde {
 
   // same interface as FnOde::sweep (see mlb_stream.cuh): NS1 first-order directions
   // starting at D0 (0 = value only), NP second-order pairs starting at pair index P0
-  template <int NS1, int NP, int P0, class F, int D0 = 0>
-  static MLB_DEV void sweep(const OdeData& D, const double (&u)[U], F&& obs) {
+  // GW > 1: cooperative form for a (32, GW) CTA, xch = shared exchange buffer of
+  // xch_doubles<NS1, NP>() doubles (see integrate); obs runs in warp 0 only
+  template <int NS1, int NP>
+  static constexpr int xch_doubles() {
+    return 2 * GATE_WARPS * (1 + NS1 + NP) * 32;
+  }
+  template <int NS1, int NP, int P0, class F, int D0 = 0, int GW = 1>
+  static MLB_DEV void sweep(const OdeData& D, const double (&u)[U], F&& obs,
+                            double* xch = nullptr) {
     static_assert(NP == 0 || (D0 == 0 && NS1 == ND), "pairs need every direction");
     if constexpr (NS1 == 0) {
-      integrate<double>(D, u, [&](int i, const double& v) {
+      auto cb = [&](int i, const double& v) {
         ObsView<0, 0> o;
         o.x[0] = v;
         obs(i, o);
-      });
+      };
+      integrate<double, decltype(cb)&, 0, GW>(D, u, cb, xch);
     } else {
       using T = DJet<NS1, NP, P0>;
       auto cb = [&](int i, const T& v) {
@@ -204,7 +253,7 @@ struct HhOde {
         for (int k = 0; k < NP; ++k) o.X[k][0] = v.h[k];
         obs(i, o);
       };
-      integrate<T, decltype(cb)&, D0>(D, u, cb);
+      integrate<T, decltype(cb)&, D0, GW>(D, u, cb, xch);
     }
   }
 };

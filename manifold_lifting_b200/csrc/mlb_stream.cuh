@@ -117,8 +117,11 @@ struct Stream {
   // One ROLE of a Jacobian sweep split over threads: integrates the state plus the NDR
   // sensitivity directions D0 .. D0+NDR-1 and writes those dy_du columns; the role with
   // BASE also writes the residual, the sigma column and dy_dn (systems.py:568-580).
-  template <int D0, int NDR, bool BASE>
-  MLB_DEV static void jacob_role(const OdeData& D, const Col& q, const Col& jac, const Col& c) {
+  // GW > 1: cooperative sweep of a (32, GW) CTA (see HhOde::integrate), xch its shared
+  // exchange buffer; the callback (all stores) runs in warp 0 only.
+  template <int D0, int NDR, bool BASE, int GW = 1>
+  MLB_DEV static void jacob_role(const OdeData& D, const Col& q, const Col& jac, const Col& c,
+                                 double* xch = nullptr) {
     double u[U];
     load_u(q, u);
     const double sig = M::sigma(u);
@@ -133,7 +136,7 @@ struct Stream {
         jac[U * Y + i] = sig;
       }
     };
-    M::template sweep<NDR, 0, 0, decltype(cb)&, D0>(D, u, cb);
+    M::template sweep<NDR, 0, 0, decltype(cb)&, D0, GW>(D, u, cb, xch);
   }
 
   // ---- block algebra ----------------------------------------------------------------
@@ -392,14 +395,14 @@ struct Stream {
     }(std::make_integer_sequence<int, M::NG>{});
   }
 
-  template <int G>
+  template <int G, int GW = 1>
   MLB_DEV static void second_order_group(const OdeData& D, const double (&u)[U], const Col& B,
-                                         double (&gu)[U]) {
+                                         double (&gu)[U], double* xch = nullptr) {
     constexpr int NP = M::PAIRS_PER_GROUP, P0 = G * NP;
     double h[M::ND];
 #pragma unroll
     for (int d = 0; d < M::ND; ++d) h[d] = 0.0;
-    M::template sweep<M::ND, NP, P0>(D, u, [&](int i, const auto& st) {
+    auto cb = [&](int i, const auto& st) {
       double b[M::ND];
 #pragma unroll
       for (int d = 0; d < M::ND; ++d) b[d] = B[i * U + M::dir_u(d)];
@@ -412,7 +415,8 @@ struct Stream {
             }(),
             ...);
       }(std::make_integer_sequence<int, NP>{});
-    });
+    };
+    M::template sweep<M::ND, NP, P0, decltype(cb)&, 0, GW>(D, u, cb, xch);
 #pragma unroll
     for (int d = 0; d < M::ND; ++d) gu[M::dir_u(d)] += h[d];
   }

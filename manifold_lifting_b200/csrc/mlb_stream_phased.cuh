@@ -157,10 +157,13 @@ __global__ void __launch_bounds__(kStreamBlock)
 
 // Jacobian sweep, one role per blockIdx.y.  src / dst select the position (working qw or
 // trial qs) and the destination blocks (Jc at an evaluation, Jt inside Newton).
+// (blockDim.y = M::GATE_WARPS warps share the chain batch of a cooperative sweep; the
+// lanes that leave early are the same in each of them, so the barriers stay consistent)
 template <class M, bool EVAL>
-__global__ void __launch_bounds__(kStreamBlock)
+__global__ void __launch_bounds__(kStreamBlock * M::GATE_WARPS)
     kp_jacob(const __grid_constant__ OdeData D, PhasedLayout L, int64_t n, int64_t ld,
              const double* q) {
+  extern __shared__ double xch[];
   MLB_PH_INDEX();
   if (!P.I(EVAL ? CT_ALIVE : CT_ACTIVE, i)) return;
   const Col src = EVAL ? col(q, ld, i) : P.S.qs;
@@ -168,8 +171,9 @@ __global__ void __launch_bounds__(kStreamBlock)
   const Col c = EVAL ? Col{nullptr, 0} : P.S.c;
   constexpr int R = M::ROLE_DIRS;
   [&]<int... K>(std::integer_sequence<int, K...>) {
-    ((blockIdx.y == K ? Stream<M>::template jacob_role<K * R, R, K == 0>(D, src, dst, c)
-                      : (void)0),
+    ((blockIdx.y == K
+          ? Stream<M>::template jacob_role<K * R, R, K == 0, M::GATE_WARPS>(D, src, dst, c, xch)
+          : (void)0),
      ...);
   }(std::make_integer_sequence<int, M::N_ROLE>{});
 }
@@ -307,9 +311,10 @@ __global__ void __launch_bounds__(32 * NCH)
 
 // second-order sweep, one pair group per blockIdx.y; partial gradients to hpart
 template <class M>
-__global__ void __launch_bounds__(kStreamBlock)
+__global__ void __launch_bounds__(kStreamBlock * M::GATE_WARPS)
     kp_second_order(const __grid_constant__ OdeData D, PhasedLayout L, int64_t n, int64_t ld,
                     const double* q) {
+  extern __shared__ double xch[];
   MLB_PH_INDEX();
   if (!P.I(CT_ALIVE, i)) return;
   constexpr int U = M::U;
@@ -318,11 +323,15 @@ __global__ void __launch_bounds__(kStreamBlock)
 #pragma unroll
   for (int a = 0; a < U; ++a) h[a] = 0.0;
   [&]<int... G>(std::integer_sequence<int, G...>) {
-    ((blockIdx.y == G ? Stream<M>::template second_order_group<G>(D, u, P.S.Jt, h) : (void)0),
+    ((blockIdx.y == G
+          ? Stream<M>::template second_order_group<G, M::GATE_WARPS>(D, u, P.S.Jt, h, xch)
+          : (void)0),
      ...);
   }(std::make_integer_sequence<int, M::NG>{});
+  if (threadIdx.y == 0) {
 #pragma unroll
-  for (int d = 0; d < M::ND; ++d) P.hpart[(int)blockIdx.y * M::ND + d] = h[M::dir_u(d)];
+    for (int d = 0; d < M::ND; ++d) P.hpart[(int)blockIdx.y * M::ND + d] = h[M::dir_u(d)];
+  }
 }
 
 // [finish a fresh evaluation: add the second-order partials] [half kick] cotangent
@@ -612,6 +621,9 @@ int phased_leapfrog_steps(const mlb_model* m, const OdeData& D, int64_t n, int64
   }
   int* host_count = m->pinned_word;
   const dim3 blk(kStreamBlock), g1(sgrid(n)), g_role(sgrid(n), M::N_ROLE), g_grp(sgrid(n), M::NG);
+  const dim3 sblk(kStreamBlock, M::GATE_WARPS);  // cooperative sweeps
+  constexpr size_t sh_jac = sizeof(double) * M::template xch_doubles<M::ROLE_DIRS, 0>();
+  constexpr size_t sh_so = sizeof(double) * M::template xch_doubles<M::ND, M::PAIRS_PER_GROUP>();
   constexpr int NCH = kChunkWarps;
   const dim3 cblk(32, NCH);
   // dynamic shared memory of the chunked kernels: [rows][32] doubles
@@ -637,9 +649,9 @@ int phased_leapfrog_steps(const mlb_model* m, const OdeData& D, int64_t n, int64
     for (int sub = 0; sub < 3; ++sub) {
       const bool fresh = first || sub == 1;
       if (fresh) {  // evaluate at the working position
-        MLB_KP((kp_jacob<M, true><<<g_role, blk, 0, s>>>(D, L, n, ld, io.q)));
+        MLB_KP((kp_jacob<M, true><<<g_role, sblk, sh_jac, s>>>(D, L, n, ld, io.q)));
         MLB_KP((kp_eval_mid<M, NCH><<<g1, cblk, sh_eval, s>>>(D, L, n, ld, io.q, io.p)));
-        MLB_KP((kp_second_order<M><<<g_grp, blk, 0, s>>>(D, L, n, ld, io.q)));
+        MLB_KP((kp_second_order<M><<<g_grp, sblk, sh_so, s>>>(D, L, n, ld, io.q)));
       }
       if (io.n_step <= 0) {  // only h_init is wanted
         MLB_KP((kp_kick_project<M, NCH><<<g1, cblk, sh_proj, s>>>(L, n, ld, io.p, io.q, io.dt, io.dt_pc,
@@ -660,7 +672,7 @@ int phased_leapfrog_steps(const mlb_model* m, const OdeData& D, int64_t n, int64
         if (SOLVER == MLB_SOLVER_QUASI_NEWTON)
           MLB_KP((kp_constr<M><<<g1, blk, 0, s>>>(D, L, n)));
         else
-          MLB_KP((kp_jacob<M, false><<<g_role, blk, 0, s>>>(D, L, n, ld, io.q)));
+          MLB_KP((kp_jacob<M, false><<<g_role, sblk, sh_jac, s>>>(D, L, n, ld, io.q)));
         MLB_KP((kp_update<M, SOLVER, NCH><<<g1, cblk, sh_upd, s>>>(L, n, o, counter)));
         active = read_counter();
       }

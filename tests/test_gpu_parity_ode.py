@@ -301,8 +301,11 @@ def test_hh_ops_and_step_match_autodiff_golden():
         out = integ.steps(mlb.states.ChainState(g["step_q0"][None], g["step_p0"][None]), 1,
                           raise_on_failure=False)  # fmt: skip
         assert int(out.status[0]) == 0
+        # cond(capacitance) ~ 1e12: the last iterations of a solve hover at the tolerances
+        # and their number moves with the rounding of exp / reductions; the converged point
+        # (next assertions) does not
         want = g[f"step_iters_{sid}"]
-        assert abs(int(out.iters_fwd[0]) - want[0]) <= 1 and abs(int(out.iters_rev[0]) - want[1]) <= 1
+        assert abs(int(out.iters_fwd[0]) - want[0]) <= 2 and abs(int(out.iters_rev[0]) - want[1]) <= 2
         assert scaled_err(cpu(out.pos), g[f"step_q_{sid}"][None]) < 1e-7
         assert scaled_err(cpu(out.mom), g[f"step_p_{sid}"][None]) < 1e-2
         assert rel_err(cpu(out.h_final), g[f"step_h_{sid}"]) < 1e-7
