@@ -560,6 +560,19 @@ def run_mlb(args, emit):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         hbm_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
         flops_step = flops.step_flops(model, solver, mean_iters)
+        if args.workload in ("hier", "toy"):
+            kernel_name = "k_leapfrog_steps (fused trajectory, one launch)"
+        elif args.single_kernel:
+            kernel_name = "ks_leapfrog_steps (fused trajectory, one launch)"
+        else:
+            kernel_name = ("mlb_leapfrog_steps call = host-driven sub-phase kernels; kp_jacob and "
+                           "kp_second_order (sensitivity sweeps) dominate, see profiles/")
+        # DRAM bytes of the dominant kernel from the committed ncu --set full capture
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
+                args.workload, {})
+        except (OSError, ValueError):
+            traffic = {}
         ach_tf = flops_step * done_local / (float(np.mean(ms)) * 1e-3) / 1e12
         bytes_step = flops.step_bytes(model)
         ach_gbs = bytes_step * (done1_all / world) / (ms1_mean * 1e-3) / 1e9
@@ -580,9 +593,10 @@ def run_mlb(args, emit):
             },
             "roofline": {
                 "bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": ach_tf / fp64_peak if fp64_peak > 0 else None, "traffic": None,
-                "kernel": ("ks_leapfrog_steps" if args.workload in ("fn", "hh") else "k_leapfrog_steps")
-                          + " (fused trajectory)",
+                "frac": ach_tf / fp64_peak if fp64_peak > 0 else None,
+                "traffic": traffic.get("bytes_per_launch"),
+                "traffic_source": traffic.get("source"),
+                "kernel": kernel_name,
                 "algorithmic_flops_per_chain_step": flops_step,
                 "peak_source": "DFMA-loop microbenchmark run live in this process "
                                "(MEASURED_PEAKS.json has no fp64 entry)",
@@ -590,8 +604,7 @@ def run_mlb(args, emit):
             "roofline_hbm": {
                 "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ach_gbs / hbm_peak, "traffic": None,
-                "kernel": ("ks_leapfrog_steps" if args.workload in ("fn", "hh") else "k_leapfrog_steps")
-                          + ", one step per launch, L2 flushed",
+                "kernel": kernel_name + ", one step per launch, L2 flushed",
                 "algorithmic_bytes_per_chain_step": bytes_step,
                 "ms_per_launch": ms1_mean, "peak_source": hbm_src,
             },

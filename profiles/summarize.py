@@ -3,6 +3,7 @@
 
   python profiles/summarize.py launches gpurun_out/launches_X.csv profiles/X_launches.md "<cmd>"
   python profiles/summarize.py full gpurun_out/prof_X.ncu-rep profiles/X_full.md
+  python profiles/summarize.py full gpurun_out/prof_X_raw.csv profiles/X_full.md
 
 `launches`: per-kernel count / total device time / share from a
 `ncu --metrics gpu__time_duration.sum --csv` log.  `full`: the handful of counters the
@@ -30,6 +31,10 @@ FULL_KEYS = [
     "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
     "smsp__issue_active.avg.pct_of_peak_sustained_active",
     "smsp__inst_executed.sum",
+    "smsp__thread_inst_executed_pred_on_per_inst_executed.ratio",
+    "sm__warps_active.avg.per_cycle_active",
+    "l1tex__t_bytes_pipe_lsu_mem_global_op_ld.sum",
+    "lts__t_bytes.sum",
     "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum",
     "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum",
     "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum",
@@ -79,8 +84,13 @@ def launches(src, dst, cmd):
 
 
 def full(src, dst):
-    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True,
-                         text=True, check=True).stdout
+    # a .ncu-rep, or the `ncu -i X.ncu-rep --page raw --csv` dump of one made on the GPU box
+    # (reports of the large ODE kernels exceed what a gpurun call may bring back)
+    if src.endswith(".csv"):
+        out = open(src).read()
+    else:
+        out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True,
+                             text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units, body = rows[0], rows[1], rows[2:]
     col = {h: i for i, h in enumerate(hdr)}
