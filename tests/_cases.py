@@ -121,3 +121,38 @@ def rel_err(a, b):
 
 
 __all__ = [n for n in dir() if not n.startswith("__")]
+
+
+def toy_posterior_moments(sigma=0.1, y=1.0, coeff=2.0, half_width=3.0, n_grid=6001):
+    """E[theta0^2], E[theta1^2], E[|theta0|], E[|theta1|] under p(theta | y) ∝ N(theta; 0, I)
+    N(y; F(theta), sigma^2) by tensor-product quadrature on a fine grid.  The theta-marginal
+    of the lifted constrained target IS this posterior (notebook cells around :1580), so
+    this is an anchor that depends on neither implementation under test."""
+    g = np.linspace(-half_width, half_width, n_grid)
+    t0, t1 = g[:, None], g[None, :]
+    F = t1**2 + coeff * t0**2 * (t0**2 - 0.5)
+    logp = -0.5 * (t0**2 + t1**2) - 0.5 * ((y - F) / sigma) ** 2
+    w = np.exp(logp - logp.max())
+    z = w.sum()
+    return {"t0_sq": float((w * t0**2).sum() / z), "t1_sq": float((w * t1**2).sum() / z),
+            "t0_abs": float((w * np.abs(t0)).sum() / z),
+            "t1_abs": float((w * np.abs(t1)).sum() / z)}  # fmt: skip
+
+
+def toy_manifold_inits(n, rng, y=1.0, coeff=2.0):
+    """Points on the limiting manifold F(theta) = y with eta = 0 (what the reference
+    starts its toy chains from, toy_2d_model.py:119-157; closed form for coeff = 2, y = 1:
+    theta1 = +-sqrt(y - coeff theta0^2 (theta0^2 - 1/2)), |theta0| <= 1)."""
+    t0 = rng.uniform(-1.0, 1.0, n)
+    t1 = np.sqrt(np.maximum(y - coeff * t0**2 * (t0**2 - 0.5), 0.0)) * rng.choice([-1.0, 1.0], n)
+    return np.stack([t0, t1, np.zeros(n)], 1)
+
+
+def mc_standard_error(x):
+    """Monte-Carlo standard error of the mean of x[n_chain, n_draw] from the spread of
+    the per-chain means (chains are independent)."""
+    m = np.asarray(x).mean(1)
+    return float(m.std(ddof=1) / np.sqrt(m.size))
+
+
+__all__ = [n for n in dir() if not n.startswith("__")]

@@ -181,3 +181,31 @@ def test_philox_stream_reference_values():
     assert 0.0 < u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.02
     assert not np.allclose(co.philox_normals(1, 5, 0, 4), co.philox_normals(1, 5, 1, 4))
     assert not np.allclose(co.philox_normals(1, 5, 0, 4), co.philox_normals(1, 6, 0, 4))
+
+
+def test_oracle_sampler_reproduces_toy_posterior_moments():
+    """Statistical anchor for the oracle (the reference has no bit-wise golden vector for
+    the constrained path): static constrained HMC of the C++ oracle on the toy
+    model against tensor-product quadrature of p(theta | y), within Monte-Carlo error."""
+    from _cases import mc_standard_error, toy_manifold_inits, toy_posterior_moments
+
+    sigma = 0.1
+    cm = co.OracleModel.toy(sigma, 1.0, 2.0)
+    q = toy_manifold_inits(512, np.random.default_rng(2))
+    opts = co.solver_opts(co.SOLVER_NEWTON)
+    n_warm, n_main = 300, 500
+    tr = np.empty((q.shape[0], n_main, 2))
+    acc = []
+    for it in range(n_warm + n_main):
+        r = cm.hmc_transition(q, 0.1, 20, opts, seed=4, iteration=it)
+        q = r["q"]
+        if it >= n_warm:
+            tr[:, it - n_warm] = q[:, :2]
+            acc.append(r["accept_stat"].mean())
+    assert np.mean(acc) > 0.6
+    want = toy_posterior_moments(sigma)
+    got = {"t0_sq": tr[..., 0] ** 2, "t1_sq": tr[..., 1] ** 2,
+           "t0_abs": np.abs(tr[..., 0]), "t1_abs": np.abs(tr[..., 1])}  # fmt: skip
+    for k, x in got.items():
+        se = mc_standard_error(x)
+        assert se < 2e-3 and abs(x.mean() - want[k]) < 5 * se, (k, x.mean(), want[k], se)

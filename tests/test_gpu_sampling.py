@@ -1,0 +1,102 @@
+"""Chain-level parity (north_star: "chain summary statistics must agree within Monte-Carlo
+error"): the GPU sampler's posterior moments against (i) tensor-product quadrature of the
+toy posterior, an anchor independent of both implementations, with the notebook's
+statistical anchors (accept rate at the dual-averaging target, no convergence errors,
+R-hat ~ 1; notebooks/Two-dimensional_example.ipynb raw lines 2565-2684), and (ii) chains
+of the CPU oracle sampler for the eight-schools model."""
+import numpy as np
+import pytest
+import torch
+
+import c_oracle as co
+from _cases import (EIGHT_SCHOOLS_SIGMA, EIGHT_SCHOOLS_Y, mc_standard_error,
+                    toy_manifold_inits, toy_posterior_moments)  # fmt: skip
+
+pytestmark = pytest.mark.gpu
+
+
+def _sampler(mlb, system, step_size, n_step, seed):
+    integ = mlb.integrators.ConstrainedLeapfrogIntegrator(
+        system, step_size, projection_solver=mlb.jitted_solve_projection_onto_manifold_newton,
+        projection_solver_kwargs=dict(constraint_tol=1e-9, position_tol=1e-8, max_iters=50))
+    return mlb.samplers.StaticMetropolisHMC(system, integ, n_step=n_step, seed=seed), integ
+
+
+@pytest.mark.parametrize("adapt_step", [False, True])
+def test_toy_posterior_moments_match_quadrature(adapt_step):
+    """adapt_step False: the notebook's setting (step size 0.1): accept rate ~0.99 and
+    (almost) no integrator errors, its statistical anchors.  True: dual averaging to an
+    accept rate of 0.8, where a good part of the rejections ARE projection failures at the
+    larger step - the chain must still be exact."""
+    import manifold_lifting_b200 as mlb
+
+    sigma = 0.1
+    model = mlb.models.Toy2DModel(sigma, 1.0, 2.0)
+    system = mlb.IndependentAdditiveNoiseModelSystem(model, model.data, model.dim_u)
+    n = 4096
+    q0 = toy_manifold_inits(n, np.random.default_rng(11))
+    sampler, integ = _sampler(mlb, system, 0.1, 20, seed=5)
+    adapters = [mlb.ToleranceAdapter()]  # warm-up at 1e-6 / 1e-5, main at 1e-9 / 1e-8
+    if adapt_step:
+        adapters.append(mlb.adapters.DualAveragingStepSizeAdapter(0.8))
+    _, traces, stats = sampler.sample_chains(300, 500, q0, adapters=adapters, trace_dim=2)
+    th = traces["pos"].cpu().numpy()  # [n, 500, 2]
+    assert integ.projection_solver_kwargs["constraint_tol"] == 1e-9  # ToleranceAdapter.finalize
+    acc = float(stats["accept_stat"].mean())
+    errs = float((stats["convergence_error"] + stats["non_reversible_step"]).mean())
+    if adapt_step:
+        assert 0.6 < acc < 0.95 and float(integ.step_size) > 0.1
+    else:
+        assert acc > 0.97 and errs < 5e-3, (acc, errs)
+    want = toy_posterior_moments(sigma)
+    got = {"t0_sq": th[..., 0] ** 2, "t1_sq": th[..., 1] ** 2,
+           "t0_abs": np.abs(th[..., 0]), "t1_abs": np.abs(th[..., 1])}  # fmt: skip
+    for k, x in got.items():
+        se = mc_standard_error(x)
+        assert se < 2e-3 and abs(x.mean() - want[k]) < 5 * se, (k, x.mean(), want[k], se)
+    # symmetric posterior: odd moments vanish
+    for j in range(2):
+        assert abs(th[..., j].mean()) < 5 * mc_standard_error(th[..., j]) + 1e-3
+    for j in range(2):
+        r = mlb.parallel.rhat(torch.as_tensor(np.abs(th[:512, :, j])).cuda().contiguous(), "rank")
+        assert r < 1.05, r
+
+
+def test_eight_schools_chain_statistics_match_cpu_oracle_chains():
+    import manifold_lifting_b200 as mlb
+
+    y, s = EIGHT_SCHOOLS_Y, EIGHT_SCHOOLS_SIGMA
+    model = mlb.models.EightSchoolsModel(y, s)
+    system = mlb.HierarchicalLatentVariableModelSystem(model, model.data, model.dim_u)
+    rng = np.random.default_rng(3)
+
+    def inits(n):
+        q = model.sample_initial_states(rng, n)
+        q[:, 0] = np.clip(q[:, 0], -10, 10)
+        q[:, 1] = np.clip(q[:, 1], -2, 3)
+        par = model.generate_params(q[:, :2])
+        q[:, 10:] = (y[None] - par["μ"][:, None] - par["τ"][:, None] * q[:, 2:10]) / s[None]
+        return q
+
+    n_step, n_warm, n_main = 8, 200, 300
+    sampler, integ = _sampler(mlb, system, 0.2, n_step, seed=17)
+    _, traces, stats = sampler.sample_chains(
+        n_warm, n_main, inits(4096), adapters=[mlb.adapters.DualAveragingStepSizeAdapter(0.8)],
+        trace_dim=2)  # fmt: skip
+    g = traces["pos"].cpu().numpy()
+    eps = float(integ.step_size)
+    assert 0.6 < float(stats["accept_stat"].mean()) < 0.95
+    # CPU oracle sampler, same step size, its own chains and random numbers
+    cm = co.OracleModel.hier(y, s)
+    opts = co.solver_opts(co.SOLVER_NEWTON)
+    qc = inits(384)
+    c = np.empty((qc.shape[0], n_main, 2))
+    for it in range(n_warm + n_main):
+        qc = cm.hmc_transition(qc, eps, n_step, opts, seed=99, iteration=it)["q"]
+        if it >= n_warm:
+            c[:, it - n_warm] = qc[:, :2]
+    for j, name in enumerate(("u0 = mu", "u1 = log tau")):
+        for f in (lambda x: x, lambda x: x**2):
+            a, b = f(g[..., j]), f(c[..., j])
+            se = np.hypot(mc_standard_error(a), mc_standard_error(b))
+            assert abs(a.mean() - b.mean()) < 5 * se, (name, a.mean(), b.mean(), se)
