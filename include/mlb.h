@@ -223,8 +223,10 @@ typedef struct mlb_adapt_opts {
 
 /* Per-chain sampling statistics accumulated by mlb_hmc_sample, SoA rows:
  *   0 sum accept_stat, 1 n_accepted, 2 n_convergence_error, 3 n_non_reversible_step,
- *   4 n_hamiltonian_diverged, 5 leapfrog steps completed, 6 projection iterations. */
-#define MLB_STAT_ROWS 7
+ *   4 n_hamiltonian_diverged, 5 leapfrog steps completed, 6 projection iterations,
+ *   7 sum of tree depths (mlb_nuts_sample only; row 1 there counts transitions whose
+ *   state changed). */
+#define MLB_STAT_ROWS 8
 
 /* n_iter static-HMC transitions per chain in ONE launch (momentum refresh, n_step
  * constrained leapfrog steps with |dh| > max_delta_h test, Metropolis accept; notebook
@@ -249,6 +251,25 @@ int mlb_hmc_sample(const mlb_model* m, int64_t n, int64_t ld, double* q, double 
 void mlb_philox_normals_host(uint64_t seed, uint64_t chain, uint32_t iter, int32_t n,
                              double* out);
 double mlb_philox_uniform_host(uint64_t seed, uint64_t chain, uint32_t iter);
+
+/* n_iter dynamic multinomial HMC (NUTS) transitions per chain in ONE launch: Mici's
+ * `DynamicMultinomialHMC`, the sampler the reference builds at example_models/utils.py:
+ * 286-288 (max_tree_depth :70-73): momentum refresh, binary tree doubling in a uniformly
+ * drawn direction with constrained leapfrog steps, multinomial proposal with weights
+ * exp(h_init - h), no-U-turn termination per subtree and for the tree, termination on an
+ * integrator error or |h - h_init| > max_delta_h.  accept_stat (the adaptation statistic)
+ * is the mean of min(1, exp(h_init - h)) over the tree's steps.  Random numbers: momentum
+ * normals as in mlb_hmc_sample; the k-th uniform of a transition is Philox counter
+ * (k, iter, chain | 1 << 63), k = 1, 2, ... in order of use.  Arguments as mlb_hmc_sample;
+ * trace_n_step / trace_depth ([n_iter][n], NULL to skip) receive the tree size / depth
+ * of every transition.  Toy / hierarchical models only (MLB_ERR_UNSUPPORTED otherwise). */
+int mlb_nuts_sample(const mlb_model* m, int64_t n, int64_t ld, double* q, double dt,
+                    int32_t max_tree_depth, int32_t n_iter, const mlb_solver_opts* opts,
+                    double max_delta_h, uint64_t seed, uint64_t chain0, uint32_t iter0,
+                    const double* mom_noise, double* adapt, const mlb_adapt_opts* adapt_opts,
+                    double* trace_q, int32_t trace_every, int32_t trace_dim,
+                    double* trace_accept, int32_t* trace_n_step, int32_t* trace_depth,
+                    double* stats, int32_t* last_status, void* stream);
 
 /* ---- host-buffer entry point (what a reference-side binding calls; see
  * INTEGRATION.md).  q, p are HOST arrays in the reference's natural layout

@@ -20,7 +20,7 @@ PARAM_UNBOUNDED, PARAM_NORMAL = 0, 1
 FLAG_SINGLE_KERNEL = 1
 NORM_MAX, NORM_EUCLIDEAN = 0, 1
 ST_OK, ST_DIVERGED, ST_NOT_CONVERGED, ST_NON_REVERSIBLE, ST_H_DIVERGED, ST_LINALG = range(6)
-ADAPT_ROWS, STAT_ROWS = 5, 7
+ADAPT_ROWS, STAT_ROWS = 5, 8
 
 EXPORTS = (
     "mlb_version", "mlb_last_error", "mlb_model_create", "mlb_model_destroy",
@@ -33,7 +33,7 @@ EXPORTS = (
     "mlb_project_onto_cotangent_space", "mlb_leapfrog_steps", "mlb_hmc_sample",
     "mlb_philox_normals_host", "mlb_philox_uniform_host", "mlb_leapfrog_steps_host",
     "mlb_aos_to_soa", "mlb_soa_to_aos", "mlb_launch_count", "mlb_measure_fp64_tflops",
-    "mlb_selftest_fast_math", "mlb_selftest_exp",
+    "mlb_selftest_fast_math", "mlb_selftest_exp", "mlb_nuts_sample",
 )  # fmt: skip
 
 

@@ -362,6 +362,40 @@ int mlb_hmc_sample(const mlb_model* m, int64_t n, int64_t ld, double* q, double 
   return m->ops->sample(m, opts->solver, n, ld, q, to_opts(opts), a, s);
 }
 
+int mlb_nuts_sample(const mlb_model* m, int64_t n, int64_t ld, double* q, double dt,
+                    int32_t max_tree_depth, int32_t n_iter, const mlb_solver_opts* opts,
+                    double max_delta_h, uint64_t seed, uint64_t chain0, uint32_t iter0,
+                    const double* mom_noise, double* adapt, const mlb_adapt_opts* adapt_opts,
+                    double* trace_q, int32_t trace_every, int32_t trace_dim,
+                    double* trace_accept, int32_t* trace_n_step, int32_t* trace_depth,
+                    double* stats, int32_t* last_status, void* stream) {
+  MLB_COMMON_ARGS();
+  MLB_ARG(q && opts && n_iter >= 0 && max_tree_depth >= 0 && max_tree_depth <= 20);
+  MLB_ARG(!adapt || adapt_opts);
+  if (!m->ops->nuts) {
+    g_err = "the dynamic sampler is built for the toy / hierarchical models only";
+    return MLB_ERR_UNSUPPORTED;
+  }
+  SampleArgs a;
+  a.dt = dt, a.max_delta_h = max_delta_h, a.n_step = 0, a.n_iter = n_iter;
+  a.trace_every = trace_every > 0 ? trace_every : 1;
+  MLB_ARG(trace_dim >= 0 && trace_dim <= m->Q);
+  a.trace_dim = trace_dim > 0 ? trace_dim : m->Q;
+  a.seed = seed, a.chain0 = chain0, a.iter0 = iter0;
+  a.mom_noise = mom_noise, a.unif = nullptr, a.adapt = adapt;
+  a.a_target = adapt_opts ? adapt_opts->adapt_stat_target : 0.8;
+  a.a_reg = adapt_opts ? adapt_opts->log_step_size_reg_coefficient : 0.05;
+  a.a_decay = adapt_opts ? adapt_opts->iter_decay_coeff : 0.75;
+  a.a_offset = adapt_opts ? adapt_opts->iter_offset : 10.0;
+  a.trace_q = trace_q, a.trace_accept = trace_accept, a.stats = stats;
+  a.last_status = last_status;
+  NutsArgs na;
+  na.max_depth = max_tree_depth, na.scratch = nullptr, na.lds = 0;
+  na.trace_n_step = trace_n_step, na.trace_depth = trace_depth;
+  if (n == 0 || n_iter == 0) return MLB_OK;
+  return m->ops->nuts(m, opts->solver, n, ld, q, to_opts(opts), a, na, s);
+}
+
 void mlb_philox_normals_host(uint64_t seed, uint64_t chain, uint32_t iter, int32_t n,
                              double* out) {
   for (int j = 0; 2 * j < n; ++j) {

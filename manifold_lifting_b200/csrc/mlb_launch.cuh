@@ -319,6 +319,10 @@ struct SampleArgs {
   int32_t* last_status;
 };
 
+}  // namespace mlb
+#include "mlb_nuts.cuh"
+namespace mlb {
+
 template <class M, int SOLVER>
 __global__ void __launch_bounds__(kBlock, MLB_LF_MIN_BLOCKS)
     k_hmc_sample(const __grid_constant__ typename M::Params P, int64_t n, int64_t ld,
@@ -455,6 +459,9 @@ struct ModelOps {
                cudaStream_t);
   int (*sample)(const mlb_model*, int, int64_t, int64_t, double*, const Opts&,
                 const SampleArgs&, cudaStream_t);
+  // dynamic multinomial HMC (mlb_nuts.cuh); NULL where it is not built
+  int (*nuts)(const mlb_model*, int, int64_t, int64_t, double*, const Opts&,
+              const SampleArgs&, const NutsArgs&, cudaStream_t);
 };
 
 inline unsigned grid_for(int64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
@@ -576,6 +583,23 @@ struct Launch {
       return finish_launch();
     });
   }
+  static int nuts(const mlb_model* m, int solver, int64_t n, int64_t ld, double* q,
+                  const Opts& o, const SampleArgs& a, const NutsArgs& na0, cudaStream_t s) {
+    // per-chain tree storage (edges, summed momentum, proposal, pending siblings per level)
+    NutsArgs na = na0;
+    na.lds = (n + 31) / 32 * 32;
+    const size_t bytes = sizeof(double) * (size_t)NutsRows<M::Q>::total(na.max_depth) * (size_t)na.lds;
+    if (cudaMallocAsync((void**)&na.scratch, bytes, s) != cudaSuccess) {
+      g_err = "tree scratch allocation failed";
+      return (int)MLB_ERR_CUDA;
+    }
+    const int rc = dispatch_solver(solver, [&]<int S>() {
+      k_nuts_sample<M, S><<<grid_for(n), kBlock, 0, s>>>(P(m), n, ld, q, o, a, na);
+      return finish_launch();
+    });
+    cudaFreeAsync(na.scratch, s);
+    return rc;
+  }
 };
 
 template <class M>
@@ -583,7 +607,7 @@ ModelOps make_ops(int model, int dim_y, int param) {
   using L = Launch<M>;
   return ModelOps{model, dim_y, param, &L::constr, &L::jacob, &L::decompose, &L::logdet,
                   &L::nld, &L::block_op, &L::project_cotangent, &L::solve, &L::steps,
-                  &L::sample};
+                  &L::sample, &L::nuts};
 }
 
 }  // namespace mlb

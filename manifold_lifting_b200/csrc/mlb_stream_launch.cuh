@@ -505,7 +505,7 @@ ModelOps make_stream_ops(int model, int param) {
   using L = StreamLaunch<M>;
   return ModelOps{model, 0 /* any dim_y */, param, &L::constr, &L::jacob, &L::decompose,
                   &L::logdet, &L::nld, &L::block_op, &L::project_cotangent, &L::solve,
-                  &L::steps, &L::sample};
+                  &L::steps, &L::sample, nullptr};
 }
 
 }  // namespace mlb

@@ -10,8 +10,8 @@ kernel per chain; the cross-chain mean at the end of warm-up is the only reducti
 
 Random numbers are counter-based (Philox4x32-10 keyed by seed, GLOBAL chain index,
 iteration), so a run is bit-identical however the chains are sharded over GPUs.
-(The reference's dynamic multinomial sampler, utils.py:286-288, is a "next" row in
-SURVEY.md 8f and is not implemented here.)
+`DynamicMultinomialHMC` is the reference's default sampler (utils.py:286-288): same
+driver, with the tree built per chain inside the kernel (csrc/mlb_nuts.cuh).
 """
 import ctypes as C
 
@@ -117,6 +117,42 @@ class StaticMetropolisHMC:
             "diverging": stats[4] / n_it,
             "n_step": stats[5],
             "projection_iters": stats[6],
+            "tree_depth": stats[7] / n_it,
             "last_status": last,
         }
         return ChainState(q), traces, out_stats
+
+
+class DynamicMultinomialHMC(StaticMetropolisHMC):
+    """Mici `DynamicMultinomialHMC(system, integrator, rng, max_tree_depth=10,
+    max_delta_h=1000)` as the reference constructs it (example_models/utils.py:286-288),
+    batched: every chain builds its own tree inside one kernel (`mlb_nuts_sample`).
+    `sample_chains` and the adapters work as for the static sampler; `stats` additionally
+    reports the mean tree depth, and `n_step` the integrator steps taken."""
+
+    def __init__(self, system, integrator, rng=None, max_tree_depth=10, max_delta_h=1000.0,
+                 seed=None):  # fmt: skip
+        super().__init__(system, integrator, rng=rng, n_step=0, seed=seed,
+                         max_delta_h=max_delta_h)  # fmt: skip
+        self.max_tree_depth = int(max_tree_depth)
+        self.trace_n_step = self.trace_depth = None  # set to int32 [n_iter, n] tensors to record
+
+    def _launch(self, q, n_iter, adapt=None, adapt_opts=None, trace_q=None, trace_every=1,
+                trace_accept=None, stats=None, last_status=None, chain_offset=0,
+                mom_noise=None, unif=None, trace_dim=0):  # fmt: skip
+        if unif is not None:
+            raise ValueError("the dynamic sampler draws its uniforms from Philox")
+        sysm, integ = self.system, self.integrator
+        n = q.shape[0]
+        opts = integ.solver_opts()
+        pq, ld = p_soa(q, sysm.dim_q)
+        check(lib().mlb_nuts_sample(
+            sysm._h, C.c_int64(n), C.c_int64(ld), pq, C.c_double(integ.step_size_scalar()),
+            C.c_int32(self.max_tree_depth), C.c_int32(n_iter), C.byref(opts),
+            C.c_double(self.max_delta_h), C.c_uint64(self.seed), C.c_uint64(chain_offset),
+            C.c_uint32(self.iteration), p_vec(mom_noise), p_vec(adapt),
+            None if adapt_opts is None else C.byref(adapt_opts), p_vec(trace_q),
+            C.c_int32(trace_every), C.c_int32(trace_dim), p_vec(trace_accept),
+            p_vec(self.trace_n_step, torch.int32), p_vec(self.trace_depth, torch.int32),
+            p_vec(stats), p_vec(last_status, torch.int32), stream_ptr()))  # fmt: skip
+        self.iteration += n_iter

@@ -535,6 +535,104 @@ static double philox_uniform(uint64_t seed, uint64_t chain, uint32_t iter) {
   return u01(c[0], c[1]);
 }
 
+// k-th uniform of one transition (k = 0 is philox_uniform: the Metropolis draw of the
+// static sampler; the dynamic sampler numbers its draws 1, 2, ... in the order it uses them)
+static double philox_uniform_k(uint64_t seed, uint64_t chain, uint32_t iter, uint32_t k) {
+  uint32_t c[4] = {k, iter, (uint32_t)chain,
+                   ((uint32_t)(chain >> 32) & 0x7fffffffu) | 0x80000000u};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  return u01(c[0], c[1]);
+}
+
+// ------------------------------------------------ dynamic multinomial HMC (NUTS)
+// Restatement of Mici 0.2.1 `DynamicMultinomialHMC` (the sampler the reference builds at
+// example_models/utils.py:286-288 with `max_tree_depth`, :70-73), from its published
+// algorithm - Mici's source is not in the reference tree: recursive
+// binary-tree doubling in a uniformly drawn direction, multinomial sampling of the
+// proposal with weights exp(h_init - h) (uniform sampling inside a new subtree, biased
+// progressive sampling between the old tree and the new subtree), no-U-turn termination
+// on the summed momentum (identity metric: dh/dmom = p) checked for every subtree and for
+// the whole tree, termination on an integrator error or |h - h_init| > max_delta_h.
+// accept_stat = mean over the tree's integrator steps of min(1, exp(h_init - h)) (a
+// failed step counts as 0).  The extra sub-tree checks of later Mici versions
+// (`do_extra_subtree_checks`) are not applied.
+struct Tree {
+  Chain neg, pos;            // edge states (time order), evaluated
+  std::vector<double> rho;   // sum of momenta over the tree's states
+  std::vector<double> prop;  // proposal position
+  double lw;                 // log of the summed weights
+  void init(const Model& M) { neg.init(M), pos.init(M), rho.assign(M.Q, 0), prop.assign(M.Q, 0); }
+};
+
+struct NutsCtx {
+  const Model& M;
+  Work& W;
+  const StepOpts& so;
+  double dt, h0, max_delta_h;
+  uint64_t seed, chain;
+  uint32_t iter, k;  // next uniform index
+  const double* unif;  // optional supplied draws (index k - 1)
+  int n_unif;
+  int n_step, status;  // integrator steps taken; first failure status
+  double sum_acc;
+  double draw() {
+    double u = (unif && (int)k - 1 < n_unif) ? unif[k - 1] : philox_uniform_k(seed, chain, iter, k);
+    ++k;
+    return u;
+  }
+};
+
+static double log_add_exp(double a, double b) {
+  double m = a > b ? a : b;
+  return m + std::log(std::exp(a - m) + std::exp(b - m));
+}
+
+static bool no_u_turn_violated(const Model& M, const Chain& a, const Chain& b,
+                               const std::vector<double>& rho) {
+  double da = 0.0, db = 0.0;
+  for (int k = 0; k < M.Q; ++k) da += a.p[k] * rho[k], db += b.p[k] * rho[k];
+  return da < 0.0 || db < 0.0;
+}
+
+// Builds a subtree of 2^depth states beyond `edge` in direction dir; returns true if the
+// transition must terminate (the subtree is then discarded).
+static bool build_tree(NutsCtx& X, int depth, const Chain& edge, int dir, Tree& out) {
+  const Model& M = X.M;
+  if (depth == 0) {
+    Chain N;
+    N.init(M);
+    int f, r;
+    int st = leapfrog_step(M, X.W, const_cast<Chain&>(edge), N, dir * X.dt, X.so, &f, &r);
+    X.n_step += 1;
+    if (st != ST_OK) {
+      if (X.status == ST_OK) X.status = st;
+      return true;
+    }
+    double h = hamiltonian(M, N);
+    if (std::isnan(h) || std::fabs(h - X.h0) > X.max_delta_h) {
+      if (X.status == ST_OK) X.status = ST_H_DIVERGED;
+      return true;
+    }
+    double d = X.h0 - h;
+    X.sum_acc += std::exp(d < 0.0 ? d : 0.0);
+    out.neg = N, out.pos = N, out.rho = N.p, out.prop = N.q, out.lw = d;
+    return false;
+  }
+  Tree inner, outer;
+  inner.init(M), outer.init(M);
+  if (build_tree(X, depth - 1, edge, dir, inner)) return true;
+  if (build_tree(X, depth - 1, dir > 0 ? inner.pos : inner.neg, dir, outer)) return true;
+  const double lw = log_add_exp(inner.lw, outer.lw);
+  const double u = X.draw();
+  out.prop = (u < std::exp(outer.lw - lw)) ? outer.prop : inner.prop;
+  out.lw = lw;
+  out.rho = inner.rho;
+  for (int k = 0; k < M.Q; ++k) out.rho[k] += outer.rho[k];
+  if (dir > 0) out.neg = inner.neg, out.pos = outer.pos;
+  else out.neg = outer.neg, out.pos = inner.pos;
+  return no_u_turn_violated(M, out.neg, out.pos, out.rho);
+}
+
 }  // namespace orc
 
 // ======================================================================== C API
@@ -809,6 +907,66 @@ void orc_hmc_transition(void* h, int64_t n, double* q, double dt,
       status[i] = st, accepted[i] = acc, accept_stat[i] = a_stat, n_done[i] = done;
       if (iters_total) iters_total[i] = tot;
       if (h_out) h_out[i] = acc ? h1 : h0;
+    }
+  }
+}
+
+// One dynamic multinomial HMC transition per chain.  unif: optional [n][n_unif] supplied
+// uniforms (draw k of the transition reads unif[i][k - 1]; Philox beyond n_unif).
+void orc_nuts_transition(void* h, int64_t n, double* q, double dt,
+                         const double* dt_per_chain, int max_depth,
+                         const orc_solver_opts* opts, double max_delta_h,
+                         const double* mom_noise, const double* unif, int n_unif,
+                         uint64_t seed, uint64_t chain0, uint32_t iter, int32_t* status,
+                         double* accept_stat, int32_t* n_step, int32_t* depth_out) {
+  const Model& M = *(Model*)h;
+  StepOpts so = to_step_opts(opts);
+#pragma omp parallel
+  {
+    Work W;
+    W.init(M);
+    Chain C;
+    C.init(M);
+    Tree T, S;
+    T.init(M), S.init(M);
+#pragma omp for schedule(dynamic, 4)
+    for (int64_t i = 0; i < n; ++i) {
+      const int Q = M.Q;
+      std::memcpy(C.q.data(), q + i * Q, sizeof(double) * Q);
+      if (mom_noise) {
+        std::memcpy(C.p.data(), mom_noise + i * Q, sizeof(double) * Q);
+      } else {
+        for (int j = 0; 2 * j < Q; ++j) {
+          double a, b;
+          philox_normal_pair(seed, chain0 + i, iter, (uint32_t)j, &a, &b);
+          C.p[2 * j] = a;
+          if (2 * j + 1 < Q) C.p[2 * j + 1] = b;
+        }
+      }
+      int st0 = evaluate_at(M, W, C) ? ST_OK : ST_LINALG;
+      project_cotangent(M, W, C.J, C.G, C.p.data());
+      NutsCtx X{M, W, so, dt_per_chain ? dt_per_chain[i] : dt, hamiltonian(M, C), max_delta_h,
+                seed, (uint64_t)(chain0 + i), iter, 1u, unif ? unif + i * n_unif : nullptr,
+                n_unif, 0, st0, 0.0};
+      T.neg = C, T.pos = C, T.rho = C.p, T.prop = C.q, T.lw = 0.0;
+      int depth = 0;
+      for (; depth < max_depth && st0 == ST_OK; ++depth) {
+        const int dir = X.draw() < 0.5 ? 1 : -1;
+        if (build_tree(X, depth, dir > 0 ? T.pos : T.neg, dir, S)) break;
+        if (X.draw() < std::exp(S.lw - T.lw)) T.prop = S.prop;
+        T.lw = log_add_exp(T.lw, S.lw);
+        for (int k = 0; k < Q; ++k) T.rho[k] += S.rho[k];
+        if (dir > 0) T.pos = S.pos; else T.neg = S.neg;
+        if (no_u_turn_violated(M, T.neg, T.pos, T.rho)) {
+          ++depth;
+          break;
+        }
+      }
+      std::memcpy(q + i * Q, T.prop.data(), sizeof(double) * Q);
+      status[i] = X.status;
+      accept_stat[i] = X.n_step > 0 ? X.sum_acc / X.n_step : 0.0;
+      n_step[i] = X.n_step;
+      if (depth_out) depth_out[i] = depth;
     }
   }
 }

@@ -226,6 +226,25 @@ class OracleModel:
         return dict(q=q, p=p, status=status, n_done=n_done, iters_fwd=itf, iters_rev=itr,
                     h_init=h0, h_final=h1)  # fmt: skip
 
+    def nuts_transition(self, q, dt, opts, max_depth=10, mom_noise=None, unif=None, seed=0,
+                        chain0=0, iteration=0, max_delta_h=1000.0, dt_per_chain=None):  # fmt: skip
+        """One dynamic multinomial HMC transition per chain (oracle/c/chmc_oracle.cpp
+        `orc_nuts_transition`).  unif: optional [n, n_unif] supplied uniforms."""
+        q = _f(q).copy()
+        n = q.shape[0]
+        status, n_step, depth = (np.empty(n, np.int32) for _ in range(3))
+        a_stat = np.empty(n)
+        mom_noise = None if mom_noise is None else _f(mom_noise)
+        unif = None if unif is None else _f(unif)
+        dpc = None if dt_per_chain is None else _f(dt_per_chain)
+        lib().orc_nuts_transition(
+            self.h, C.c_int64(n), _p(q), C.c_double(dt), _p(dpc), C.c_int(max_depth),
+            C.byref(opts), C.c_double(max_delta_h), _p(mom_noise), _p(unif),
+            C.c_int(0 if unif is None else unif.shape[1]), C.c_uint64(seed),
+            C.c_uint64(chain0), C.c_uint32(iteration), _p(status), _p(a_stat), _p(n_step),
+            _p(depth))  # fmt: skip
+        return dict(q=q, status=status, accept_stat=a_stat, n_step=n_step, depth=depth)
+
     def hmc_transition(self, q, dt, n_step, opts, mom_noise=None, unif=None, seed=0,
                        chain0=0, iteration=0, max_delta_h=1000.0, dt_per_chain=None):  # fmt: skip
         q = _f(q).copy()

@@ -100,3 +100,74 @@ def test_eight_schools_chain_statistics_match_cpu_oracle_chains():
             a, b = f(g[..., j]), f(c[..., j])
             se = np.hypot(mc_standard_error(a), mc_standard_error(b))
             assert abs(a.mean() - b.mean()) < 5 * se, (name, a.mean(), b.mean(), se)
+
+
+# ------------------------------------------------------- dynamic multinomial HMC (NUTS)
+@pytest.mark.parametrize("kind", ["toy", "hier"])
+def test_nuts_transitions_match_oracle_trees(kind):
+    """Tree by tree: the kernel builds its trees iteratively (pending sibling per level),
+    the oracle recursively as Mici does; with the same Philox streams they must take the
+    same number of steps to the same depth, report the same accept statistic and pick
+    the same proposal."""
+    import manifold_lifting_b200 as mlb
+    from test_gpu_parity import make_case
+
+    _, _, cm, gm, gs, q = make_case(kind, "unbounded" if kind == "hier" else None, 640, seed=5)
+    dt = 0.1 if kind == "toy" else 0.25
+    sampler, integ = _sampler(mlb, gs, dt, 0, seed=31)
+    nuts = mlb.samplers.DynamicMultinomialHMC(gs, integ, max_tree_depth=7, seed=31)
+    n, n_iter = q.shape[0], 3
+    nuts.trace_n_step = torch.zeros(n_iter, n, dtype=torch.int32, device="cuda")
+    nuts.trace_depth = torch.zeros(n_iter, n, dtype=torch.int32, device="cuda")
+    acc = torch.zeros(n_iter, n, dtype=torch.float64, device="cuda")
+    qg = mlb._lib.soa_clone(mlb._lib.to_soa(q))
+    nuts._launch(qg, n_iter, trace_accept=acc, chain_offset=1000)
+    qo = q.copy()
+    opts = co.solver_opts(co.SOLVER_NEWTON)
+    same_all = np.ones(n, bool)
+    for it in range(n_iter):
+        r = cm.nuts_transition(qo, dt, opts, max_depth=7, seed=31, chain0=1000, iteration=it)
+        qo = r["q"]
+        ns, dp = nuts.trace_n_step[it].cpu().numpy(), nuts.trace_depth[it].cpu().numpy()
+        same = same_all & (ns == r["n_step"]) & (dp == r["depth"])
+        # a chain whose tree differed once (a draw within rounding of its threshold)
+        # follows another trajectory from then on
+        assert same.mean() > 0.97 - 0.01 * it, (it, same.mean())
+        a = acc[it].cpu().numpy()
+        assert np.abs(a[same] - r["accept_stat"][same]).max() < 1e-9
+        same_all = same
+    assert r["n_step"].max() > 7 and r["depth"].max() >= 3  # real trees were built
+    same_q = np.abs(qg.cpu().numpy() - qo).max(1) < 1e-8
+    assert (same_q | ~same_all).all() and same_q.mean() > 0.9
+
+
+def test_nuts_toy_posterior_moments_and_notebook_anchors():
+    """The reference's default sampler at the notebook's step size: accept statistic
+    0.995-0.996 and no convergence errors (notebooks/Two-dimensional_example.ipynb raw
+    lines 2565-2684, sigma-dependent to the third digit), posterior moments against
+    quadrature, R-hat ~ 1."""
+    import manifold_lifting_b200 as mlb
+
+    sigma = 0.1
+    model = mlb.models.Toy2DModel(sigma, 1.0, 2.0)
+    system = mlb.IndependentAdditiveNoiseModelSystem(model, model.data, model.dim_u)
+    n = 4096
+    q0 = toy_manifold_inits(n, np.random.default_rng(13))
+    _, integ = _sampler(mlb, system, 0.1, 0, seed=0)
+    nuts = mlb.samplers.DynamicMultinomialHMC(system, integ, max_tree_depth=10, seed=8)
+    _, traces, stats = nuts.sample_chains(150, 300, q0, adapters=[mlb.ToleranceAdapter()],
+                                          trace_dim=2)  # fmt: skip
+    th = traces["pos"].cpu().numpy()
+    acc = float(stats["accept_stat"].mean())
+    assert 0.985 < acc < 0.999, acc
+    assert float((stats["convergence_error"] + stats["non_reversible_step"]).mean()) < 5e-3
+    assert 3.0 < float(stats["tree_depth"].mean()) < 7.0
+    want = toy_posterior_moments(sigma)
+    got = {"t0_sq": th[..., 0] ** 2, "t1_sq": th[..., 1] ** 2,
+           "t0_abs": np.abs(th[..., 0]), "t1_abs": np.abs(th[..., 1])}  # fmt: skip
+    for k, x in got.items():
+        se = mc_standard_error(x)
+        assert se < 2e-3 and abs(x.mean() - want[k]) < 5 * se, (k, x.mean(), want[k], se)
+    for j in range(2):
+        r = mlb.parallel.rhat(torch.as_tensor(np.abs(th[:512, :, j])).cuda().contiguous(), "rank")
+        assert r < 1.05, r
