@@ -48,6 +48,10 @@ def parse_args():
                          "host-driven sub-phase kernels (MLB_FLAG_SINGLE_KERNEL)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ess", action="store_true", help="skip the ESS/s leg")
+    ap.add_argument("--ess-sampler", default="both", choices=("both", "nuts", "static"),
+                    help="samplers of the ESS/s leg: dynamic multinomial HMC (the reference's "
+                         "default, utils.py:286-288; key `ess`) and / or static-trajectory "
+                         "Metropolis HMC (key `ess_static`)")
     a = ap.parse_args()
     wl = a.workload
     a.n_chain = a.n_chain or {"fn": 16384, "hh": 1024}.get(wl, 65536)
@@ -245,12 +249,15 @@ def run_reference(args, emit):
 # ------------------------------------------------------------------------ ESS/s leg
 
 ESS_WARM, ESS_MAIN, ESS_N_STEP, ESS_SUBSET, ESS_SEED = 150, 200, 8, 8192, 202101
+ESS_MAX_DEPTH = 10  # max_tree_depth default of the reference (utils.py:70-73)
 
 
-def ess_leg(args, mlb, model, system, q0, rank, world, n, with_cpu):
+def ess_leg(args, mlb, model, system, q0, rank, world, n, with_cpu, nuts=True):
     """Second half of BASELINE.json's metric: bulk-ESS per second of the latent parameters
-    under static-trajectory constrained HMC (Mici StaticMetropolisHMC semantics, n_step=8,
-    dual-averaging warm-up to accept rate 0.8), GPU sampler vs the CPU oracle sampler.
+    under constrained HMC - by default the reference's sampler, dynamic multinomial HMC
+    (utils.py:286-288; `--ess-sampler static` for static-trajectory Metropolis HMC with
+    n_step=8) - with dual-averaging warm-up to accept statistic 0.8, GPU sampler vs the CPU
+    oracle sampler.
 
     The CPU leg continues the SAME chains (Philox streams are keyed by seed / global chain
     id / iteration) from the GPU's post-warm-up states, so both legs have identical ESS
@@ -262,14 +269,17 @@ def ess_leg(args, mlb, model, system, q0, rank, world, n, with_cpu):
     from manifold_lifting_b200 import parallel
     from manifold_lifting_b200.adapters import DualAveragingStepSizeAdapter
     from manifold_lifting_b200.integrators import ConstrainedLeapfrogIntegrator
-    from manifold_lifting_b200.samplers import StaticMetropolisHMC
+    from manifold_lifting_b200.samplers import DynamicMultinomialHMC, StaticMetropolisHMC
     from manifold_lifting_b200.solvers import SOLVER_IDS
 
     solver_fn = {v: k for k, v in SOLVER_IDS.items()}[SOLVERS[args.solver]]
     integ = ConstrainedLeapfrogIntegrator(
         system, args.step_size, projection_solver=solver_fn,
         projection_solver_kwargs=dict(constraint_tol=1e-9, position_tol=1e-8, max_iters=50))
-    sampler = StaticMetropolisHMC(system, integ, n_step=ESS_N_STEP, seed=ESS_SEED)
+    if nuts:
+        sampler = DynamicMultinomialHMC(system, integ, max_tree_depth=ESS_MAX_DEPTH, seed=ESS_SEED)
+    else:
+        sampler = StaticMetropolisHMC(system, integ, n_step=ESS_N_STEP, seed=ESS_SEED)
     state, _, _ = sampler.sample_chains(ESS_WARM, 0, q0, chain_offset=rank * n,
                                         adapters=[DualAveragingStepSizeAdapter(0.8, 0.05)])  # fmt: skip
     eps = float(integ.step_size)
@@ -293,8 +303,12 @@ def ess_leg(args, mlb, model, system, q0, rank, world, n, with_cpu):
                        + stats["non_reversible_step"].sum()])  # fmt: skip
     parallel.all_reduce_sum_(acc)
     out = {
-        "sampler": f"static HMC, n_step={ESS_N_STEP}, {ESS_WARM} warm-up + {ESS_MAIN} main "
-                   f"iterations, dual-averaging target 0.8",
+        "sampler": (f"dynamic multinomial HMC (NUTS), max_tree_depth={ESS_MAX_DEPTH}" if nuts
+                    else f"static HMC, n_step={ESS_N_STEP}")
+                   + f", {ESS_WARM} warm-up + {ESS_MAIN} main iterations, dual-averaging "
+                     f"target 0.8",
+        "mean_tree_depth": float(stats["tree_depth"].mean()) if nuts else None,
+        "mean_steps_per_transition": float(stats["n_step"].mean()) / ESS_MAIN,
         "step_size": eps, "accept_stat": float(acc[0]) / (n * world),
         "integrator_error_rate": float(acc[1]) / (n * world),
         "seconds_main": secs, "chains": n * world,
@@ -316,8 +330,12 @@ def ess_leg(args, mlb, model, system, q0, rank, world, n, with_cpu):
         tr = np.empty((n_cpu, ESS_MAIN, model.dim_u))
         t0 = time.perf_counter()
         for it in range(ESS_MAIN):
-            r = cm.hmc_transition(qc, eps, ESS_N_STEP, opts, seed=ESS_SEED, chain0=0,
-                                  iteration=ESS_WARM + it)  # fmt: skip
+            if nuts:
+                r = cm.nuts_transition(qc, eps, opts, max_depth=ESS_MAX_DEPTH, seed=ESS_SEED,
+                                       chain0=0, iteration=ESS_WARM + it)  # fmt: skip
+            else:
+                r = cm.hmc_transition(qc, eps, ESS_N_STEP, opts, seed=ESS_SEED, chain0=0,
+                                      iteration=ESS_WARM + it)  # fmt: skip
             qc = r["q"]
             tr[:, it] = qc[:, : model.dim_u]
         csecs = time.perf_counter() - t0
@@ -619,13 +637,15 @@ def run_mlb(args, emit):
             r, cores, desc, secs = cpu_oracle_rate(args, 12.0, args.cpu_sample_chains)
             line["cpu_baseline"] = {"value": r, "unit": "steps/s", "cores": cores,
                                     "kind": "port", "sample": desc, "seconds": secs}  # fmt: skip
-    ess = None
+    ess = {}
     if not args.no_ess and args.workload in ("hier", "toy"):
-        ess = ess_leg(args, mlb, model, system, q0, rank, world, n,
-                      with_cpu=not args.no_cpu_baseline and world == 1)  # fmt: skip
+        for key, nuts in (("ess", True), ("ess_static", False)):
+            if args.ess_sampler in ("both", "nuts" if nuts else "static"):
+                ess[key] = ess_leg(args, mlb, model, system, q0, rank, world, n,
+                                   with_cpu=not args.no_cpu_baseline and world == 1,
+                                   nuts=nuts)  # fmt: skip
     if rank == 0:
-        if ess is not None:
-            line["ess"] = ess
+        line.update({k: v for k, v in ess.items() if v is not None})
         emit(line)
     if world > 1:
         dist.barrier()
