@@ -132,10 +132,13 @@ __global__ void __launch_bounds__(kBlock, MLB_LF_MIN_BLOCKS)
       if (!terminate) {
         double lw_cur = h0 - h;
         sum_acc += exp(lw_cur < 0.0 ? lw_cur : 0.0);
-        // the leaf as a one-state subtree
-#pragma unroll 1
-        for (int k = 0; k < Q; ++k)
-          SC(R::CUR + k) = pw[k], SC(R::CUR + Q + k) = pw[k], SC(R::CUR + 2 * Q + k) = qw[k];
+        // the leaf as a one-state subtree, in registers: it is born after the step and
+        // parked before the next one, so it never competes with the step for registers
+        // (the first version kept it in global scratch: 160 GB of DRAM writes per launch
+        // and 5.3 long-scoreboard stall cycles per issue)
+        double c_pf[Q], c_rh[Q], c_pr[Q];
+#pragma unroll
+        for (int k = 0; k < Q; ++k) c_pf[k] = pw[k], c_rh[k] = pw[k], c_pr[k] = qw[k];
         int lvl = 0;
 #pragma unroll 1
         while ((leaf >> lvl) & 1) {  // a left sibling waits at this level: merge
@@ -144,12 +147,11 @@ __global__ void __launch_bounds__(kBlock, MLB_LF_MIN_BLOCKS)
           const double lw_new = log_add_exp(lw_left, lw_cur);
           const bool take_outer = draw() < exp(lw_cur - lw_new);
           double d_first = 0.0, d_last = 0.0;
-#pragma unroll 1
+#pragma unroll
           for (int k = 0; k < Q; ++k) {
-            const double rho = SC(sl + Q + k) + SC(R::CUR + Q + k), pf = SC(sl + k);
-            SC(R::CUR + Q + k) = rho, SC(R::CUR + k) = pf;
-            if (!take_outer) SC(R::CUR + 2 * Q + k) = SC(sl + 2 * Q + k);
-            d_first = fma(pf, rho, d_first), d_last = fma(pw[k], rho, d_last);
+            c_rh[k] += SC(sl + Q + k), c_pf[k] = SC(sl + k);
+            if (!take_outer) c_pr[k] = SC(sl + 2 * Q + k);
+            d_first = fma(c_pf[k], c_rh[k], d_first), d_last = fma(pw[k], c_rh[k], d_last);
           }
           lw_cur = lw_new;
           if (d_first < 0.0 || d_last < 0.0) {
@@ -160,8 +162,9 @@ __global__ void __launch_bounds__(kBlock, MLB_LF_MIN_BLOCKS)
         }
         if (!terminate) {  // park as the pending sibling of level lvl (= depth: complete)
           const int sl = R::slot(lvl);
-#pragma unroll 1
-          for (int k = 0; k < 3 * Q; ++k) SC(sl + k) = SC(R::CUR + k);
+#pragma unroll
+          for (int k = 0; k < Q; ++k)
+            SC(sl + k) = c_pf[k], SC(sl + Q + k) = c_rh[k], SC(sl + 2 * Q + k) = c_pr[k];
           SC(R::lw(na.max_depth) + lvl) = lw_cur;
         }
       }
