@@ -172,7 +172,7 @@ def cpu_oracle_rate(args, target_seconds=12.0, sample_chains=0):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import c_oracle as co
 
-    cores = co.max_threads()
+    cores = co.use_all_cores()
     n = sample_chains or {"fn": 16 * cores, "hh": 4 * cores}.get(
         args.workload, 2048 * max(1, cores // 4))
     data, q, p = make_inputs(args, n, 10**6)
@@ -319,7 +319,7 @@ def ess_leg(args, mlb, model, system, q0, rank, world, n, with_cpu, nuts=True):
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import c_oracle as co
 
-        cores = co.max_threads()
+        cores = co.use_all_cores()
         n_cpu = min(sub, 64 * cores)
         if args.workload == "hier":
             cm = co.OracleModel.hier(model.data["y_obs"], model.data["σ"])

@@ -665,6 +665,15 @@ int orc_dim_u(void* h) { return ((Model*)h)->U; }
 int orc_dim_y(void* h) { return ((Model*)h)->Y; }
 int orc_dim_q(void* h) { return ((Model*)h)->Q; }
 int orc_is_dense(void* h) { return ((Model*)h)->dense ? 1 : 0; }
+// torchrun exports OMP_NUM_THREADS=1 to its workers: the timed CPU legs set the thread
+// count explicitly so that they use the host cores whatever launched them
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 int orc_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -335,3 +335,13 @@ def philox_uniform(seed, chain, iteration):
 
 def max_threads():
     return lib().orc_max_threads()
+
+
+def use_all_cores():
+    """OpenMP threads = the cores this process may run on, whatever OMP_NUM_THREADS says
+    (torchrun sets it to 1 for its workers).  Returns the count."""
+    import os
+
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().orc_set_num_threads(C.c_int(n))
+    return max_threads()
