@@ -437,6 +437,11 @@ struct StepsIO {
   // q, p given as chain-major rows [n][Q] (the reference's layout) instead of [Q][ld];
   // only the register-resident family reads it (it touches q, p once per launch)
   bool row_major = false;
+  // sampler use of the ODE family's host-driven path: project p onto the cotangent space
+  // first (h_init is taken after that), and stop a chain with MLB_ST_H_DIVERGED when
+  // |h - h_init| > max_delta_h after a step (<= 0: no check)
+  bool project_first = false;
+  double max_delta_h = 0.0;
 };
 
 // Table of launchers for one compiled-in model; one translation unit per model so the

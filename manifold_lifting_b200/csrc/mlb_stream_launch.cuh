@@ -356,6 +356,10 @@ template <class M, int SOLVER>
 int phased_leapfrog_steps(const mlb_model* m, const OdeData& D, int64_t n, int64_t ld,
                           const Opts& o, const StepsIO& io, cudaStream_t s);
 
+template <class M, int SOLVER>
+int phased_hmc_sample(const mlb_model* m, const OdeData& D, int64_t n, int64_t ld, double* q,
+                      const Opts& o, const SampleArgs& a, cudaStream_t s);
+
 template <class M>
 struct StreamLaunch {
   static constexpr int U = M::U;
@@ -484,6 +488,11 @@ struct StreamLaunch {
     if (solver > MLB_SOLVER_NEWTON_LS) {
       g_err = "Mici's own solvers are not built for ODE models";
       return MLB_ERR_UNSUPPORTED;
+    }
+    if (!(o.flags & MLB_FLAG_SINGLE_KERNEL) && solver != MLB_SOLVER_NEWTON_LS) {
+      if (solver == MLB_SOLVER_QUASI_NEWTON)
+        return phased_hmc_sample<M, MLB_SOLVER_QUASI_NEWTON>(m, D, n, ld, q, o, a, s);
+      return phased_hmc_sample<M, MLB_SOLVER_NEWTON>(m, D, n, ld, q, o, a, s);
     }
     ScratchBuf sb;
     const int64_t lds = pad32(n);

@@ -345,11 +345,15 @@ __global__ void __launch_bounds__(kStreamBlock)
 }
 
 // [finish a fresh evaluation: add the second-order partials] [half kick] cotangent
-// projection p -= J^T Gram^-1 J p [commit the step / record h_init]; observation-chunked
+// projection p -= J^T Gram^-1 J p [commit the step / record h_init]; observation-chunked.
+// commit: 0 no, 1 a completed step (with the |h - h_init| > max_dh test if max_dh > 0),
+// 2 the momentum refresh of a sampler transition (committed momentum and h_init are those
+// AFTER the projection; no step is counted)
 template <class M, int NCH>
 __global__ void __launch_bounds__(32 * NCH)
     kp_kick_project(PhasedLayout L, int64_t n, int64_t ld, double* p, double* q, double dt,
-                    const double* dt_pc, int fresh, int kick, int first, int commit) {
+                    const double* dt_pc, int fresh, int kick, int first, int commit,
+                    double max_dh) {
   using S = Stream<M>;
   constexpr int U = M::U;
   extern __shared__ double sh[];
@@ -436,8 +440,15 @@ __global__ void __launch_bounds__(32 * NCH)
       if (commit) P.S.cq[a] = qw[a], P.S.cp[a] = pa, hs = fma(pa, pa, hs);
     }
     if (commit) {
-      P.Dv(CD_HLAST, i) = P.Dv(CD_NLD, i) + P.Dv(CD_LOGDET, i) + 0.5 * hs;
-      P.I(CT_DONE, i) += 1;
+      const double h = P.Dv(CD_NLD, i) + P.Dv(CD_LOGDET, i) + 0.5 * hs;
+      P.Dv(CD_HLAST, i) = h;
+      if (commit == 2) {
+        P.Dv(CD_HINIT, i) = h;
+      } else {
+        P.I(CT_DONE, i) += 1;
+        if (max_dh > 0.0 && fabs(h - P.Dv(CD_HINIT, i)) > max_dh)
+          P.I(CT_STATUS, i) = MLB_ST_H_DIVERGED, P.I(CT_ALIVE, i) = 0;
+      }
     }
   }
 }
@@ -683,15 +694,23 @@ int phased_leapfrog_steps(const mlb_model* m, const OdeData& D, int64_t n, int64
         MLB_KP((kp_eval_mid<M, NCH><<<g1, cblk, sh_eval, s>>>(D, L, n, ld, io.q, io.p)));
         MLB_KP((kp_second_order<M><<<g_grp, blk, 0, s>>>(D, L, n, ld, io.q)));
       }
+      bool fresh_g = fresh;  // the second-order partials are added to the gradient once
+      if (first && io.project_first) {  // momentum refresh: project, then h_init
+        MLB_KP((kp_kick_project<M, NCH><<<g1, cblk, sh_proj, s>>>(
+            L, n, ld, io.p, io.q, io.dt, io.dt_pc, 1, 0, 0, 2, 0.0)));
+        first = false, fresh_g = false;
+        if (io.n_step <= 0) break;
+      }
       if (io.n_step <= 0) {  // only h_init is wanted
         MLB_KP((kp_kick_project<M, NCH><<<g1, cblk, sh_proj, s>>>(L, n, ld, io.p, io.q, io.dt, io.dt_pc,
-                                                      1, 0, 1, 0)));
+                                                      1, 0, 1, 0, 0.0)));
         first = false;
         break;
       }
       // note: with first == true the Hamiltonian is recorded BEFORE the kick
-      MLB_KP((kp_kick_project<M, NCH><<<g1, cblk, sh_proj, s>>>(L, n, ld, io.p, io.q, io.dt, io.dt_pc,
-                                                    fresh, sub != 1, first, sub == 2)));
+      MLB_KP((kp_kick_project<M, NCH><<<g1, cblk, sh_proj, s>>>(
+          L, n, ld, io.p, io.q, io.dt, io.dt_pc, fresh_g, sub != 1, first, sub == 2,
+          io.max_delta_h)));
       first = false;
       if (sub == 2) break;
       const double sign = sub == 0 ? 1.0 : -1.0;
@@ -718,6 +737,137 @@ int phased_leapfrog_steps(const mlb_model* m, const OdeData& D, int64_t n, int64
   MLB_KP((kp_finish<M><<<g1, blk, 0, s>>>(L, n, io.status, io.n_done, io.iters_fwd,
                                           io.iters_rev, io.h_init, io.h_final)));
 #undef MLB_KP
+  return MLB_OK;
+}
+
+// ------------------------------------------------------ host-driven static HMC sampler
+// One transition = kp_smp_begin (momentum draw, proposal copy, per-chain step size) ->
+// phased_leapfrog_steps on the proposal (momentum refresh projected first, |dh| test per
+// step) -> kp_smp_end (Metropolis accept, statistics, trace, dual averaging): the
+// semantics of ks_hmc_sample (mlb_stream_launch.cuh), with the trajectory on the
+// sub-phase kernels.  Per-chain rows after the proposal: dt, h_init, h_final (doubles),
+// status, n_done, iters_fwd, iters_rev (int32).
+struct SmpLayout {
+  double* base;  // [2 Q + 3 + 2][lds]
+  int64_t lds;
+  int Q;
+  __host__ __device__ double* qc() const { return base; }
+  __host__ __device__ double* pc() const { return base + (int64_t)Q * lds; }
+  __host__ __device__ double* dt() const { return base + (int64_t)2 * Q * lds; }
+  __host__ __device__ double* h0() const { return dt() + lds; }
+  __host__ __device__ double* h1() const { return dt() + 2 * lds; }
+  __host__ __device__ int32_t* ints() const { return reinterpret_cast<int32_t*>(dt() + 3 * lds); }
+  __host__ __device__ int32_t* status() const { return ints(); }
+  __host__ __device__ int32_t* n_done() const { return ints() + lds; }
+  __host__ __device__ int32_t* itf() const { return ints() + 2 * lds; }
+  __host__ __device__ int32_t* itr() const { return ints() + 3 * lds; }
+  static int64_t rows(int Q) { return 2 * (int64_t)Q + 3 + 2; }
+};
+
+template <int NCH>
+__global__ void __launch_bounds__(32 * NCH)
+    kp_smp_begin(SmpLayout W, int64_t n, int64_t ld, const double* q, SampleArgs a, int it) {
+  const int64_t i = (int64_t)blockIdx.x * 32 + threadIdx.x;
+  if (i >= n) return;
+  const int Q = W.Q;
+  int k0, k1;
+  row_chunk<NCH>(Q, k0, k1);
+  double* qc = W.qc() + i;
+  double* pc = W.pc() + i;
+  const double* mn = a.mom_noise ? a.mom_noise + (int64_t)it * Q * ld + i : nullptr;
+#pragma unroll 1
+  for (int k = k0; k < k1; ++k) {
+    qc[(int64_t)k * W.lds] = q[(int64_t)k * ld + i];
+    double v;
+    if (mn) {
+      v = mn[(int64_t)k * ld];
+    } else {
+      double n0, n1;
+      philox_normal_pair(a.seed, a.chain0 + (uint64_t)i, a.iter0 + (uint32_t)it,
+                         (uint32_t)(k >> 1), n0, n1);
+      v = (k & 1) ? n1 : n0;
+    }
+    pc[(int64_t)k * W.lds] = v;
+  }
+  if (threadIdx.y == 0) W.dt()[i] = a.adapt ? a.adapt[4 * ld + i] : a.dt;
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(32 * NCH)
+    kp_smp_end(SmpLayout W, int64_t n, int64_t ld, double* q, SampleArgs a, int it) {
+  const int64_t i = (int64_t)blockIdx.x * 32 + threadIdx.x;
+  if (i >= n) return;
+  const int Q = W.Q;
+  const int st = W.status()[i];
+  double a_stat = 0.0;
+  bool accept = false;
+  if (st == MLB_ST_OK) {
+    const double d = W.h0()[i] - W.h1()[i];
+    a_stat = (d != d) ? 0.0 : exp(d < 0.0 ? d : 0.0);
+    const double u = a.unif ? a.unif[(int64_t)it * ld + i]
+                            : philox_uniform(a.seed, a.chain0 + (uint64_t)i,
+                                             a.iter0 + (uint32_t)it);
+    accept = u < a_stat;
+  }
+  int k0, k1;
+  row_chunk<NCH>(Q, k0, k1);
+  if (accept) {
+#pragma unroll 4
+    for (int k = k0; k < k1; ++k) q[(int64_t)k * ld + i] = W.qc()[(int64_t)k * W.lds + i];
+  }
+  if (a.trace_q && (it + 1) % a.trace_every == 0) {
+    double* tq = a.trace_q + (int64_t)((it + 1) / a.trace_every - 1) * a.trace_dim * ld + i;
+    for (int k = k0; k < k1 && k < a.trace_dim; ++k)
+      tq[(int64_t)k * ld] = accept ? W.qc()[(int64_t)k * W.lds + i] : q[(int64_t)k * ld + i];
+  }
+  if (threadIdx.y != 0) return;
+  if (a.trace_accept) a.trace_accept[(int64_t)it * ld + i] = a_stat;
+  if (a.stats) {
+    a.stats[0 * ld + i] += a_stat, a.stats[1 * ld + i] += accept;
+    a.stats[2 * ld + i] +=
+        (st == MLB_ST_DIVERGED || st == MLB_ST_NOT_CONVERGED || st == MLB_ST_LINALG);
+    a.stats[3 * ld + i] += (st == MLB_ST_NON_REVERSIBLE);
+    a.stats[4 * ld + i] += (st == MLB_ST_H_DIVERGED);
+    a.stats[5 * ld + i] += W.n_done()[i];
+    a.stats[6 * ld + i] += W.itf()[i] + W.itr()[i];
+  }
+  if (a.last_status) a.last_status[i] = st;
+  if (a.adapt) {  // Mici DualAveragingStepSizeAdapter.update
+    double ad_iter = a.adapt[0 * ld + i], ad_smooth = a.adapt[1 * ld + i];
+    double ad_err = a.adapt[2 * ld + i];
+    const double ad_target = a.adapt[3 * ld + i];
+    ad_iter += 1;
+    const double w = 1.0 / (a.a_offset + ad_iter);
+    ad_err = (1.0 - w) * ad_err + w * (a.a_target - a_stat);
+    const double sw = pow(1.0 / ad_iter, a.a_decay);
+    const double log_eps = ad_target - ad_err * sqrt(ad_iter) / a.a_reg;
+    ad_smooth = (1.0 - sw) * ad_smooth + sw * log_eps;
+    a.adapt[0 * ld + i] = ad_iter, a.adapt[1 * ld + i] = ad_smooth;
+    a.adapt[2 * ld + i] = ad_err, a.adapt[4 * ld + i] = exp(log_eps);
+  }
+}
+
+template <class M, int SOLVER>
+int phased_hmc_sample(const mlb_model* m, const OdeData& D, int64_t n, int64_t ld, double* q,
+                      const Opts& o, const SampleArgs& a, cudaStream_t s) {
+  constexpr int NCH = kChunkWarps;
+  SmpLayout W;
+  W.lds = pad32(n), W.Q = M::U + D.Y;
+  ScratchBuf sb;
+  int rc = sb.alloc(SmpLayout::rows(W.Q), W.lds, s);
+  if (rc != MLB_OK) return rc;
+  W.base = sb.p;
+  const dim3 g1(sgrid(n)), cblk(32, NCH);
+  for (int it = 0; it < a.n_iter; ++it) {
+    kp_smp_begin<NCH><<<g1, cblk, 0, s>>>(W, n, ld, q, a, it);
+    if ((rc = finish_launch()) != MLB_OK) return rc;
+    StepsIO io{W.qc(), W.pc(), 0.0, W.dt(), a.n_step, W.status(), W.n_done(), W.itf(),
+               W.itr(), W.h0(), W.h1()};
+    io.project_first = true, io.max_delta_h = a.max_delta_h;
+    if ((rc = phased_leapfrog_steps<M, SOLVER>(m, D, n, W.lds, o, io, s)) != MLB_OK) return rc;
+    kp_smp_end<NCH><<<g1, cblk, 0, s>>>(W, n, ld, q, a, it);
+    if ((rc = finish_launch()) != MLB_OK) return rc;
+  }
   return MLB_OK;
 }
 

@@ -311,9 +311,13 @@ def test_hh_ops_and_step_match_autodiff_golden():
         assert rel_err(cpu(out.h_final), g[f"step_h_{sid}"]) < 1e-7
 
 
-def test_fn_hmc_transitions_match_oracle_decisions():
-    """Static-HMC transitions of the streaming family: accept / reject decisions, accept
-    statistics and new positions with supplied momentum noise and uniforms."""
+@pytest.mark.parametrize("single_kernel", [False, True])
+def test_fn_hmc_transitions_match_oracle_decisions(single_kernel):
+    """Static-HMC transitions of the streaming family (host-driven sub-phase kernels by
+    default, one kernel with MLB_FLAG_SINGLE_KERNEL): accept / reject decisions, accept
+    statistics and new positions with supplied momentum noise and uniforms, then with the
+    device Philox streams; dual averaging and the per-chain statistics of the two paths
+    against each other."""
     mlb, g, cm, gm, gs = fn_case()
     q = fn_states(cm, 48)
     rng = np.random.default_rng(5)
@@ -330,6 +334,7 @@ def test_fn_hmc_transitions_match_oracle_decisions():
     integ = mlb.integrators.ConstrainedLeapfrogIntegrator(
         gs, dt, projection_solver=mlb.jitted_solve_projection_onto_manifold_newton,
         projection_solver_kwargs=dict(constraint_tol=1e-9, position_tol=1e-8, max_iters=50))
+    integ.single_kernel = single_kernel
     sampler = mlb.samplers.StaticMetropolisHMC(gs, integ, n_step=n_step, seed=1)
     qg = mlb._lib.soa_clone(mlb._lib.to_soa(q))
     tr_acc = torch.empty(n_iter, n, dtype=torch.float64, device="cuda")
@@ -345,6 +350,29 @@ def test_fn_hmc_transitions_match_oracle_decisions():
     qg2 = mlb._lib.soa_clone(mlb._lib.to_soa(q))
     sampler2._launch(qg2, 1, chain_offset=100)
     assert scaled_err(cpu(qg2), qo2) < 1e-8
+
+
+def test_fn_sampler_paths_agree_with_adaptation_and_traces():
+    """sample_chains (dual-averaging warm-up, traces, statistics) through the host-driven
+    sampler and through the one-kernel sampler: same step size, same traces."""
+    mlb, g, cm, gm, gs = fn_case()
+    q = fn_states(cm, 40)
+    res = []
+    for single in (False, True):
+        integ = mlb.integrators.ConstrainedLeapfrogIntegrator(
+            gs, 0.01, projection_solver=mlb.jitted_solve_projection_onto_manifold_newton,
+            projection_solver_kwargs=dict(constraint_tol=1e-9, position_tol=1e-8, max_iters=50))
+        integ.single_kernel = single
+        sampler = mlb.samplers.StaticMetropolisHMC(gs, integ, n_step=2, seed=3)
+        _, traces, stats = sampler.sample_chains(
+            3, 3, q, adapters=[mlb.adapters.DualAveragingStepSizeAdapter(0.8)], trace_dim=9)
+        res.append((float(integ.step_size), cpu(traces["pos"]), {k: cpu(v) for k, v in stats.items()}))
+    (e0, t0, s0), (e1, t1, s1) = res
+    assert abs(e0 - e1) < 1e-9 * e1
+    same = np.abs(t0 - t1).max(axis=(1, 2)) < 1e-7
+    assert same.mean() > 0.9
+    assert np.abs(s0["accept_stat"] - s1["accept_stat"])[same].max() < 1e-6
+    assert (s0["n_step"] == s1["n_step"])[same].all()
 
 
 def test_fn_host_buffer_entry_point():
