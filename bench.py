@@ -252,7 +252,8 @@ ESS_WARM, ESS_MAIN, ESS_N_STEP, ESS_SUBSET, ESS_SEED = 150, 200, 8, 8192, 202101
 ESS_MAX_DEPTH = 10  # max_tree_depth default of the reference (utils.py:70-73)
 
 
-def ess_leg(args, mlb, model, system, q0, rank, world, n, with_cpu, nuts=True):
+def ess_leg(args, mlb, model, system, q0, rank, world, n, with_cpu, nuts=True,
+            oracle_model=None):
     """Second half of BASELINE.json's metric: bulk-ESS per second of the latent parameters
     under constrained HMC - by default the reference's sampler, dynamic multinomial HMC
     (utils.py:286-288; `--ess-sampler static` for static-trajectory Metropolis HMC with
@@ -265,6 +266,9 @@ def ess_leg(args, mlb, model, system, q0, rank, world, n, with_cpu, nuts=True):
     the two traces is reported as a sampler-level parity figure.  ESS is estimated on
     the first ESS_SUBSET chains of each rank and scaled to the chain count."""
     import torch
+
+    ode = args.workload in ("fn", "hh")
+    ESS_WARM, ESS_MAIN, ESS_N_STEP = (30, 40, 4) if ode else (150, 200, 8)
 
     from manifold_lifting_b200 import parallel
     from manifold_lifting_b200.adapters import DualAveragingStepSizeAdapter
@@ -320,8 +324,10 @@ def ess_leg(args, mlb, model, system, q0, rank, world, n, with_cpu, nuts=True):
         import c_oracle as co
 
         cores = co.use_all_cores()
-        n_cpu = min(sub, 64 * cores)
-        if args.workload == "hier":
+        n_cpu = min(sub, (2 if ode else 64) * cores)
+        if oracle_model is not None:
+            cm = oracle_model(co)
+        elif args.workload == "hier":
             cm = co.OracleModel.hier(model.data["y_obs"], model.data["σ"])
         else:
             cm = co.OracleModel.toy(model.sigma, model.y, model.coeff)
@@ -644,6 +650,12 @@ def run_mlb(args, emit):
                 ess[key] = ess_leg(args, mlb, model, system, q0, rank, world, n,
                                    with_cpu=not args.no_cpu_baseline and world == 1,
                                    nuts=nuts)  # fmt: skip
+    elif not args.no_ess and args.workload == "fn":
+        # the dynamic sampler is built for the toy / hierarchical models only
+        ess["ess_static"] = ess_leg(
+            args, mlb, model, system, q0, rank, world, n,
+            with_cpu=not args.no_cpu_baseline and world == 1, nuts=False,
+            oracle_model=lambda co: co.OracleModel.fn(*data))  # fmt: skip
     if rank == 0:
         line.update({k: v for k, v in ess.items() if v is not None})
         emit(line)
