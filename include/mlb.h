@@ -262,7 +262,10 @@ double mlb_philox_uniform_host(uint64_t seed, uint64_t chain, uint32_t iter);
  * normals as in mlb_hmc_sample; the k-th uniform of a transition is Philox counter
  * (k, iter, chain | 1 << 63), k = 1, 2, ... in order of use.  Arguments as mlb_hmc_sample;
  * trace_n_step / trace_depth ([n_iter][n], NULL to skip) receive the tree size / depth
- * of every transition.  Toy / hierarchical models only (MLB_ERR_UNSUPPORTED otherwise). */
+ * of every transition.  Toy / hierarchical models: every chain builds its tree inside one
+ * kernel (asynchronous).  ODE models: the trees of all chains grow in lock-step rounds
+ * driven from the host over the sub-phase kernels (quasi-Newton / Newton solvers; the
+ * call blocks the calling thread). */
 int mlb_nuts_sample(const mlb_model* m, int64_t n, int64_t ld, double* q, double dt,
                     int32_t max_tree_depth, int32_t n_iter, const mlb_solver_opts* opts,
                     double max_delta_h, uint64_t seed, uint64_t chain0, uint32_t iter0,

@@ -373,7 +373,7 @@ int mlb_nuts_sample(const mlb_model* m, int64_t n, int64_t ld, double* q, double
   MLB_ARG(q && opts && n_iter >= 0 && max_tree_depth >= 0 && max_tree_depth <= 20);
   MLB_ARG(!adapt || adapt_opts);
   if (!m->ops->nuts) {
-    g_err = "the dynamic sampler is built for the toy / hierarchical models only";
+    g_err = "the dynamic sampler is not built for this model";
     return MLB_ERR_UNSUPPORTED;
   }
   SampleArgs a;

@@ -442,6 +442,10 @@ struct StepsIO {
   // |h - h_init| > max_delta_h after a step (<= 0: no check)
   bool project_first = false;
   double max_delta_h = 0.0;
+  // chains with alive_mask[i] == 0 are left untouched (status MLB_ST_OK, nothing done);
+  // NULL = all chains (the host-driven dynamic sampler steps only the chains whose tree
+  // is still growing)
+  const int32_t* alive_mask = nullptr;
 };
 
 // Table of launchers for one compiled-in model; one translation unit per model so the

@@ -360,6 +360,10 @@ template <class M, int SOLVER>
 int phased_hmc_sample(const mlb_model* m, const OdeData& D, int64_t n, int64_t ld, double* q,
                       const Opts& o, const SampleArgs& a, cudaStream_t s);
 
+template <class M, int SOLVER>
+int phased_nuts_sample(const mlb_model* m, const OdeData& D, int64_t n, int64_t ld, double* q,
+                       const Opts& o, const SampleArgs& a, const NutsArgs& na, cudaStream_t s);
+
 template <class M>
 struct StreamLaunch {
   static constexpr int U = M::U;
@@ -506,6 +510,17 @@ struct StreamLaunch {
     if (solver == MLB_SOLVER_NEWTON) return go.template operator()<MLB_SOLVER_NEWTON>();
     return go.template operator()<MLB_SOLVER_NEWTON_LS>();
   }
+  static int nuts(const mlb_model* m, int solver, int64_t n, int64_t ld, double* q,
+                  const Opts& o, const SampleArgs& a, const NutsArgs& na, cudaStream_t s) {
+    MLB_ODE();
+    if (solver > MLB_SOLVER_NEWTON) {
+      g_err = "the host-driven dynamic sampler takes the quasi-Newton and Newton solvers";
+      return MLB_ERR_UNSUPPORTED;
+    }
+    if (solver == MLB_SOLVER_QUASI_NEWTON)
+      return phased_nuts_sample<M, MLB_SOLVER_QUASI_NEWTON>(m, D, n, ld, q, o, a, na, s);
+    return phased_nuts_sample<M, MLB_SOLVER_NEWTON>(m, D, n, ld, q, o, a, na, s);
+  }
 #undef MLB_ODE
 };
 
@@ -514,7 +529,7 @@ ModelOps make_stream_ops(int model, int param) {
   using L = StreamLaunch<M>;
   return ModelOps{model, 0 /* any dim_y */, param, &L::constr, &L::jacob, &L::decompose,
                   &L::logdet, &L::nld, &L::block_op, &L::project_cotangent, &L::solve,
-                  &L::steps, &L::sample, nullptr};
+                  &L::steps, &L::sample, &L::nuts};
 }
 
 }  // namespace mlb

@@ -152,16 +152,20 @@ MLB_DEV void cta_bcast_from_warp0(double (&v)[R], double* sh) {
 
 template <class M, int NCH>
 __global__ void __launch_bounds__(32 * NCH)
-    kp_begin(PhasedLayout L, int64_t n, int64_t ld, const double* q, const double* p) {
+    kp_begin(PhasedLayout L, int64_t n, int64_t ld, const double* q, const double* p,
+             const int32_t* alive_mask) {
   MLB_PH_INDEX();
   const int Q = L.U + L.Y;
   const Col qw = col(q, ld, i), pw = col(p, ld, i);
+  const int alive = alive_mask ? alive_mask[i] != 0 : 1;
   int k0, k1;
   row_chunk<NCH>(Q, k0, k1);
+  if (alive) {
 #pragma unroll 4
-  for (int k = k0; k < k1; ++k) P.S.cq[k] = qw[k], P.S.cp[k] = pw[k];
+    for (int k = k0; k < k1; ++k) P.S.cq[k] = qw[k], P.S.cp[k] = pw[k];
+  }
   if (threadIdx.y != 0) return;
-  P.I(CT_ALIVE, i) = 1, P.I(CT_ACTIVE, i) = 0, P.I(CT_ITERS, i) = 0;
+  P.I(CT_ALIVE, i) = alive, P.I(CT_ACTIVE, i) = 0, P.I(CT_ITERS, i) = 0;
   P.I(CT_STATUS, i) = MLB_ST_OK, P.I(CT_DONE, i) = 0, P.I(CT_TF, i) = 0, P.I(CT_TR, i) = 0;
   P.I(CT_NCONSTR, i) = 0;
   P.Dv(CD_HINIT, i) = nan(""), P.Dv(CD_HLAST, i) = nan("");
@@ -684,7 +688,7 @@ int phased_leapfrog_steps(const mlb_model* m, const OdeData& D, int64_t n, int64
     return *host_count;
   };
   cudaMemsetAsync(counter, 0, sizeof(int), s);
-  MLB_KP((kp_begin<M, NCH><<<g1, cblk, 0, s>>>(L, n, ld, io.q, io.p)));
+  MLB_KP((kp_begin<M, NCH><<<g1, cblk, 0, s>>>(L, n, ld, io.q, io.p, io.alive_mask)));
   bool first = true;
   for (int step = 0; step < io.n_step || first; ++step) {
     for (int sub = 0; sub < 3; ++sub) {

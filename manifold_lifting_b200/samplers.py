@@ -126,7 +126,8 @@ class StaticMetropolisHMC:
 class DynamicMultinomialHMC(StaticMetropolisHMC):
     """Mici `DynamicMultinomialHMC(system, integrator, rng, max_tree_depth=10,
     max_delta_h=1000)` as the reference constructs it (example_models/utils.py:286-288),
-    batched: every chain builds its own tree inside one kernel (`mlb_nuts_sample`).
+    batched: every chain builds its own tree inside one kernel (toy / hierarchical models)
+    or all trees grow in host-driven lock-step rounds (ODE models) (`mlb_nuts_sample`).
     `sample_chains` and the adapters work as for the static sampler; `stats` additionally
     reports the mean tree depth, and `n_step` the integrator steps taken."""
 

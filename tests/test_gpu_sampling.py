@@ -171,3 +171,41 @@ def test_nuts_toy_posterior_moments_and_notebook_anchors():
     for j in range(2):
         r = mlb.parallel.rhat(torch.as_tensor(np.abs(th[:512, :, j])).cuda().contiguous(), "rank")
         assert r < 1.05, r
+
+
+def test_nuts_host_driven_ode_family_matches_oracle_trees():
+    """FitzHugh-Nagumo: the dynamic sampler driven from the host over the sub-phase kernels
+    (one round = one step of every chain whose tree is still growing) against the oracle's
+    recursive trees, same Philox streams: tree sizes, depths, accept statistics, proposals."""
+    import manifold_lifting_b200 as mlb
+    from _cases import fn_data, fn_states
+
+    g, y_obs = fn_data()
+    cm = co.OracleModel.fn(y_obs, g["t_seq"], g["dt"], "unbounded")
+    gm = mlb.models.FitzHughNagumoModel(y_obs, g["t_seq"], g["dt"], "unbounded")
+    gs = mlb.IndependentAdditiveNoiseModelSystem(gm, gm.data, gm.dim_u)
+    q = fn_states(cm, 40)
+    dt, depth_max, n_iter = 0.02, 4, 2
+    _, integ = _sampler(mlb, gs, dt, 0, seed=0)
+    nuts = mlb.samplers.DynamicMultinomialHMC(gs, integ, max_tree_depth=depth_max, seed=23)
+    n = q.shape[0]
+    nuts.trace_n_step = torch.zeros(n_iter, n, dtype=torch.int32, device="cuda")
+    nuts.trace_depth = torch.zeros(n_iter, n, dtype=torch.int32, device="cuda")
+    acc = torch.zeros(n_iter, n, dtype=torch.float64, device="cuda")
+    qg = mlb._lib.soa_clone(mlb._lib.to_soa(q))
+    nuts._launch(qg, n_iter, trace_accept=acc, chain_offset=500)
+    qo = q.copy()
+    opts = co.solver_opts(co.SOLVER_NEWTON)
+    same_all = np.ones(n, bool)
+    for it in range(n_iter):
+        r = cm.nuts_transition(qo, dt, opts, max_depth=depth_max, seed=23, chain0=500,
+                               iteration=it)  # fmt: skip
+        qo = r["q"]
+        ns, dp = nuts.trace_n_step[it].cpu().numpy(), nuts.trace_depth[it].cpu().numpy()
+        same = same_all & (ns == r["n_step"]) & (dp == r["depth"])
+        assert same.mean() > 0.85, (it, same.mean(), ns, r["n_step"])
+        assert np.abs(acc[it].cpu().numpy()[same] - r["accept_stat"][same]).max() < 1e-6
+        same_all = same
+    assert r["n_step"].max() >= 7
+    dq = np.abs(qg.cpu().numpy() - qo) / np.maximum(np.abs(qo).max(1, keepdims=True), 1.0)
+    assert (dq.max(1)[same_all] < 1e-7).all()
