@@ -269,6 +269,8 @@ def ess_leg(args, mlb, model, system, q0, rank, world, n, with_cpu, nuts=True,
 
     ode = args.workload in ("fn", "hh")
     ESS_WARM, ESS_MAIN, ESS_N_STEP = (30, 40, 4) if ode else (150, 200, 8)
+    if ode and nuts:
+        ESS_WARM, ESS_MAIN = 15, 20
 
     from manifold_lifting_b200 import parallel
     from manifold_lifting_b200.adapters import DualAveragingStepSizeAdapter
@@ -651,11 +653,15 @@ def run_mlb(args, emit):
                                    with_cpu=not args.no_cpu_baseline and world == 1,
                                    nuts=nuts)  # fmt: skip
     elif not args.no_ess and args.workload == "fn":
-        # the dynamic sampler is built for the toy / hierarchical models only
-        ess["ess_static"] = ess_leg(
-            args, mlb, model, system, q0, rank, world, n,
-            with_cpu=not args.no_cpu_baseline and world == 1, nuts=False,
-            oracle_model=lambda co: co.OracleModel.fn(*data))  # fmt: skip
+        # static sampler by default; the host-driven dynamic sampler (a transition costs as
+        # many lock-step rounds as the largest tree of the batch) with --ess-sampler nuts
+        for key, nuts in (("ess", True), ("ess_static", False)):
+            if args.ess_sampler == ("nuts" if nuts else "static") or (
+                    args.ess_sampler == "both" and not nuts):
+                ess[key] = ess_leg(
+                    args, mlb, model, system, q0, rank, world, n,
+                    with_cpu=not args.no_cpu_baseline and world == 1, nuts=nuts,
+                    oracle_model=lambda co: co.OracleModel.fn(*data))  # fmt: skip
     if rank == 0:
         line.update({k: v for k, v in ess.items() if v is not None})
         emit(line)
