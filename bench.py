@@ -652,7 +652,7 @@ def run_mlb(args, emit):
                 ess[key] = ess_leg(args, mlb, model, system, q0, rank, world, n,
                                    with_cpu=not args.no_cpu_baseline and world == 1,
                                    nuts=nuts)  # fmt: skip
-    elif not args.no_ess and args.workload == "fn":
+    elif not args.no_ess and args.workload in ("fn", "hh"):
         # static sampler by default; the host-driven dynamic sampler (a transition costs as
         # many lock-step rounds as the largest tree of the batch) with --ess-sampler nuts
         for key, nuts in (("ess", True), ("ess_static", False)):
@@ -661,7 +661,8 @@ def run_mlb(args, emit):
                 ess[key] = ess_leg(
                     args, mlb, model, system, q0, rank, world, n,
                     with_cpu=not args.no_cpu_baseline and world == 1, nuts=nuts,
-                    oracle_model=lambda co: co.OracleModel.fn(*data))  # fmt: skip
+                    oracle_model=(lambda co: co.OracleModel.fn(*data)) if args.workload == "fn"
+                    else (lambda co: co.OracleModel.hh(y_obs, consts, "normal")))  # fmt: skip
     if rank == 0:
         line.update({k: v for k, v in ess.items() if v is not None})
         emit(line)
