@@ -455,6 +455,11 @@ def run_mlb(args, emit):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the mlb arm)")
     torch.cuda.set_device(local)
+    bound_cpus = 0
+    if world > 1:  # one process per GPU: stay on the cores (and NUMA node) next to it
+        from manifold_lifting_b200 import parallel as _par
+
+        bound_cpus = _par.bind_to_gpu_cpus(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -612,6 +617,7 @@ def run_mlb(args, emit):
                 "step_size": args.step_size, "solver": args.solver,
                 "constraint_tol": 1e-9, "position_tol": 1e-8, "reverse_check_tol": 2e-8,
                 "chains_total": n * world, "mean_projection_iters_per_step": mean_iters,
+                "cpus_bound_per_rank": bound_cpus or None,
                 "failed_chain_fraction": failed,
                 "timing": "sum of per-step CUDA-event intervals on the launch stream; "
                           "state reset and L2 flushed (256 MiB memset) between steps, "

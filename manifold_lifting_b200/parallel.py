@@ -44,6 +44,37 @@ def init_from_env(backend=None):
     return world()
 
 
+def bind_to_gpu_cpus(local_rank=None):
+    """Pin this process (and the pinned host buffers it allocates afterwards, by first
+    touch) to the CPU cores NVML reports as local to its GPU, so that with one process per
+    GPU on a multi-socket host the host <-> device copies do not cross the socket
+    interconnect.  (On this pool's 8 x B200 boxes NVML reports all 32 cores as local to
+    every GPU, so it changes nothing there: the host-entry throughput of 8 ranks stays at
+    4.2x of one rank - the ranks share PCIe uplinks - while the device throughput is 7.9x.)
+    Returns the number of cores bound to, or 0 if NVML / affinity calls are unavailable."""
+    if not hasattr(os, "sched_setaffinity"):
+        return 0
+    local = int(os.environ.get("LOCAL_RANK", "0")) if local_rank is None else int(local_rank)
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = (int(visible.split(",")[local])
+                if visible and visible.replace(",", "").isdigit() else local)  # fmt: skip
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return 0
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:  # noqa: BLE001  (NVML missing, containers without affinity rights, ...)
+        return 0
+
+
 def shard_chains(n_chain_total, rank=None, world_size=None):
     """Contiguous block of global chain indices owned by `rank`: (first, count).  The
     first `n % world` ranks get one extra chain.  Global chain ids key the Philox streams,
