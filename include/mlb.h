@@ -274,6 +274,18 @@ int mlb_nuts_sample(const mlb_model* m, int64_t n, int64_t ld, double* q, double
                     double* trace_accept, int32_t* trace_n_step, int32_t* trace_depth,
                     double* stats, int32_t* last_status, void* stream);
 
+/* ---- mlift.linalg tridiagonal primitives (reference mlift/linalg.py:46-114; used by the
+ * state-space systems' "tridiagonal + low rank" Gram algebra, systems.py:1189-1238),
+ * batched over chains.  All arrays component-major with leading dimension ld >= n:
+ * a, c [dim-1][ld] (lower / upper diagonal), b [dim][ld] (main diagonal),
+ * d, x [n_rhs][dim][ld] (the reference vmaps the solve over right-hand sides,
+ * systems.py:1193-1195, 1221-1223), out [n]. */
+int mlb_tridiagonal_solve(int64_t n, int32_t dim, int32_t n_rhs, int64_t ld, const double* a,
+                          const double* b, const double* c, const double* d, double* x,
+                          void* stream);
+int mlb_tridiagonal_pos_def_log_det(int64_t n, int32_t dim, int64_t ld, const double* a,
+                                    const double* b, double* out, void* stream);
+
 /* ---- host-buffer entry point (what a reference-side binding calls; see
  * INTEGRATION.md).  q, p are HOST arrays in the reference's natural layout
  * [n_chain][Q] row-major (one NumPy `state.pos` per row); the call stages them through

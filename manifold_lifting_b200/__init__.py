@@ -6,8 +6,8 @@ imports (`import mlift`, `from mlift.systems import ...`) resolve to the CUDA pa
 """
 import sys
 
-from . import (_lib, adapters, errors, integrators, models, parallel, samplers, solvers, states,
-               systems, transitions)  # fmt: skip
+from . import (_lib, adapters, errors, integrators, linalg, models, parallel, samplers, solvers,
+               states, systems, transitions)  # fmt: skip
 from .adapters import *  # noqa: F401,F403
 from .solvers import *  # noqa: F401,F403
 from .systems import *  # noqa: F401,F403
@@ -17,6 +17,6 @@ def install_as_mlift():
     """Register this package under the name `mlift` (drop-in for the reference)."""
     me = sys.modules[__name__]
     sys.modules.setdefault("mlift", me)
-    for sub in ("systems", "solvers", "adapters", "transitions"):
+    for sub in ("systems", "solvers", "adapters", "transitions", "linalg"):
         sys.modules.setdefault(f"mlift.{sub}", getattr(me, sub))
     return me

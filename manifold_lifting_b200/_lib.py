@@ -34,6 +34,7 @@ EXPORTS = (
     "mlb_philox_normals_host", "mlb_philox_uniform_host", "mlb_leapfrog_steps_host",
     "mlb_aos_to_soa", "mlb_soa_to_aos", "mlb_launch_count", "mlb_measure_fp64_tflops",
     "mlb_selftest_fast_math", "mlb_selftest_exp", "mlb_nuts_sample",
+    "mlb_tridiagonal_solve", "mlb_tridiagonal_pos_def_log_det",
 )  # fmt: skip
 
 

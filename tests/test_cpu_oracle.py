@@ -237,3 +237,22 @@ def test_oracle_dynamic_sampler_reproduces_toy_posterior_and_notebook_accept_rat
         x = tr[..., j] ** 2
         se = mc_standard_error(x)
         assert se < 3e-3 and abs(x.mean() - want[k]) < 5 * se, (k, x.mean(), want[k], se)
+
+
+def test_tridiagonal_restatement_matches_dense_linear_algebra():
+    """oracle/mlift_oracle/linalg.py (the scans of mlift/linalg.py:46-114 as loops) against
+    dense NumPy: np.linalg.solve and slogdet of the assembled matrix, including dim 1 and 2
+    and a non-symmetric system (a != c, as in lmult_by_inv_jacob_product, systems.py:1212-1231)."""
+    from mlift_oracle import linalg as ol
+
+    rng = np.random.default_rng(0)
+    for dim in (1, 2, 3, 10, 200):
+        a, c = rng.normal(size=dim - 1), rng.normal(size=dim - 1)
+        b = 2.5 + np.abs(rng.normal(size=dim)) + np.pad(np.abs(a), (1, 0)) + np.pad(np.abs(c), (0, 1))
+        d = rng.normal(size=dim)
+        T = np.diag(b) + np.diag(a, -1) + np.diag(c, 1)
+        x = ol.tridiagonal_solve(a, b, c, d)
+        assert np.abs(x - np.linalg.solve(T, d)).max() < 1e-12 * max(1.0, np.abs(x).max())
+        S = np.diag(b) + np.diag(a, -1) + np.diag(a, 1)
+        sign, ld = np.linalg.slogdet(S)
+        assert sign > 0 and abs(ol.tridiagonal_pos_def_log_det(a, b) - ld) < 1e-10 * max(1.0, abs(ld))
