@@ -116,7 +116,8 @@ typedef struct mlb_solver_opts {
  * host-driven sequence of sub-phase kernels whose sweeps are split over sensitivity
  * directions / pair groups (several warps per batch of 32 chains); the call then blocks
  * the calling thread while it polls per-iteration convergence counts.  This flag selects
- * the fully asynchronous single-kernel path instead (one thread per chain). */
+ * the fully asynchronous single-kernel path instead (one thread per chain).  The same holds
+ * for mlb_hmc_sample on those models; mlb_nuts_sample on them is always host-driven. */
 #define MLB_FLAG_SINGLE_KERNEL 1
 
 /* ---- lifecycle */
@@ -238,7 +239,9 @@ typedef struct mlb_adapt_opts {
  * size.  `trace_q` ([n_iter / trace_every][trace_dim][n], NULL to skip) receives the first
  * `trace_dim` position components (0 = all Q; the latent parameters u come first),
  * `trace_accept` ([n_iter][n], NULL to skip) per-transition accept_stat,
- * `stats` [MLB_STAT_ROWS][n] is accumulated into (not zeroed). */
+ * `stats` [MLB_STAT_ROWS][n] is accumulated into (not zeroed).  For the ODE models the
+ * transitions are driven from the host over the sub-phase kernels (the call blocks the
+ * calling thread) unless opts->flags has MLB_FLAG_SINGLE_KERNEL. */
 int mlb_hmc_sample(const mlb_model* m, int64_t n, int64_t ld, double* q, double dt,
                    int32_t n_step, int32_t n_iter, const mlb_solver_opts* opts,
                    double max_delta_h, uint64_t seed, uint64_t chain0, uint32_t iter0,
