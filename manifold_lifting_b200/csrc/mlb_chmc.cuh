@@ -224,16 +224,21 @@ struct TrajOut {
   double h_init, h_last;
 };
 
+// run_trajectory_ev: the evaluation C is the caller's.  With have_eval it already holds the
+// evaluation at qw (a previous call ended there) and the leading evaluation is skipped;
+// after a successful return it holds the evaluation at the new qw.  The dynamic sampler
+// chains single steps this way without re-evaluating the Jacobian / Gram factor / gradient
+// at every tree leaf.
 template <class M, int SOLVER, bool PROJECT_FIRST, bool CHECK_H, int kStride>
-MLB_DEV TrajOut run_trajectory(const typename M::Params& P, double (&qw)[M::Q],
-                               double (&pw)[M::Q], double* cq, double* cp, int n_step,
-                               double dt, const Opts& o, double max_delta_h) {
+MLB_DEV TrajOut run_trajectory_ev(const typename M::Params& P, double (&qw)[M::Q],
+                                  double (&pw)[M::Q], double* cq, double* cp, int n_step,
+                                  double dt, const Opts& o, double max_delta_h, Eval<M>& C,
+                                  bool have_eval) {
   using B = typename M::B;
   constexpr int Q = M::Q;
   TrajOut t;
   t.status = MLB_ST_OK, t.done = 0, t.it_fwd = 0, t.it_rev = 0;
   t.h_init = t.h_last = nan("");
-  Eval<M> C;
   int sub = PROJECT_FIRST ? -1 : 0;
   bool first = true;
 #pragma unroll
@@ -241,7 +246,7 @@ MLB_DEV TrajOut run_trajectory(const typename M::Params& P, double (&qw)[M::Q],
 #pragma unroll 1
   for (;;) {
     if (first || sub == 1) {  // trajectory start / new position after the forward solve
-      const bool ok = evaluate_at<M>(P, qw, C);
+      const bool ok = (first && have_eval) ? C.G.ok : evaluate_at<M>(P, qw, C);
       if (first && !PROJECT_FIRST) t.h_init = t.h_last = hamiltonian<M>(C, pw);
       first = false;
       if (!ok) {
@@ -314,6 +319,15 @@ MLB_DEV TrajOut run_trajectory(const typename M::Params& P, double (&qw)[M::Q],
     for (int k = 0; k < Q; ++k) qw[k] = cq[k * kStride], pw[k] = cp[k * kStride];
   }
   return t;
+}
+
+template <class M, int SOLVER, bool PROJECT_FIRST, bool CHECK_H, int kStride>
+MLB_DEV TrajOut run_trajectory(const typename M::Params& P, double (&qw)[M::Q],
+                               double (&pw)[M::Q], double* cq, double* cp, int n_step,
+                               double dt, const Opts& o, double max_delta_h) {
+  Eval<M> C;
+  return run_trajectory_ev<M, SOLVER, PROJECT_FIRST, CHECK_H, kStride>(
+      P, qw, pw, cq, cp, n_step, dt, o, max_delta_h, C, false);
 }
 
 }  // namespace mlb

@@ -96,9 +96,13 @@ __global__ void __launch_bounds__(kBlock, MLB_LF_MIN_BLOCKS)
 #pragma unroll
       for (int k = 0; k < Q; ++k) pw[k] = col[k * kBlock];
     }
-    // momentum refresh: project onto the cotangent space, h_init (no step)
-    const TrajOut t0 = run_trajectory<M, SOLVER, true, false, kBlock>(
-        P, qw, pw, &commit[0][threadIdx.x], &commit[Q][threadIdx.x], 0, dti, o, 0.0);
+    // momentum refresh: project onto the cotangent space, h_init (no step); C keeps the
+    // evaluation at the point the next step starts from (see run_trajectory_ev)
+    Eval<M> C;
+    const TrajOut t0 = run_trajectory_ev<M, SOLVER, true, false, kBlock>(
+        P, qw, pw, &commit[0][threadIdx.x], &commit[Q][threadIdx.x], 0, dti, o, 0.0, C, false);
+    bool have_eval = t0.status == MLB_ST_OK;  // both edges of the one-state tree are here
+    int last_dir = 0;
     int st = t0.status;
     const double h0 = t0.h_init;
 #pragma unroll 1
@@ -114,12 +118,15 @@ __global__ void __launch_bounds__(kBlock, MLB_LF_MIN_BLOCKS)
     while (active) {
       if (leaf == 0) {  // new doubling: direction, start from that edge of the tree
         dir = draw() < 0.5 ? 1 : -1;
+        if (last_dir != 0 && dir != last_dir) have_eval = false;  // C sits at the other edge
         const int eq = dir > 0 ? R::EP_Q : R::EN_Q, ep = dir > 0 ? R::EP_P : R::EN_P;
 #pragma unroll 1
         for (int k = 0; k < Q; ++k) qw[k] = SC(eq + k), pw[k] = SC(ep + k);
       }
-      const TrajOut t = run_trajectory<M, SOLVER, false, false, kBlock>(
-          P, qw, pw, &commit[0][threadIdx.x], &commit[Q][threadIdx.x], 1, dir * dti, o, 0.0);
+      const TrajOut t = run_trajectory_ev<M, SOLVER, false, false, kBlock>(
+          P, qw, pw, &commit[0][threadIdx.x], &commit[Q][threadIdx.x], 1, dir * dti, o, 0.0, C,
+          have_eval);
+      have_eval = t.status == MLB_ST_OK, last_dir = dir;
       n_leaf += 1;
       its += t.it_fwd + t.it_rev;
       bool terminate = false;
