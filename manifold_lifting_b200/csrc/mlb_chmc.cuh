@@ -14,6 +14,10 @@
 #pragma once
 #include "mlb_models.cuh"
 
+#ifndef MLB_HI_NORM
+#define MLB_HI_NORM 1  // high-word maximum norm in the fused solver loops (0: exact always)
+#endif
+
 namespace mlb {
 
 struct SolveOut {
@@ -52,16 +56,31 @@ MLB_DEV SolveOut solve_projection(const typename M::Params& P, double (&q)[M::Q]
     double mu[Q];
 #pragma unroll
     for (int k = 0; k < Q; ++k) mu[k] = 0.0;
+    // the fused drivers (WANT_MU = false) only compare the norms with the tolerances:
+    // under the maximum norm they use the high-word norm (mlb_common.cuh) and fall back to
+    // the exact one when a comparison would be ambiguous
+    const bool hi_norm = MLB_HI_NORM && !WANT_MU && o.norm == MLB_NORM_MAX;
+    auto residual_norm = [&](const double (&c)[Y]) {
+      if (!hi_norm) return vec_norm<Y>(c, o.norm);
+      const double t = max_norm_hi<Y>(c);
+      return (norm_hi_ambiguous(t, o.ctol) || norm_hi_ambiguous(t, o.dtol))
+                 ? vec_norm<Y>(c, MLB_NORM_MAX) : t;
+    };
+    auto update_norm = [&](const double (&d)[Q]) {
+      if (!hi_norm) return vec_norm<Q>(d, o.norm);
+      const double t = max_norm_hi<Q>(d);
+      return norm_hi_ambiguous(t, o.ptol) ? vec_norm<Q>(d, MLB_NORM_MAX) : t;
+    };
     while (keep_iterating(r.iters, r.ndq, r.err, o)) {
       double c[Y], delta[Q];
       if (SOLVER == MLB_SOLVER_QUASI_NEWTON) {
         M::constr(P, q, c);
-        r.err = vec_norm<Y>(c, o.norm);
+        r.err = residual_norm(c);
         B::lmult_pinv(Jp, Gp, c, delta);
       } else {
         typename B::Jac Jc;
         M::jacob(P, q, Jc, c);
-        r.err = vec_norm<Y>(c, o.norm);
+        r.err = residual_norm(c);
         double x[Y];
         bool ok = B::lmult_inv_jacob_product(Jc, Jp, c, x);
         if (!ok) {
@@ -76,7 +95,7 @@ MLB_DEV SolveOut solve_projection(const typename M::Params& P, double (&q)[M::Q]
         q[k] -= delta[k];
       }
       r.iters += 1;
-      r.ndq = vec_norm<Q>(delta, o.norm);
+      r.ndq = update_norm(delta);
     }
     if (WANT_MU) {
 #pragma unroll
@@ -306,7 +325,14 @@ MLB_DEV TrajOut run_trajectory_ev(const typename M::Params& P, double (&qw)[M::Q
     } else {
 #pragma unroll
       for (int k = 0; k < Q; ++k) qs[k] -= cq[k * kStride];
-      if (vec_norm<Q>(qs, o.rev_norm) > o.rev_tol) {
+      double rev_err;
+      if (MLB_HI_NORM && o.rev_norm == MLB_NORM_MAX) {
+        rev_err = max_norm_hi<Q>(qs);
+        if (norm_hi_ambiguous(rev_err, o.rev_tol)) rev_err = vec_norm<Q>(qs, MLB_NORM_MAX);
+      } else {
+        rev_err = vec_norm<Q>(qs, o.rev_norm);
+      }
+      if (rev_err > o.rev_tol) {
         t.status = MLB_ST_NON_REVERSIBLE;
         break;
       }

@@ -139,6 +139,25 @@ MLB_DEV double vec_norm(const double (&v)[N], int kind) {
   return sqrt(s);
 }
 
+// Maximum norm truncated to its high word: max over the high 32 bits of |v_i| (two integer
+// instructions per element instead of a 64-bit compare-and-select), returned as the double
+// with that high word and a zero low word.  It compares against a threshold exactly like
+// the true norm unless the two share their high word (`norm_hi_ambiguous`), which callers
+// resolve with the exact norm; NaN / inf stay above every finite threshold.
+template <int N>
+MLB_DEV double max_norm_hi(const double (&v)[N]) {
+  unsigned m = 0u;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const unsigned a = (unsigned)__double2hiint(v[i]) & 0x7fffffffu;
+    m = a > m ? a : m;
+  }
+  return __hiloint2double((int)m, 0);
+}
+MLB_DEV bool norm_hi_ambiguous(double truncated, double threshold) {
+  return __double2hiint(truncated) == __double2hiint(threshold);
+}
+
 // ---- K x K factorizations, fully unrolled, static indexing only (stay in registers)
 
 // in-place lower Cholesky; rdiag <- reciprocal diagonal; false if a pivot is not positive
