@@ -263,3 +263,34 @@ def test_example_script_end_to_end(tmp_path):
     assert set(summ["mean"]) == {"μ", "τ"} and "total_sampling_time" in summ
     assert os.path.exists(tmp_path / "final_chain_states.pkl")
     assert os.path.exists(tmp_path / "trace_0_μ.npy")
+
+
+def test_eight_schools_posterior_is_the_same_under_both_parametrisations():
+    """`unbounded` (mu = u0, tau = exp(u1)) and `normal` (mu = 5 u0,
+    tau = 5 tan(pi Phi(u1) / 2)) are two charts of the same prior (prior.py:17-70,
+    transforms.py:43-55, 87-144): the posterior of (mu, tau) must not depend on the chart.
+    A wrong Jacobian term in either pull-back, or a wrong second derivative in the
+    log-det gradient, shifts these moments."""
+    import manifold_lifting_b200 as mlb
+
+    y, s = EIGHT_SCHOOLS_Y, EIGHT_SCHOOLS_SIGMA
+    res = {}
+    for par in ("unbounded", "normal"):
+        model = mlb.models.EightSchoolsModel(y, s, par)
+        system = mlb.HierarchicalLatentVariableModelSystem(model, model.data, model.dim_u)
+        rng = np.random.default_rng(5)
+        q = model.sample_initial_states(rng, 2048)
+        _, integ = _sampler(mlb, system, 0.1, 0, seed=0)
+        nuts = mlb.samplers.DynamicMultinomialHMC(system, integ, max_tree_depth=8, seed=41)
+        _, traces, stats = nuts.sample_chains(
+            250, 300, q, adapters=[mlb.adapters.DualAveragingStepSizeAdapter(0.8)], trace_dim=2)
+        u = traces["pos"].cpu().numpy()
+        p = model.generate_params(u.reshape(-1, 2))
+        res[par] = (p["μ"].reshape(u.shape[:2]), np.log(p["τ"]).reshape(u.shape[:2]),
+                    float(stats["accept_stat"].mean()))  # fmt: skip
+        assert 0.6 < res[par][2] < 0.95
+    for j, name in enumerate(("mu", "log tau")):
+        for f in (lambda x: x, lambda x: x**2):
+            a, b = f(res["unbounded"][j]), f(res["normal"][j])
+            se = np.hypot(mc_standard_error(a), mc_standard_error(b))
+            assert abs(a.mean() - b.mean()) < 5 * se, (name, a.mean(), b.mean(), se)
