@@ -294,3 +294,36 @@ def test_eight_schools_posterior_is_the_same_under_both_parametrisations():
             a, b = f(res["unbounded"][j]), f(res["normal"][j])
             se = np.hypot(mc_standard_error(a), mc_standard_error(b))
             assert abs(a.mean() - b.mean()) < 5 * se, (name, a.mean(), b.mean(), se)
+
+
+def test_fitzhugh_nagumo_chains_concentrate_on_the_generating_parameters():
+    """The reference's simulated FitzHugh-Nagumo data (200 observations, noise 0.1) were
+    generated at alpha = 3, beta = 1, gamma = 3, delta = 1/3, epsilon = zeta = 1/15,
+    x_init = (-1, 1) (fitzhugh_nagumo.py:146-149 and the data file): chains of the
+    host-driven sampler started around those values must stay there - the posterior is
+    tight - with a healthy accept rate and agreeing chains."""
+    import manifold_lifting_b200 as mlb
+    from _cases import FN_U_TRUE, fn_data, fn_states
+
+    g, y_obs = fn_data()
+    cm = co.OracleModel.fn(y_obs, g["t_seq"], g["dt"], "unbounded")
+    gm = mlb.models.FitzHughNagumoModel(y_obs, g["t_seq"], g["dt"], "unbounded")
+    gs = mlb.IndependentAdditiveNoiseModelSystem(gm, gm.data, gm.dim_u)
+    q = fn_states(cm, 256, spread=0.02)
+    sampler, integ = _sampler(mlb, gs, 0.05, 4, seed=9)
+    _, traces, stats = sampler.sample_chains(
+        25, 40, q, adapters=[mlb.adapters.DualAveragingStepSizeAdapter(0.8)], trace_dim=9)
+    u = traces["pos"].cpu().numpy()  # [256, 40, 9]
+    assert 0.5 < float(stats["accept_stat"].mean()) < 0.99
+    mean, sd = u.mean((0, 1)), u.std((0, 1))
+    print("FN posterior means", np.round(mean, 3), "sds", np.round(sd, 3))
+    # only x0 is observed: alpha, beta and x0(0) are pinned by the data; the unobserved
+    # x1 can be rescaled against gamma, delta, zeta, so of those only the product
+    # gamma * delta (the x0 -> x1 -> x0 feedback gain) is
+    for k in (0, 1, 7):
+        assert abs(mean[k] - FN_U_TRUE[k]) < 0.15, (k, mean[k], FN_U_TRUE[k])
+        assert sd[k] < 0.25
+    gd = u[..., 2] + u[..., 3]
+    assert abs(gd.mean() - (FN_U_TRUE[2] + FN_U_TRUE[3])) < 0.25, gd.mean()
+    # noise scale: log sigma near log 0.1
+    assert abs(mean[6] - FN_U_TRUE[6]) < 0.3
