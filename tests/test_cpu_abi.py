@@ -163,3 +163,18 @@ def test_reference_api_surface():
     assert mlift is me and mlift.solvers is mlb.solvers
     # out-of-scope baselines stay importable by name (transitions.py:9,66,129)
     import mlift.transitions  # noqa: F401
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: include/mlb.h must compile as C99 (no C++ in signatures)."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    header = os.path.join(ROOT, "include", "mlb.h")
+    for std, lang in (("-std=c99", "c"), ("-std=c++17", "c++")):
+        r = subprocess.run([gcc, std, "-fsyntax-only", "-x", lang, header],
+                           capture_output=True, text=True)  # fmt: skip
+        assert r.returncode == 0, r.stderr
