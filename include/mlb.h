@@ -289,6 +289,53 @@ int mlb_tridiagonal_solve(int64_t n, int32_t dim, int32_t n_rhs, int64_t ld, con
 int mlb_tridiagonal_pos_def_log_det(int64_t n, int32_t dim, int64_t ld, const double* a,
                                     const double* b, double* out, void* stream);
 
+/* ---- "tridiagonal + low rank" Gram algebra of the state-space systems (reference
+ * mlift/systems.py:1161-1243, the closures of PartiallyInvertibleStateSpaceModelSystem),
+ * batched over chains, on top of the Thomas recurrence above.  The Jacobian blocks are the
+ * reference's tuple (dc_du, dc_dv, (dc_dn[0], dc_dn[1]), dx_dy) (systems.py:1136-1150), one
+ * component-major device array each with the same leading dimension ld >= n:
+ * dc_du [dim_y * dim_u][ld] (row k * dim_u + a), dc_dv, dc_dn0, dx_dy [dim_y][ld],
+ * dc_dn1 [dim_y - 1][ld].  dx_dy is read by mlb_ssm_log_det_sqrt_gram only (may be NULL
+ * elsewhere).  The decomposition is the reference's (a [dim_y - 1][ld], b [dim_y][ld],
+ * chol_cap_mtx [dim_u * dim_u][ld], row r * dim_u + c, lower triangular, NaN where the
+ * capacitance matrix is not positive definite).  1 <= dim_u <= MLB_SSM_MAX_DIM_U.  */
+#define MLB_SSM_MAX_DIM_U 8
+typedef struct mlb_ssm_blocks {
+  const double* dc_du;
+  const double* dc_dv;
+  const double* dc_dn0;
+  const double* dc_dn1;
+  const double* dx_dy;
+} mlb_ssm_blocks;
+
+/* systems.py:1189-1197 */
+int mlb_ssm_decompose_gram(int64_t n, int32_t dim_y, int32_t dim_u, int64_t ld,
+                           const mlb_ssm_blocks* J, double* a, double* b, double* chol_cap,
+                           void* stream);
+/* systems.py:1199-1210: out [dim_y][ld] = (J J^T)^{-1} vct, vct [dim_y][ld], out != vct */
+int mlb_ssm_lmult_by_inv_gram(int64_t n, int32_t dim_y, int32_t dim_u, int64_t ld,
+                              const mlb_ssm_blocks* J, const double* a, const double* b,
+                              const double* chol_cap, const double* vct, double* out,
+                              void* stream);
+/* systems.py:1212-1232: out = (J_l J_r^T)^{-1} vct (non-symmetric tridiagonal part, pivoted
+ * LU on the capacitance matrix as np.linalg.solve) */
+int mlb_ssm_lmult_by_inv_jacob_product(int64_t n, int32_t dim_y, int32_t dim_u, int64_t ld,
+                                       const mlb_ssm_blocks* J_l, const mlb_ssm_blocks* J_r,
+                                       const double* vct, double* out, void* stream);
+/* systems.py:1234-1243, given the blocks and their decomposition: out [n] =
+ * sum log diag(chol_cap) + tridiagonal_pos_def_log_det(a, b) / 2 - sum log|dx_dy| */
+int mlb_ssm_log_det_sqrt_gram(int64_t n, int32_t dim_y, int32_t dim_u, int64_t ld,
+                              const mlb_ssm_blocks* J, const double* a, const double* b,
+                              const double* chol_cap, double* out, void* stream);
+/* systems.py:1161-1175: out [dim_y][ld] = J vct, vct [dim_u + 2 dim_y][ld] = (u, v, n) parts */
+int mlb_ssm_lmult_by_jacob_constr(int64_t n, int32_t dim_y, int32_t dim_u, int64_t ld,
+                                  const mlb_ssm_blocks* J, const double* vct, double* out,
+                                  void* stream);
+/* systems.py:1177-1187: out [dim_u + 2 dim_y][ld] = J^T vct, vct [dim_y][ld] */
+int mlb_ssm_rmult_by_jacob_constr(int64_t n, int32_t dim_y, int32_t dim_u, int64_t ld,
+                                  const mlb_ssm_blocks* J, const double* vct, double* out,
+                                  void* stream);
+
 /* ---- host-buffer entry point (what a reference-side binding calls; see
  * INTEGRATION.md).  q, p are HOST arrays in the reference's natural layout
  * [n_chain][Q] row-major (one NumPy `state.pos` per row); the call stages them through

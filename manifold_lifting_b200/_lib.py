@@ -35,6 +35,9 @@ EXPORTS = (
     "mlb_aos_to_soa", "mlb_soa_to_aos", "mlb_launch_count", "mlb_measure_fp64_tflops",
     "mlb_selftest_fast_math", "mlb_selftest_exp", "mlb_nuts_sample",
     "mlb_tridiagonal_solve", "mlb_tridiagonal_pos_def_log_det",
+    "mlb_ssm_decompose_gram", "mlb_ssm_lmult_by_inv_gram",
+    "mlb_ssm_lmult_by_inv_jacob_product", "mlb_ssm_log_det_sqrt_gram",
+    "mlb_ssm_lmult_by_jacob_constr", "mlb_ssm_rmult_by_jacob_constr",
 )  # fmt: skip
 
 

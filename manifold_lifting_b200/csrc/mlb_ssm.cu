@@ -1,0 +1,498 @@
+// "Tridiagonal + low rank" Gram algebra of the state-space systems (reference
+// mlift/systems.py:1161-1243, PartiallyInvertibleStateSpaceModelSystem), batched over chains.
+//
+// The constraint Jacobian of a scalar state-space model has blocks
+//   dc_du [Y x U] dense, dc_dv [Y] diagonal, dc_dn = (dc_dn0 [Y] diagonal, dc_dn1 [Y-1] first
+//   sub-diagonal), dx_dy [Y] (enters the log-determinant only),
+// so the Gram matrix is T + dc_du dc_du^T with T symmetric tridiagonal, and every product
+// with its inverse is two Thomas solves around a U x U capacitance system (Woodbury).
+//
+// Execution model: one chain per thread, every array component-major ([rows][ld], element
+// (k, chain i) at p[k * ld + i]), so a warp's access to one row of 32 chains is one
+// coalesced 256-byte transaction.  Everything that is a SUM over observations (capacitance
+// matrix, dc_du^T T^{-1} vct) is accumulated in the forward elimination sweep alone (see
+// k_ssm_decompose); only the final solve needs the backward sweep, whose inputs (1 / b', the
+// multipliers, the eliminated right-hand side) go through a per-call scratch area / the
+// output array in the same layout.  The U x U capacitance matrix, its factor and the
+// U-vectors live in registers.  The sweeps'
+// loads do not depend on computed values, so each thread fetches kP rows ahead into
+// registers and then runs kP dependent steps (one DRAM round trip per kP steps).
+// One IEEE division per observation (1 / b'); the reference's other divisions by b' are
+// multiplications by that reciprocal (results agree with a NumPy restatement of the
+// reference to ~1e-13 relative, tests/test_gpu_state_space.py).
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+
+#include "../../include/mlb.h"
+#include "mlb_launch.cuh"
+
+namespace mlb {
+
+struct SsmBlocks {
+  const double *du, *dv, *n0, *n1, *dxdy;
+};
+
+MLB_DEV int clampi(int k, int lo, int hi) { return k < lo ? lo : (k > hi ? hi : k); }
+
+template <int U>
+struct PrefetchDepth {
+  static constexpr int value = U <= 2 ? 8 : (U <= 4 ? 6 : 4);
+};
+
+// ---- systems.py:1189-1197  decompose_gram:
+// a = dc_dn0[:-1] * dc_dn1, b = dc_dv^2 + dc_dn0^2 + pad(dc_dn1^2, (1, 0)),
+// cap = I + dc_du^T T^{-1} dc_du (T = tridiag(a, b, a); the reference vmaps tridiagonal_solve
+// over the columns of dc_du), chol(cap).
+// The Thomas elimination is T = L D L^T (L unit lower bidiagonal with the multipliers w,
+// D = diag(b')), so dc_du^T T^{-1} dc_du = sum_k d'_k d'_k^T / b'_k with d' = L^{-1} dc_du
+// the forward-eliminated right-hand sides: ONE forward sweep, no backward substitution and
+// no scratch -- the kernel reads the blocks once and writes a, b and the factor, i.e. it
+// moves exactly its algorithmic bytes.
+template <int U>
+__global__ void __launch_bounds__(128)
+    k_ssm_decompose(int64_t n, int Y, int64_t ld, SsmBlocks J, double* a_out, double* b_out,
+                    double* chol_out) {
+  constexpr int P = PrefetchDepth<U>::value;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double rbp = 0.0, a_prev = 0.0, n1_prev = 0.0, dp[U], cap[U][U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    dp[u] = 0.0;
+#pragma unroll
+    for (int v = 0; v < U; ++v) cap[u][v] = u == v ? 1.0 : 0.0;
+  }
+  for (int k0 = 0; k0 < Y; k0 += P) {
+    double du[P][U], dv[P], n0[P], n1[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const int k = clampi(k0 + j, 0, Y - 1);
+#pragma unroll
+      for (int u = 0; u < U; ++u) du[j][u] = J.du[(int64_t)(k * U + u) * ld + i];
+      dv[j] = J.dv[(int64_t)k * ld + i], n0[j] = J.n0[(int64_t)k * ld + i];
+      n1[j] = Y > 1 ? J.n1[(int64_t)clampi(k, 0, Y - 2) * ld + i] : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const int k = k0 + j;
+      if (k < Y) {
+        const double bk = dv[j] * dv[j] + n0[j] * n0[j] + n1_prev * n1_prev;
+        const double ak = n0[j] * n1[j];  // meaningful for k < Y - 1
+        b_out[(int64_t)k * ld + i] = bk;
+        if (k < Y - 1) a_out[(int64_t)k * ld + i] = ak;
+        const double w = a_prev * rbp;  // 0 at k = 0
+        rbp = 1.0 / (bk - w * a_prev);
+#pragma unroll
+        for (int u = 0; u < U; ++u) dp[u] = du[j][u] - w * dp[u];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const double z = dp[u] * rbp;
+#pragma unroll
+          for (int v = 0; v <= u; ++v) cap[u][v] = fma(z, dp[v], cap[u][v]);
+        }
+        a_prev = ak, n1_prev = n1[j];
+      }
+    }
+  }
+  // the factorisation reads the lower triangle only
+  double rdiag[U];
+  const bool ok = chol_lower<U>(cap, rdiag);
+#pragma unroll
+  for (int r = 0; r < U; ++r)
+#pragma unroll
+    for (int c = 0; c < U; ++c)
+      chol_out[(int64_t)(r * U + c) * ld + i] =
+          ok ? cap[r][c] : __longlong_as_double(0x7ff8000000000000LL);
+}
+
+// shared tail of the two inverse products: out = T^{-1} (vct - du s) given the stored
+// elimination (w, 1 / b') and the upper diagonal cu
+template <int U, int P>
+MLB_DEV void thomas_apply_lowrank(int Y, int64_t ld, int64_t i, const double* du_p,
+                                  const double (&s)[U], const double* vct, const double* wv,
+                                  const double* cu, const double* rb, double* out) {
+  double dp = 0.0;
+  for (int k0 = 0; k0 < Y; k0 += P) {
+    double du[P][U], vv[P], ww[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const int k = clampi(k0 + j, 0, Y - 1);
+#pragma unroll
+      for (int u = 0; u < U; ++u) du[j][u] = du_p[(int64_t)(k * U + u) * ld + i];
+      vv[j] = vct[(int64_t)k * ld + i], ww[j] = wv[(int64_t)k * ld + i];
+    }
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const int k = k0 + j;
+      if (k < Y) {
+        double d = vv[j];
+#pragma unroll
+        for (int u = 0; u < U; ++u) d = fma(-du[j][u], s[u], d);
+        dp = d - ww[j] * dp;
+        out[(int64_t)k * ld + i] = dp;
+      }
+    }
+  }
+  double x = 0.0;
+  for (int k0 = Y - 1; k0 >= 0; k0 -= P) {
+    double dd[P], cv[P], rv[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const int k = clampi(k0 - j, 0, Y - 1);
+      dd[j] = out[(int64_t)k * ld + i], rv[j] = rb[(int64_t)k * ld + i];
+      cv[j] = k < Y - 1 ? cu[(int64_t)k * ld + i] : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const int k = k0 - j;
+      if (k >= 0) {
+        x = (dd[j] - cv[j] * x) * rv[j];
+        out[(int64_t)k * ld + i] = x;
+      }
+    }
+  }
+}
+
+// ---- systems.py:1199-1210  lmult_by_inv_gram:
+// T^{-1} (vct - dc_du cho_solve(chol_cap, dc_du^T T^{-1} vct)); with T = L D L^T the inner
+// product is dc_du^T T^{-1} vct = sum_k d'_k v'_k / b'_k (d' = L^{-1} dc_du, v' = L^{-1} vct):
+// one forward sweep, then the solve of the corrected right-hand side.
+// scratch: rb [Y][ld], wv [Y][ld]
+template <int U>
+__global__ void __launch_bounds__(128)
+    k_ssm_inv_gram(int64_t n, int Y, int64_t ld, const double* du_p, const double* a,
+                   const double* b, const double* chol, const double* vct, double* out,
+                   double* rb, double* wv) {
+  constexpr int P = PrefetchDepth<U>::value;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double rbp = 0.0, vp = 0.0, dp[U], s[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) dp[u] = 0.0, s[u] = 0.0;
+  for (int k0 = 0; k0 < Y; k0 += P) {
+    double du[P][U], av[P], bv[P], vv[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const int k = clampi(k0 + j, 0, Y - 1);
+#pragma unroll
+      for (int u = 0; u < U; ++u) du[j][u] = du_p[(int64_t)(k * U + u) * ld + i];
+      av[j] = k > 0 ? a[(int64_t)(k - 1) * ld + i] : 0.0;
+      bv[j] = b[(int64_t)k * ld + i], vv[j] = vct[(int64_t)k * ld + i];
+    }
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const int k = k0 + j;
+      if (k < Y) {
+        const double w = av[j] * rbp;
+        rbp = 1.0 / (bv[j] - w * av[j]);
+        vp = vv[j] - w * vp;
+        rb[(int64_t)k * ld + i] = rbp, wv[(int64_t)k * ld + i] = w;
+        const double z = vp * rbp;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          dp[u] = du[j][u] - w * dp[u];
+          s[u] = fma(dp[u], z, s[u]);
+        }
+      }
+    }
+  }
+  double L[U][U], rdiag[U];
+#pragma unroll
+  for (int r = 0; r < U; ++r) {
+#pragma unroll
+    for (int c = 0; c < U; ++c) L[r][c] = chol[(int64_t)(r * U + c) * ld + i];
+    rdiag[r] = 1.0 / L[r][r];
+  }
+  chol_solve<U>(L, rdiag, s);
+  thomas_apply_lowrank<U, P>(Y, ld, i, du_p, s, vct, wv, a, rb, out);
+}
+
+// ---- systems.py:1212-1232  lmult_by_inv_jacob_product: (J_l J_r^T)^{-1} vct with
+// a = dn1_l * dn0_r[:-1], b = dv_l dv_r + dn0_l dn0_r + pad(dn1_l dn1_r, (1, 0)),
+// c = dn0_l[:-1] * dn1_r, cap = I + du_r^T T^{-1} du_l (np.linalg.solve: pivoted LU),
+// T^{-1} (vct - du_l cap^{-1} du_r^T T^{-1} vct).
+// The elimination is T = L Ub (L unit lower bidiagonal, Ub upper bidiagonal with diagonal b'
+// and super-diagonal c), so du_r^T T^{-1} X = (Ub^{-T} du_r)^T (L^{-1} X): with
+// z_k = (du_r[k] - c_{k-1} z_{k-1}) / b'_k both the capacitance matrix and the inner product
+// with vct are sums over ONE forward sweep.
+// scratch: rb, wv, cu [Y][ld] each
+// 65,536 chains are 512 CTAs: four resident CTAs per SM (<= 128 registers) keep them in ONE
+// wave on 148 SMs; at 160 registers (three per SM) the launch ran 1.15 waves
+template <int U>
+__global__ void __launch_bounds__(128, U <= 3 ? 4 : 1)
+    k_ssm_inv_jacob_product(int64_t n, int Y, int64_t ld, SsmBlocks Jl, SsmBlocks Jr,
+                            const double* vct, double* out, double* rb, double* wv,
+                            double* cu) {
+  constexpr int P = U <= 2 ? 4 : (U <= 4 ? 3 : 2);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double rbp = 0.0, a_prev = 0.0, c_prev = 0.0, n1n1_prev = 0.0, tp = 0.0;
+  double dp[U], z[U], cap[U][U], s[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    dp[u] = 0.0, z[u] = 0.0, s[u] = 0.0;
+#pragma unroll
+    for (int v = 0; v < U; ++v) cap[u][v] = u == v ? 1.0 : 0.0;
+  }
+  for (int k0 = 0; k0 < Y; k0 += P) {
+    double dul[P][U], dur[P][U], dvl[P], dvr[P], n0l[P], n0r[P], n1l[P], n1r[P], vv[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const int k = clampi(k0 + j, 0, Y - 1);
+      const int k1 = clampi(k, 0, Y - 2 > 0 ? Y - 2 : 0);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        dul[j][u] = Jl.du[(int64_t)(k * U + u) * ld + i];
+        dur[j][u] = Jr.du[(int64_t)(k * U + u) * ld + i];
+      }
+      dvl[j] = Jl.dv[(int64_t)k * ld + i], dvr[j] = Jr.dv[(int64_t)k * ld + i];
+      n0l[j] = Jl.n0[(int64_t)k * ld + i], n0r[j] = Jr.n0[(int64_t)k * ld + i];
+      n1l[j] = Y > 1 ? Jl.n1[(int64_t)k1 * ld + i] : 0.0;
+      n1r[j] = Y > 1 ? Jr.n1[(int64_t)k1 * ld + i] : 0.0;
+      vv[j] = vct[(int64_t)k * ld + i];
+    }
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const int k = k0 + j;
+      if (k < Y) {
+        const double bk = dvl[j] * dvr[j] + n0l[j] * n0r[j] + n1n1_prev;
+        // a_k = dn1_l[k] dn0_r[k] (row k + 1, column k), c_k = dn0_l[k] dn1_r[k]
+        const double ak = n1l[j] * n0r[j], ck = n0l[j] * n1r[j];
+        const double w = a_prev * rbp;  // 0 at k = 0
+        rbp = 1.0 / (bk - w * c_prev);
+        rb[(int64_t)k * ld + i] = rbp, wv[(int64_t)k * ld + i] = w;
+        if (k < Y - 1) cu[(int64_t)k * ld + i] = ck;
+        tp = vv[j] - w * tp;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          dp[u] = dul[j][u] - w * dp[u];
+          z[u] = (dur[j][u] - c_prev * z[u]) * rbp;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          s[u] = fma(z[u], tp, s[u]);
+#pragma unroll
+          for (int v = 0; v < U; ++v) cap[u][v] = fma(z[u], dp[v], cap[u][v]);
+        }
+        a_prev = ak, c_prev = ck, n1n1_prev = n1l[j] * n1r[j];
+      }
+    }
+  }
+  const bool ok = lu_solve<U>(cap, s);
+  if (!ok) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) s[u] = __longlong_as_double(0x7ff8000000000000LL);
+  }
+  thomas_apply_lowrank<U, 4>(Y, ld, i, Jl.du, s, vct, wv, cu, rb, out);
+}
+
+MLB_DEV double log1m_exp_ssm(double v) {  // mlift/math.py:7-14
+  return v > 0.69314718055994530942 ? log(-expm1(v)) : log1p(-exp(v));
+}
+
+// ---- systems.py:1234-1243  log_det_sqrt_gram from the blocks and the decomposition:
+// sum log diag(chol_cap) + tridiagonal_pos_def_log_det(a, b) / 2 - sum log|dx_dy|
+__global__ void __launch_bounds__(128)
+    k_ssm_log_det(int64_t n, int Y, int U, int64_t ld, const double* a, const double* b,
+                  const double* chol, const double* dxdy, double* out) {
+  constexpr int P = 8;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double l = log(b[i]), lm = 0.0, sx = log(fabs(dxdy[i]));
+  for (int k0 = 1; k0 < Y; k0 += P) {
+    double lb[P], la[P], lx[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const int k = clampi(k0 + j, 1, Y - 1);
+      lb[j] = log(b[(int64_t)k * ld + i]);
+      la[j] = 2.0 * log(fabs(a[(int64_t)(k - 1) * ld + i]));
+      lx[j] = log(fabs(dxdy[(int64_t)k * ld + i]));
+    }
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      if (k0 + j < Y) {
+        const double v1 = lb[j] + l, v2 = la[j] + lm;
+        lm = l;
+        l = v1 + log1m_exp_ssm(v2 - v1);
+        sx += lx[j];
+      }
+    }
+  }
+  double sc = 0.0;
+  for (int u = 0; u < U; ++u) sc += log(chol[(int64_t)(u * U + u) * ld + i]);
+  out[i] = sc + 0.5 * l - sx;
+}
+
+// ---- systems.py:1161-1175  lmult_by_jacob_constr: J vct, vct = (vct_u, vct_v, vct_n) [Q]
+__global__ void __launch_bounds__(128)
+    k_ssm_lmult_jacob(int64_t n, int Y, int U, int64_t ld, SsmBlocks J, const double* vct,
+                      double* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y;
+  if (i >= n) return;
+  const double* vv = vct + (int64_t)U * ld;
+  const double* vn = vct + (int64_t)(U + Y) * ld;
+  double s = 0.0;
+  for (int u = 0; u < U; ++u) s = fma(J.du[(int64_t)(k * U + u) * ld + i], vct[(int64_t)u * ld + i], s);
+  s += J.dv[(int64_t)k * ld + i] * vv[(int64_t)k * ld + i];
+  s += J.n0[(int64_t)k * ld + i] * vn[(int64_t)k * ld + i];
+  if (k > 0) s += J.n1[(int64_t)(k - 1) * ld + i] * vn[(int64_t)(k - 1) * ld + i];
+  out[(int64_t)k * ld + i] = s;
+}
+
+// ---- systems.py:1177-1187  rmult_by_jacob_constr: J^T vct, vct [Y] -> [Q]
+// one thread per chain walks the observations (the U-sized part is a sum over them, added
+// in observation order: deterministic)
+__global__ void __launch_bounds__(128)
+    k_ssm_rmult_jacob(int64_t n, int Y, int U, int64_t ld, SsmBlocks J, const double* vct,
+                      double* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double* ov = out + (int64_t)U * ld;
+  double* on = out + (int64_t)(U + Y) * ld;
+  double acc[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) acc[u] = 0.0;
+  double w = vct[i];
+#pragma unroll 4
+  for (int k = 0; k < Y; ++k) {
+    const double wn = k < Y - 1 ? vct[(int64_t)(k + 1) * ld + i] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (u < U) acc[u] = fma(w, J.du[(int64_t)(k * U + u) * ld + i], acc[u]);
+    ov[(int64_t)k * ld + i] = w * J.dv[(int64_t)k * ld + i];
+    double t = w * J.n0[(int64_t)k * ld + i];
+    if (k < Y - 1) t += J.n1[(int64_t)k * ld + i] * wn;
+    on[(int64_t)k * ld + i] = t;
+    w = wn;
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u)
+    if (u < U) out[(int64_t)u * ld + i] = acc[u];
+}
+
+static SsmBlocks dev_blocks(const mlb_ssm_blocks* J) {
+  return SsmBlocks{J->dc_du, J->dc_dv, J->dc_dn0, J->dc_dn1, J->dx_dy};
+}
+
+static bool blocks_ok(const mlb_ssm_blocks* J, int Y) {
+  return J && J->dc_du && J->dc_dv && J->dc_dn0 && (Y == 1 || J->dc_dn1);
+}
+
+// scratch rows in units of [ld] doubles
+struct Scratch {
+  double* p = nullptr;
+  cudaStream_t s;
+  int alloc(size_t rows, int64_t ld, cudaStream_t st) {
+    s = st;
+    MLB_CUDA_OK(cudaMallocAsync((void**)&p, sizeof(double) * rows * (size_t)ld, st));
+    return MLB_OK;
+  }
+  ~Scratch() {
+    if (p) cudaFreeAsync(p, s);
+  }
+};
+
+#define MLB_SSM_DISPATCH_U(U_, ...)                                    \
+  switch (U_) {                                                        \
+    case 1: { constexpr int UU = 1; __VA_ARGS__; } break;              \
+    case 2: { constexpr int UU = 2; __VA_ARGS__; } break;              \
+    case 3: { constexpr int UU = 3; __VA_ARGS__; } break;              \
+    case 4: { constexpr int UU = 4; __VA_ARGS__; } break;              \
+    case 5: { constexpr int UU = 5; __VA_ARGS__; } break;              \
+    case 6: { constexpr int UU = 6; __VA_ARGS__; } break;              \
+    case 7: { constexpr int UU = 7; __VA_ARGS__; } break;              \
+    case 8: { constexpr int UU = 8; __VA_ARGS__; } break;              \
+    default: break;                                                    \
+  }
+
+}  // namespace mlb
+
+using namespace mlb;
+
+extern "C" {
+
+int mlb_ssm_decompose_gram(int64_t n, int32_t dim_y, int32_t dim_u, int64_t ld,
+                           const mlb_ssm_blocks* J, double* a, double* b, double* chol_cap,
+                           void* stream) {
+  MLB_ARG(n >= 0 && dim_y >= 1 && dim_u >= 1 && dim_u <= MLB_SSM_MAX_DIM_U && ld >= n);
+  MLB_ARG(blocks_ok(J, dim_y) && b && chol_cap && (dim_y == 1 || a));
+  if (n == 0) return MLB_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned g = (unsigned)((n + 127) / 128);
+  MLB_SSM_DISPATCH_U(dim_u, k_ssm_decompose<UU><<<g, 128, 0, s>>>(n, dim_y, ld, dev_blocks(J), a,
+                                                                 b, chol_cap));
+  return finish_launch();
+}
+
+int mlb_ssm_lmult_by_inv_gram(int64_t n, int32_t dim_y, int32_t dim_u, int64_t ld,
+                              const mlb_ssm_blocks* J, const double* a, const double* b,
+                              const double* chol_cap, const double* vct, double* out,
+                              void* stream) {
+  MLB_ARG(n >= 0 && dim_y >= 1 && dim_u >= 1 && dim_u <= MLB_SSM_MAX_DIM_U && ld >= n);
+  MLB_ARG(J && J->dc_du && b && chol_cap && vct && out && vct != out && (dim_y == 1 || a));
+  if (n == 0) return MLB_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  Scratch sc;
+  if (int rc = sc.alloc((size_t)dim_y * 2, ld, s)) return rc;
+  const unsigned g = (unsigned)((n + 127) / 128);
+  MLB_SSM_DISPATCH_U(dim_u, k_ssm_inv_gram<UU><<<g, 128, 0, s>>>(
+                                n, dim_y, ld, J->dc_du, a, b, chol_cap, vct, out, sc.p,
+                                sc.p + (size_t)dim_y * (size_t)ld));
+  return finish_launch();
+}
+
+int mlb_ssm_lmult_by_inv_jacob_product(int64_t n, int32_t dim_y, int32_t dim_u, int64_t ld,
+                                       const mlb_ssm_blocks* J_l, const mlb_ssm_blocks* J_r,
+                                       const double* vct, double* out, void* stream) {
+  MLB_ARG(n >= 0 && dim_y >= 1 && dim_u >= 1 && dim_u <= MLB_SSM_MAX_DIM_U && ld >= n);
+  MLB_ARG(blocks_ok(J_l, dim_y) && blocks_ok(J_r, dim_y) && vct && out && vct != out);
+  if (n == 0) return MLB_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  Scratch sc;
+  if (int rc = sc.alloc((size_t)dim_y * 3, ld, s)) return rc;
+  const size_t row = (size_t)dim_y * (size_t)ld;
+  const unsigned g = (unsigned)((n + 127) / 128);
+  MLB_SSM_DISPATCH_U(dim_u, k_ssm_inv_jacob_product<UU><<<g, 128, 0, s>>>(
+                                n, dim_y, ld, dev_blocks(J_l), dev_blocks(J_r), vct, out, sc.p,
+                                sc.p + row, sc.p + 2 * row));
+  return finish_launch();
+}
+
+int mlb_ssm_log_det_sqrt_gram(int64_t n, int32_t dim_y, int32_t dim_u, int64_t ld,
+                              const mlb_ssm_blocks* J, const double* a, const double* b,
+                              const double* chol_cap, double* out, void* stream) {
+  MLB_ARG(n >= 0 && dim_y >= 1 && dim_u >= 1 && dim_u <= MLB_SSM_MAX_DIM_U && ld >= n);
+  MLB_ARG(J && J->dx_dy && b && chol_cap && out && (dim_y == 1 || a));
+  if (n == 0) return MLB_OK;
+  k_ssm_log_det<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      n, dim_y, dim_u, ld, a, b, chol_cap, J->dx_dy, out);
+  return finish_launch();
+}
+
+int mlb_ssm_lmult_by_jacob_constr(int64_t n, int32_t dim_y, int32_t dim_u, int64_t ld,
+                                  const mlb_ssm_blocks* J, const double* vct, double* out,
+                                  void* stream) {
+  MLB_ARG(n >= 0 && dim_y >= 1 && dim_y <= 65535 && dim_u >= 1 &&
+          dim_u <= MLB_SSM_MAX_DIM_U && ld >= n);
+  MLB_ARG(blocks_ok(J, dim_y) && vct && out);
+  if (n == 0) return MLB_OK;
+  k_ssm_lmult_jacob<<<dim3((unsigned)((n + 127) / 128), (unsigned)dim_y), 128, 0,
+                      (cudaStream_t)stream>>>(n, dim_y, dim_u, ld, dev_blocks(J), vct, out);
+  return finish_launch();
+}
+
+int mlb_ssm_rmult_by_jacob_constr(int64_t n, int32_t dim_y, int32_t dim_u, int64_t ld,
+                                  const mlb_ssm_blocks* J, const double* vct, double* out,
+                                  void* stream) {
+  MLB_ARG(n >= 0 && dim_y >= 1 && dim_u >= 1 && dim_u <= MLB_SSM_MAX_DIM_U && ld >= n);
+  MLB_ARG(blocks_ok(J, dim_y) && vct && out);
+  if (n == 0) return MLB_OK;
+  k_ssm_rmult_jacob<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      n, dim_y, dim_u, ld, dev_blocks(J), vct, out);
+  return finish_launch();
+}
+
+}  // extern "C"

@@ -256,3 +256,30 @@ def test_tridiagonal_restatement_matches_dense_linear_algebra():
         S = np.diag(b) + np.diag(a, -1) + np.diag(a, 1)
         sign, ld = np.linalg.slogdet(S)
         assert sign > 0 and abs(ol.tridiagonal_pos_def_log_det(a, b) - ld) < 1e-10 * max(1.0, abs(ld))
+
+
+def test_state_space_restatement_matches_dense_linear_algebra():
+    """oracle/mlift_oracle/state_space.py (the closures of
+    PartiallyInvertibleStateSpaceModelSystem, mlift/systems.py:1161-1243) against the dense
+    Jacobian the blocks stand for: products, (J J^T)^{-1}, (J_l J_r^T)^{-1} and
+    log det(J J^T) / 2 - sum log|dx_dy|, including dim_y 1 and 2."""
+    from mlift_oracle import state_space as oss
+
+    rng = np.random.default_rng(1)
+    for dim_y, dim_u in ((1, 1), (2, 2), (7, 3), (60, 5), (300, 3)):
+        J, Jr = oss.random_blocks(rng, dim_y, dim_u), oss.random_blocks(rng, dim_y, dim_u)
+        Jd, Jrd = oss.dense_jacobian(*J), oss.dense_jacobian(*Jr)
+        vq, vy = rng.normal(size=dim_u + 2 * dim_y), rng.normal(size=dim_y)
+        assert np.abs(oss.lmult_by_jacob_constr(*J, vq) - Jd @ vq).max() < 1e-13
+        assert np.abs(oss.rmult_by_jacob_constr(*J, vy) - vy @ Jd).max() < 1e-13
+        a, b, chol = oss.decompose_gram(*J)
+        G = Jd @ Jd.T
+        T = np.diag(b) + (np.diag(a, -1) + np.diag(a, 1) if dim_y > 1 else 0.0)
+        assert np.abs(T + J[0] @ J[0].T - G).max() < 1e-12 * np.abs(G).max()
+        x = oss.lmult_by_inv_gram(*J, a, b, chol, vy)
+        assert np.abs(x - np.linalg.solve(G, vy)).max() < 1e-11 * max(1.0, np.abs(x).max())
+        x = oss.lmult_by_inv_jacob_product(*J, *Jr, vy)
+        ref = np.linalg.solve(Jd @ Jrd.T, vy)
+        assert np.abs(x - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
+        want = 0.5 * np.linalg.slogdet(G)[1] - np.log(np.abs(J[3])).sum()
+        assert abs(oss.log_det_sqrt_gram(*J) - want) < 1e-10 * max(1.0, abs(want))
