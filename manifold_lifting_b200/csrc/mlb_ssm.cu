@@ -288,41 +288,51 @@ __global__ void __launch_bounds__(128, U <= 3 ? 4 : 1)
   thomas_apply_lowrank<U, 4>(Y, ld, i, Jl.du, s, vct, wv, cu, rb, out);
 }
 
-MLB_DEV double log1m_exp_ssm(double v) {  // mlift/math.py:7-14
-  return v > 0.69314718055994530942 ? log(-expm1(v)) : log1p(-exp(v));
-}
-
 // ---- systems.py:1234-1243  log_det_sqrt_gram from the blocks and the decomposition:
-// sum log diag(chol_cap) + tridiagonal_pos_def_log_det(a, b) / 2 - sum log|dx_dy|
+// sum log diag(chol_cap) + tridiagonal_pos_def_log_det(a, b) / 2 - sum log|dx_dy|.
+// The reference's log-continuant recursion (linalg.py:104-114) carries l_k = log theta_k of
+// the leading minors through an exp and a log1p per observation -- a ~200-cycle dependent
+// chain.  Its increments are the Thomas pivots, l_k - l_{k-1} = log b'_k, so here the
+// dependent chain is the pivot recurrence alone (one reciprocal) and the logarithms are
+// taken off it, of products of two pivots; the two forms agree to rounding
+// (mlb_tridiagonal_pos_def_log_det keeps the reference's recursion term by term).
 __global__ void __launch_bounds__(128)
     k_ssm_log_det(int64_t n, int Y, int U, int64_t ld, const double* a, const double* b,
                   const double* chol, const double* dxdy, double* out) {
-  constexpr int P = 8;
+  constexpr int P = 8;  // even: pivots are paired inside one prefetch block
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  double l = log(b[i]), lm = 0.0, sx = log(fabs(dxdy[i]));
-  for (int k0 = 1; k0 < Y; k0 += P) {
-    double lb[P], la[P], lx[P];
+  double rbp = 0.0, st = 0.0, sx = 0.0;
+  for (int k0 = 0; k0 < Y; k0 += P) {
+    double av[P], bv[P], xv[P], piv[P];
 #pragma unroll
     for (int j = 0; j < P; ++j) {
-      const int k = clampi(k0 + j, 1, Y - 1);
-      lb[j] = log(b[(int64_t)k * ld + i]);
-      la[j] = 2.0 * log(fabs(a[(int64_t)(k - 1) * ld + i]));
-      lx[j] = log(fabs(dxdy[(int64_t)k * ld + i]));
+      const int k = clampi(k0 + j, 0, Y - 1);
+      av[j] = k > 0 ? a[(int64_t)(k - 1) * ld + i] : 0.0;
+      bv[j] = b[(int64_t)k * ld + i];
+      xv[j] = dxdy[(int64_t)k * ld + i];
     }
 #pragma unroll
     for (int j = 0; j < P; ++j) {
-      if (k0 + j < Y) {
-        const double v1 = lb[j] + l, v2 = la[j] + lm;
-        lm = l;
-        l = v1 + log1m_exp_ssm(v2 - v1);
-        sx += lx[j];
-      }
+      // rows past the end count as pivot 1 and |dx_dy| 1
+      const bool in = k0 + j < Y;
+      const double w = av[j] * rbp;
+      const double bp = bv[j] - w * av[j];
+      if (in) rbp = 1.0 / bp;
+      piv[j] = in ? bp : 1.0;
+      xv[j] = in ? fabs(xv[j]) : 1.0;
+    }
+#pragma unroll
+    for (int j = 0; j < P; j += 2) {
+      // a non-positive pivot (matrix not positive definite) must give NaN, also in a pair
+      const bool bad = piv[j] <= 0.0 || piv[j + 1] <= 0.0;
+      st += log(bad ? -1.0 : piv[j] * piv[j + 1]);
+      sx += log(xv[j] * xv[j + 1]);
     }
   }
   double sc = 0.0;
   for (int u = 0; u < U; ++u) sc += log(chol[(int64_t)(u * U + u) * ld + i]);
-  out[i] = sc + 0.5 * l - sx;
+  out[i] = sc + 0.5 * st - sx;
 }
 
 // ---- systems.py:1161-1175  lmult_by_jacob_constr: J vct, vct = (vct_u, vct_v, vct_n) [Q]
@@ -344,33 +354,46 @@ __global__ void __launch_bounds__(128)
 
 // ---- systems.py:1177-1187  rmult_by_jacob_constr: J^T vct, vct [Y] -> [Q]
 // one thread per chain walks the observations (the U-sized part is a sum over them, added
-// in observation order: deterministic)
+// in observation order: deterministic), rows prefetched P at a time like the sweeps above
+template <int U>
 __global__ void __launch_bounds__(128)
-    k_ssm_rmult_jacob(int64_t n, int Y, int U, int64_t ld, SsmBlocks J, const double* vct,
+    k_ssm_rmult_jacob(int64_t n, int Y, int64_t ld, SsmBlocks J, const double* vct,
                       double* out) {
+  constexpr int P = PrefetchDepth<U>::value;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double* ov = out + (int64_t)U * ld;
   double* on = out + (int64_t)(U + Y) * ld;
-  double acc[8];
+  double acc[U];
 #pragma unroll
-  for (int u = 0; u < 8; ++u) acc[u] = 0.0;
-  double w = vct[i];
-#pragma unroll 4
-  for (int k = 0; k < Y; ++k) {
-    const double wn = k < Y - 1 ? vct[(int64_t)(k + 1) * ld + i] : 0.0;
+  for (int u = 0; u < U; ++u) acc[u] = 0.0;
+  for (int k0 = 0; k0 < Y; k0 += P) {
+    double du[P][U], dv[P], n0[P], n1[P], w[P + 1];
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
-      if (u < U) acc[u] = fma(w, J.du[(int64_t)(k * U + u) * ld + i], acc[u]);
-    ov[(int64_t)k * ld + i] = w * J.dv[(int64_t)k * ld + i];
-    double t = w * J.n0[(int64_t)k * ld + i];
-    if (k < Y - 1) t += J.n1[(int64_t)k * ld + i] * wn;
-    on[(int64_t)k * ld + i] = t;
-    w = wn;
+    for (int j = 0; j < P; ++j) {
+      const int k = clampi(k0 + j, 0, Y - 1);
+#pragma unroll
+      for (int u = 0; u < U; ++u) du[j][u] = J.du[(int64_t)(k * U + u) * ld + i];
+      dv[j] = J.dv[(int64_t)k * ld + i], n0[j] = J.n0[(int64_t)k * ld + i];
+      n1[j] = k < Y - 1 ? J.n1[(int64_t)k * ld + i] : 0.0;
+      w[j] = vct[(int64_t)k * ld + i];
+    }
+    w[P] = k0 + P < Y ? vct[(int64_t)(k0 + P) * ld + i] : 0.0;
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const int k = k0 + j;
+      if (k < Y) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc[u] = fma(w[j], du[j][u], acc[u]);
+        ov[(int64_t)k * ld + i] = w[j] * dv[j];
+        double t = w[j] * n0[j];
+        if (k < Y - 1) t += n1[j] * w[j + 1];
+        on[(int64_t)k * ld + i] = t;
+      }
+    }
   }
 #pragma unroll
-  for (int u = 0; u < 8; ++u)
-    if (u < U) out[(int64_t)u * ld + i] = acc[u];
+  for (int u = 0; u < U; ++u) out[(int64_t)u * ld + i] = acc[u];
 }
 
 static SsmBlocks dev_blocks(const mlb_ssm_blocks* J) {
@@ -490,8 +513,10 @@ int mlb_ssm_rmult_by_jacob_constr(int64_t n, int32_t dim_y, int32_t dim_u, int64
   MLB_ARG(n >= 0 && dim_y >= 1 && dim_u >= 1 && dim_u <= MLB_SSM_MAX_DIM_U && ld >= n);
   MLB_ARG(blocks_ok(J, dim_y) && vct && out);
   if (n == 0) return MLB_OK;
-  k_ssm_rmult_jacob<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-      n, dim_y, dim_u, ld, dev_blocks(J), vct, out);
+  const unsigned g = (unsigned)((n + 127) / 128);
+  cudaStream_t s = (cudaStream_t)stream;
+  MLB_SSM_DISPATCH_U(dim_u, k_ssm_rmult_jacob<UU><<<g, 128, 0, s>>>(n, dim_y, ld, dev_blocks(J),
+                                                                   vct, out));
   return finish_launch();
 }
 
