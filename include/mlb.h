@@ -336,6 +336,27 @@ int mlb_ssm_rmult_by_jacob_constr(int64_t n, int32_t dim_y, int32_t dim_u, int64
                                   const mlb_ssm_blocks* J, const double* vct, double* out,
                                   void* stream);
 
+/* Stochastic-volatility model (reference mlift/example_models/stochastic_volatility.py:71-141:
+ * constr_split and jacob_constr_split_blocks), `unbounded` prior parametrisation: q
+ * [3 + 2 dim_y][ld] = (u = (mu, log sigma, logit((phi + 1) / 2)), v, n), y_obs [dim_y] device
+ * (shared by all chains) -> c [dim_y][ld] and, if J_out is not NULL, the five block arrays it
+ * points to (WRITTEN; same shapes as above). */
+int mlb_ssm_sv_constr_blocks(int64_t n, int32_t dim_y, int64_t ld, const double* q,
+                             const double* y_obs, double* c, const mlb_ssm_blocks* J_out,
+                             void* stream);
+/* Bookkeeping of one iteration of the projection loops (systems.py:203-227, 243-269) for the
+ * chains with active[i] != 0: error = |c|_max, mu += delta_q, q -= delta_q, n_iters += 1,
+ * norm_delta_q = |delta_q|_max, then active[i] = !(n_iters >= max_iters || error >
+ * divergence_tol || isnan(error) || (error < constraint_tol && norm_delta_q < position_tol));
+ * *n_active (device) is incremented once per chain that stays active.  c [dim_y][ld],
+ * delta_q, q, mu [dim_q][ld]; per-chain arrays [n]. */
+int mlb_ssm_projection_update(int64_t n, int32_t dim_q, int32_t dim_y, int64_t ld,
+                              const double* c, const double* delta_q, double* q, double* mu,
+                              int32_t* n_iters, double* norm_delta_q, double* error,
+                              int32_t* active, double constraint_tol, double position_tol,
+                              double divergence_tol, int32_t max_iters, int32_t* n_active,
+                              void* stream);
+
 /* ---- host-buffer entry point (what a reference-side binding calls; see
  * INTEGRATION.md).  q, p are HOST arrays in the reference's natural layout
  * [n_chain][Q] row-major (one NumPy `state.pos` per row); the call stages them through

@@ -396,6 +396,102 @@ __global__ void __launch_bounds__(128)
   for (int u = 0; u < U; ++u) out[(int64_t)u * ld + i] = acc[u];
 }
 
+// ---- stochastic-volatility model, mlift/example_models/stochastic_volatility.py:71-141
+// (constr_split / jacob_constr_split_blocks), `unbounded` prior parametrisation
+// (prior.py:17-42): mu = u0, sigma = exp(u1), phi = -1 + 2 expit(u2).
+// q rows: u [3], v [Y], n [Y].  x_t = 2 log(y_t / n_t);
+// c_0 = mu + sigma v_0 / sqrt(1 - phi^2) - x_0, c_t = mu + phi (x_{t-1} - mu) + sigma v_t - x_t.
+// One thread per chain walks the observations; y_obs is shared by all chains (broadcast
+// loads).  JAC = false: residual only (the quasi-Newton loop, systems.py:204).
+struct SsmBlocksOut {
+  double *du, *dv, *n0, *n1, *dxdy;
+};
+
+template <bool JAC>
+__global__ void __launch_bounds__(128)
+    k_ssm_sv_blocks(int64_t n, int Y, int64_t ld, const double* q, const double* y_obs,
+                    double* c, SsmBlocksOut J) {
+  constexpr int P = 8;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double mu = q[i], u1 = q[ld + i], u2 = q[2 * ld + i];
+  const double sigma = exp(u1), e = 1.0 / (1.0 + exp(-u2));
+  const double phi = -1.0 + 2.0 * e;
+  const double dmu = 1.0, dsigma = sigma, dphi = 2.0 * e * (1.0 - e);
+  const double omp = 1.0 - phi * phi, somp = sqrt(omp);
+  const double* v = q + 3 * ld;
+  const double* nn = q + (int64_t)(3 + Y) * ld;
+  double x_prev = 0.0, n_prev = 1.0;
+  for (int k0 = 0; k0 < Y; k0 += P) {
+    double vv[P], nv[P], yv[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const int k = clampi(k0 + j, 0, Y - 1);
+      vv[j] = v[(int64_t)k * ld + i], nv[j] = nn[(int64_t)k * ld + i], yv[j] = y_obs[k];
+    }
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const int k = k0 + j;
+      if (k < Y) {
+        const double x = 2.0 * log(yv[j] / nv[j]);
+        const double v0s = vv[j] / somp;  // used at k = 0 only
+        const double xm = x_prev - mu;
+        c[(int64_t)k * ld + i] = k == 0 ? mu + sigma * v0s - x : mu + phi * xm + sigma * vv[j] - x;
+        if (JAC) {
+          J.du[(int64_t)(k * 3 + 0) * ld + i] = k == 0 ? dmu : (1.0 - phi) * dmu;
+          J.du[(int64_t)(k * 3 + 1) * ld + i] = dsigma * (k == 0 ? v0s : vv[j]);
+          J.du[(int64_t)(k * 3 + 2) * ld + i] = k == 0 ? dphi * phi * sigma * v0s / omp : xm * dphi;
+          J.dv[(int64_t)k * ld + i] = k == 0 ? sigma / somp : sigma;
+          J.n0[(int64_t)k * ld + i] = 2.0 / nv[j];
+          if (k > 0) J.n1[(int64_t)(k - 1) * ld + i] = -2.0 * phi / n_prev;
+          J.dxdy[(int64_t)k * ld + i] = 2.0 / yv[j];
+        }
+        x_prev = x, n_prev = nv[j];
+      }
+    }
+  }
+}
+
+// ---- bookkeeping of one iteration of the projection loops (systems.py:203-227 /
+// 243-269) for every chain still iterating: error = |c|, mu += delta, q -= delta, i += 1,
+// |delta|, then the reference's keep-iterating test; chains that stay active are counted
+// in *n_active (the host loop reads that one integer).  Norm: maximum norm (solvers.py:6-8).
+__global__ void __launch_bounds__(128)
+    k_ssm_projection_update(int64_t n, int Q, int Y, int64_t ld, const double* c,
+                            const double* delta, double* q, double* mu, int* iters,
+                            double* norm_dq, double* error, int* active, double c_tol,
+                            double p_tol, double div_tol, int max_iters, int* n_active) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !active[i]) return;
+  // NaN must survive the maximum: fmax would drop it (np.max(abs(x)) propagates it)
+  double err = 0.0, nd = 0.0;
+  bool err_nan = false, nd_nan = false;
+#pragma unroll 4
+  for (int k = 0; k < Y; ++k) {
+    const double a = fabs(c[(int64_t)k * ld + i]);
+    err_nan |= a != a;
+    err = fmax(err, a);
+  }
+#pragma unroll 4
+  for (int k = 0; k < Q; ++k) {
+    const double d = delta[(int64_t)k * ld + i];
+    q[(int64_t)k * ld + i] -= d;
+    mu[(int64_t)k * ld + i] += d;
+    nd_nan |= d != d;
+    nd = fmax(nd, fabs(d));
+  }
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  if (err_nan) err = qnan;
+  if (nd_nan) nd = qnan;
+  const int it = iters[i] + 1;
+  iters[i] = it, norm_dq[i] = nd, error[i] = err;
+  const bool diverged = err > div_tol || err != err;
+  const bool converged = err < c_tol && nd < p_tol;
+  const bool keep = !(it >= max_iters || diverged || converged);
+  active[i] = keep ? 1 : 0;
+  if (keep) atomicAdd(n_active, 1);
+}
+
 static SsmBlocks dev_blocks(const mlb_ssm_blocks* J) {
   return SsmBlocks{J->dc_du, J->dc_dv, J->dc_dn0, J->dc_dn1, J->dx_dy};
 }
@@ -517,6 +613,40 @@ int mlb_ssm_rmult_by_jacob_constr(int64_t n, int32_t dim_y, int32_t dim_u, int64
   cudaStream_t s = (cudaStream_t)stream;
   MLB_SSM_DISPATCH_U(dim_u, k_ssm_rmult_jacob<UU><<<g, 128, 0, s>>>(n, dim_y, ld, dev_blocks(J),
                                                                    vct, out));
+  return finish_launch();
+}
+
+int mlb_ssm_sv_constr_blocks(int64_t n, int32_t dim_y, int64_t ld, const double* q,
+                             const double* y_obs, double* c, const mlb_ssm_blocks* J_out,
+                             void* stream) {
+  MLB_ARG(n >= 0 && dim_y >= 1 && ld >= n && q && y_obs && c);
+  MLB_ARG(!J_out || (blocks_ok(J_out, dim_y) && J_out->dx_dy));
+  if (n == 0) return MLB_OK;
+  const unsigned g = (unsigned)((n + 127) / 128);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (J_out) {
+    SsmBlocksOut o{const_cast<double*>(J_out->dc_du), const_cast<double*>(J_out->dc_dv),
+                   const_cast<double*>(J_out->dc_dn0), const_cast<double*>(J_out->dc_dn1),
+                   const_cast<double*>(J_out->dx_dy)};
+    k_ssm_sv_blocks<true><<<g, 128, 0, s>>>(n, dim_y, ld, q, y_obs, c, o);
+  } else {
+    k_ssm_sv_blocks<false><<<g, 128, 0, s>>>(n, dim_y, ld, q, y_obs, c, SsmBlocksOut{});
+  }
+  return finish_launch();
+}
+
+int mlb_ssm_projection_update(int64_t n, int32_t dim_q, int32_t dim_y, int64_t ld,
+                              const double* c, const double* delta_q, double* q, double* mu,
+                              int32_t* n_iters, double* norm_delta_q, double* error,
+                              int32_t* active, double constraint_tol, double position_tol,
+                              double divergence_tol, int32_t max_iters, int32_t* n_active,
+                              void* stream) {
+  MLB_ARG(n >= 0 && dim_q >= 1 && dim_y >= 1 && ld >= n && c && delta_q && q && mu);
+  MLB_ARG(n_iters && norm_delta_q && error && active && n_active);
+  if (n == 0) return MLB_OK;
+  k_ssm_projection_update<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      n, dim_q, dim_y, ld, c, delta_q, q, mu, n_iters, norm_delta_q, error, active,
+      constraint_tol, position_tol, divergence_tol, max_iters, n_active);
   return finish_launch();
 }
 

@@ -9,8 +9,14 @@ closures; every array carries a leading chain axis:
 
 `JacobBlocks` converts such a tuple once to the component-major device layout; the functions
 take either the raw arrays or a `JacobBlocks` in place of the four block arguments' first.
-The model functions that produce the blocks (`constr_split`, a Python closure in the
-reference) are not part of this module.  There is no CPU fallback.
+The model functions that produce the blocks are Python closures in the reference; one model
+is compiled in, the stochastic-volatility model of
+mlift/example_models/stochastic_volatility.py (`StochasticVolatilityModel`: `constr`,
+`jacob_constr_blocks`), and on it the reference's two projection loops
+(`quasi_newton_projection`, `newton_projection`, systems.py:190-270) run as host loops over
+the kernels, reading one integer (chains still iterating) per iteration.  The Hamiltonian
+side of these systems (gradient of the log-determinant) is not built, so there is no fused
+leapfrog step for them.  There is no CPU fallback.
 """
 import ctypes as C
 
@@ -39,6 +45,19 @@ class JacobBlocks:
         self.dc_dn0 = self._rows(dc_dn[0], self.dim_y)
         self.dc_dn1 = self._rows(dc_dn[1], self.dim_y - 1) if self.dim_y > 1 else None
         self.dx_dy = self._rows(dx_dy, self.dim_y) if dx_dy is not None else None
+
+    @classmethod
+    def empty(cls, n, dim_y, dim_u):
+        """Uninitialised device blocks (filled by a model kernel)."""
+        _lib.require_cuda()
+        self = cls.__new__(cls)
+        self.n, self.dim_y, self.dim_u = n, dim_y, dim_u
+        self.dc_du = _lib.soa_empty(n, dim_y * dim_u)
+        self.dc_dv = _lib.soa_empty(n, dim_y)
+        self.dc_dn0 = _lib.soa_empty(n, dim_y)
+        self.dc_dn1 = _lib.soa_empty(n, dim_y - 1) if dim_y > 1 else None
+        self.dx_dy = _lib.soa_empty(n, dim_y)
+        return self
 
     def _rows(self, x, rows):
         t = _lib.to_soa(torch.as_tensor(x, dtype=torch.float64))
@@ -170,3 +189,100 @@ def log_det_sqrt_gram(dc_du, dc_dv=None, dc_dn=None, dx_dy=None, gram=None):
     check(lib().mlb_ssm_log_det_sqrt_gram(*_dims(J), C.byref(cs), pa, pb, pc,
                                           C.c_void_p(out.data_ptr()), stream_ptr()))  # fmt: skip
     return out
+
+
+class StochasticVolatilityModel:
+    """Constraint side of the reference's stochastic-volatility model
+    (stochastic_volatility.py:71-141), `unbounded` prior parametrisation: q = (u, v, n) with
+    u = (mu, log sigma, logit((phi + 1) / 2)), dim_u = 3, dim_q = 3 + 2 dim_y."""
+
+    dim_u = 3
+
+    def __init__(self, y_obs):
+        _lib.require_cuda()
+        self.y_obs = torch.as_tensor(y_obs, dtype=torch.float64).contiguous().cuda()
+        if self.y_obs.ndim != 1 or self.y_obs.numel() < 1:
+            raise _lib.MlbError("y_obs must be a non-empty vector")
+        self.dim_y = self.y_obs.numel()
+        self.dim_q = 3 + 2 * self.dim_y
+
+    def _q(self, q):
+        t = _lib.to_soa(torch.as_tensor(q, dtype=torch.float64))
+        p, ld = p_soa(t, self.dim_q)
+        return t, p, ld
+
+    def constr(self, q):
+        """c(q) per chain, [n, dim_y] (constr_split(...)[0], stochastic_volatility.py:71-89)."""
+        t, pq, ld = self._q(q)
+        n = t.shape[0]
+        c = _lib.soa_empty(n, self.dim_y)
+        check(lib().mlb_ssm_sv_constr_blocks(C.c_int64(n), C.c_int32(self.dim_y), C.c_int64(ld),
+                                             pq, C.c_void_p(self.y_obs.data_ptr()),
+                                             p_soa(c)[0], None, stream_ptr()))  # fmt: skip
+        return c
+
+    def jacob_constr_blocks(self, q):
+        """(JacobBlocks, c) per chain (jacob_constr_split_blocks, :92-141)."""
+        t, pq, ld = self._q(q)
+        n = t.shape[0]
+        J = JacobBlocks.empty(n, self.dim_y, 3)
+        c = _lib.soa_empty(n, self.dim_y)
+        cs = J.c_struct()
+        check(lib().mlb_ssm_sv_constr_blocks(C.c_int64(n), C.c_int32(self.dim_y), C.c_int64(ld),
+                                             pq, C.c_void_p(self.y_obs.data_ptr()),
+                                             p_soa(c)[0], C.byref(cs), stream_ptr()))  # fmt: skip
+        return J, c
+
+    def _projection(self, q, direction, dt, constraint_tol, position_tol, divergence_tol,
+                    max_iters):  # fmt: skip
+        q = _lib.soa_clone(_lib.to_soa(torch.as_tensor(q, dtype=torch.float64)))
+        pq, ld = p_soa(q, self.dim_q)
+        n = q.shape[0]
+        mu = _lib.soa_zeros(n, self.dim_q)
+        iters = torch.zeros(n, dtype=torch.int32, device="cuda")
+        norm_dq = torch.full((n,), float("inf"), dtype=torch.float64, device="cuda")
+        error = torch.full((n,), -1.0, dtype=torch.float64, device="cuda")
+        active = torch.full((n,), 1 if max_iters > 0 else 0, dtype=torch.int32, device="cuda")
+        n_active = torch.zeros(1, dtype=torch.int32, device="cuda")
+        left = n if max_iters > 0 else 0
+        while left > 0:
+            c, delta = direction(q)
+            n_active.zero_()
+            check(lib().mlb_ssm_projection_update(
+                C.c_int64(n), C.c_int32(self.dim_q), C.c_int32(self.dim_y), C.c_int64(ld),
+                p_soa(c)[0], p_soa(delta)[0], pq, p_soa(mu)[0], C.c_void_p(iters.data_ptr()),
+                C.c_void_p(norm_dq.data_ptr()), C.c_void_p(error.data_ptr()),
+                C.c_void_p(active.data_ptr()), C.c_double(constraint_tol),
+                C.c_double(position_tol), C.c_double(divergence_tol), C.c_int32(max_iters),
+                C.c_void_p(n_active.data_ptr()), stream_ptr()))  # fmt: skip
+            left = int(n_active.item())
+        return q, mu / dt, iters, norm_dq, error
+
+    def quasi_newton_projection(self, q, jacob_constr_blocks_prev, gram_components_prev, dt,
+                                constraint_tol=1e-9, position_tol=1e-8, divergence_tol=1e10,
+                                max_iters=50):  # fmt: skip
+        """systems.py:190-228 for every chain: returns (q, mu / dt, n_iters, norm_delta_q,
+        error); each chain stops by the reference's own test, the call returns when all have."""
+        Jp, (a, b, chol) = jacob_constr_blocks_prev, gram_components_prev
+
+        def direction(q_):
+            c = self.constr(q_)
+            return c, rmult_by_jacob_constr(
+                Jp, None, None, None, lmult_by_inv_gram(Jp, None, None, None, a, b, chol, c))
+
+        return self._projection(q, direction, dt, constraint_tol, position_tol, divergence_tol,
+                                max_iters)  # fmt: skip
+
+    def newton_projection(self, q, jacob_constr_blocks_prev, dt, constraint_tol=1e-9,
+                          position_tol=1e-8, divergence_tol=1e10, max_iters=50):  # fmt: skip
+        """systems.py:230-270 for every chain (Jacobian blocks re-evaluated every iteration)."""
+        Jp = jacob_constr_blocks_prev
+
+        def direction(q_):
+            J, c = self.jacob_constr_blocks(q_)
+            return c, rmult_by_jacob_constr(
+                Jp, None, None, None,
+                lmult_by_inv_jacob_product(J, None, None, None, Jp, None, None, None, c))
+
+        return self._projection(q, direction, dt, constraint_tol, position_tol, divergence_tol,
+                                max_iters)  # fmt: skip

@@ -80,3 +80,133 @@ def random_blocks(rng, dim_y, dim_u):
     dn1 = 0.1 + 0.4 * np.abs(rng.normal(size=max(dim_y - 1, 0)))
     dx_dy = rng.normal(size=dim_y) + np.sign(rng.normal(size=dim_y)) * 0.3
     return dc_du, dc_dv, (dn0, dn1), dx_dy
+
+
+# ---- stochastic-volatility model (mlift/example_models/stochastic_volatility.py), the
+# `unbounded` prior parametrisation (prior.py:17-42): mu = u0 (normal(0, 1), real support: no
+# transform), sigma = exp(u1) (half_normal(1), transforms.py:43-55), phi = -1 + 2 expit(u2)
+# (uniform(-1, 1), transforms.py:72-84)
+
+
+def sv_generate_params(u):
+    e = 1.0 / (1.0 + np.exp(-u[2]))
+    params = {"μ": u[0], "σ": np.exp(u[1]), "ϕ": -1.0 + 2.0 * e}
+    dparams_du = {"μ": 1.0, "σ": np.exp(u[1]), "ϕ": 2.0 * e * (1.0 - e)}
+    return params, dparams_du
+
+
+def sv_constr_split(u, v, n, y):  # stochastic_volatility.py:71-89
+    params, _ = sv_generate_params(u)
+    x = 2 * np.log(y / n)
+    return np.concatenate((
+        (params["μ"] + (params["σ"] / (1 - params["ϕ"] ** 2) ** 0.5) * v[0] - x[0])[None],
+        params["μ"] + params["ϕ"] * (x[:-1] - params["μ"]) + params["σ"] * v[1:] - x[1:],
+    )), x  # fmt: skip
+
+
+def sv_jacob_constr_split_blocks(u, v, n, y):  # stochastic_volatility.py:92-141
+    dim_y = y.shape[0]
+    params, dparams_du = sv_generate_params(u)
+    x = 2 * np.log(y / n)
+    dx_dy = 2 / y
+    one_minus_phi_sq = 1 - params["ϕ"] ** 2
+    sqrt_one_minus_phi_sq = one_minus_phi_sq**0.5
+    v_0_over = v[0] / sqrt_one_minus_phi_sq
+    x_minus_mu = x[:-1] - params["μ"]
+    dc_du = np.stack((
+        np.concatenate((np.array([dparams_du["μ"]]),
+                        (1 - params["ϕ"]) * dparams_du["μ"] * np.ones(dim_y - 1))),
+        np.concatenate((np.array([dparams_du["σ"] * v_0_over]), dparams_du["σ"] * v[1:])),
+        np.concatenate((np.array([dparams_du["ϕ"] * params["ϕ"] * params["σ"] * v_0_over
+                                  / one_minus_phi_sq]), x_minus_mu * dparams_du["ϕ"])),
+    ), 1)  # fmt: skip
+    dc_dv = np.concatenate((np.array([params["σ"] / sqrt_one_minus_phi_sq]),
+                            params["σ"] * np.ones(dim_y - 1)))  # fmt: skip
+    dc_dn = 2 / n, -2 * params["ϕ"] / n[:-1]
+    c = np.concatenate((
+        np.array([params["μ"] + params["σ"] * v_0_over - x[0]]),
+        params["μ"] + params["ϕ"] * x_minus_mu + params["σ"] * v[1:] - x[1:],
+    ))  # fmt: skip
+    return (dc_du, dc_dv, dc_dn, dx_dy), c
+
+
+def sv_split(q, dim_y):
+    return q[:3], q[3 : 3 + dim_y], q[3 + dim_y :]
+
+
+def sv_generate_y(u, v, n):
+    """Forward simulation (stochastic_volatility.py:29-38 through
+    construct_state_space_model_generators): x_0, x_t, y_t = exp(x_t / 2) n_t."""
+    params, _ = sv_generate_params(u)
+    x = np.empty(v.shape[0])
+    x[0] = params["μ"] + (params["σ"] / (1 - params["ϕ"] ** 2) ** 0.5) * v[0]
+    for t in range(1, v.shape[0]):
+        x[t] = params["μ"] + params["ϕ"] * (x[t - 1] - params["μ"]) + params["σ"] * v[t]
+    return np.exp(x / 2) * n
+
+
+def maximum_norm(x):  # solvers.py:6-8
+    return np.max(np.abs(x))
+
+
+def _keep_iterating(i, norm_delta_q, error, c_tol, p_tol, div_tol, max_iters):
+    # systems.py:215-227
+    diverged = error > div_tol or np.isnan(error)
+    converged = error < c_tol and norm_delta_q < p_tol
+    return not (i >= max_iters or diverged or converged)
+
+
+def sv_quasi_newton_projection(q, jac_prev, gram_prev, dt, y, c_tol=1e-9, p_tol=1e-8,
+                               div_tol=1e10, max_iters=50):  # fmt: skip
+    """systems.py:190-228 with the state-space closures; returns (q, mu / dt, i, |dq|, err)."""
+    dim_y = y.shape[0]
+    q, mu, i, norm_delta_q, error = q.copy(), np.zeros_like(q), 0, np.inf, -1.0
+    while _keep_iterating(i, norm_delta_q, error, c_tol, p_tol, div_tol, max_iters):
+        c = sv_constr_split(*sv_split(q, dim_y), y)[0]
+        error = maximum_norm(c)
+        delta_q = rmult_by_jacob_constr(*jac_prev, lmult_by_inv_gram(*jac_prev, *gram_prev, c))
+        mu, q, i = mu + delta_q, q - delta_q, i + 1
+        norm_delta_q = maximum_norm(delta_q)
+    return q, mu / dt, i, norm_delta_q, error
+
+
+def sv_newton_projection(q, jac_prev, dt, y, c_tol=1e-9, p_tol=1e-8, div_tol=1e10,
+                         max_iters=50):  # fmt: skip
+    """systems.py:230-270 with the state-space closures."""
+    dim_y = y.shape[0]
+    q, mu, i, norm_delta_q, error = q.copy(), np.zeros_like(q), 0, np.inf, -1.0
+    while _keep_iterating(i, norm_delta_q, error, c_tol, p_tol, div_tol, max_iters):
+        jac, c = sv_jacob_constr_split_blocks(*sv_split(q, dim_y), y)
+        error = maximum_norm(c)
+        delta_q = rmult_by_jacob_constr(
+            *jac_prev, lmult_by_inv_jacob_product(*jac, *jac_prev, c))
+        mu, q, i = mu + delta_q, q - delta_q, i + 1
+        norm_delta_q = maximum_norm(delta_q)
+    return q, mu / dt, i, norm_delta_q, error
+
+
+def sv_observation_noise(rng, dim_y):
+    """Synthetic observation noise kept away from zero (|n| >= 0.2): the Jacobian has 2 / n on
+    its diagonal, and an observation with n ~ 1e-4 makes the test problem ill-conditioned
+    for every implementation alike."""
+    z = rng.normal(size=dim_y)
+    return np.where(z < 0, -1.0, 1.0) * (0.2 + np.abs(z))
+
+
+def sv_on_manifold_states(rng, n_chain, dim_y, y=None):
+    """Initial states on the manifold: u around typical values, v ~ N(0, I), observations
+    generated once from a reference chain, n = y / exp(x / 2) per chain."""
+    if y is None:
+        u_ref = np.array([-0.5, np.log(0.3), 2.0])
+        y = sv_generate_y(u_ref, rng.normal(size=dim_y), sv_observation_noise(rng, dim_y))
+    qs = np.empty((n_chain, 3 + 2 * dim_y))
+    for i in range(n_chain):
+        u = np.array([-0.5, np.log(0.3), 2.0]) + 0.2 * rng.normal(size=3)
+        v = rng.normal(size=dim_y)
+        params, _ = sv_generate_params(u)
+        x = np.empty(dim_y)
+        x[0] = params["μ"] + (params["σ"] / (1 - params["ϕ"] ** 2) ** 0.5) * v[0]
+        for t in range(1, dim_y):
+            x[t] = params["μ"] + params["ϕ"] * (x[t - 1] - params["μ"]) + params["σ"] * v[t]
+        qs[i] = np.concatenate((u, v, y / np.exp(x / 2)))
+    return qs, y

@@ -283,3 +283,40 @@ def test_state_space_restatement_matches_dense_linear_algebra():
         assert np.abs(x - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
         want = 0.5 * np.linalg.slogdet(G)[1] - np.log(np.abs(J[3])).sum()
         assert abs(oss.log_det_sqrt_gram(*J) - want) < 1e-10 * max(1.0, abs(want))
+
+
+def test_stochastic_volatility_restatement_jacobian_and_projection():
+    """oracle/mlift_oracle/state_space.py, stochastic-volatility part
+    (mlift/example_models/stochastic_volatility.py:71-141): the blocks are the Jacobian of
+    constr_split (central differences), simulated states sit on the manifold, and both
+    projection loops (systems.py:190-270) return to it from a cotangent step."""
+    from mlift_oracle import state_space as oss
+
+    rng = np.random.default_rng(2)
+    dim_y = 25
+    qs, y = oss.sv_on_manifold_states(rng, 3, dim_y)
+    for q in qs:
+        c, _ = oss.sv_constr_split(*oss.sv_split(q, dim_y), y)
+        assert np.abs(c).max() < 1e-12
+        jac, c2 = oss.sv_jacob_constr_split_blocks(*oss.sv_split(q, dim_y), y)
+        assert np.abs(c - c2).max() < 1e-14
+        Jd = oss.dense_jacobian(*jac)
+        fd = np.empty_like(Jd)
+        for j in range(q.size):
+            e = np.zeros_like(q)
+            e[j] = 1e-6 * max(1.0, abs(q[j]))
+            fd[:, j] = (oss.sv_constr_split(*oss.sv_split(q + e, dim_y), y)[0]
+                        - oss.sv_constr_split(*oss.sv_split(q - e, dim_y), y)[0]) / (2 * e[j])  # fmt: skip
+        assert np.abs(Jd - fd).max() < 1e-6 * np.abs(Jd).max()
+        gram = oss.decompose_gram(*jac)
+        p = rng.normal(size=q.size)
+        p -= oss.rmult_by_jacob_constr(
+            *jac, oss.lmult_by_inv_gram(*jac, *gram, oss.lmult_by_jacob_constr(*jac, p)))
+        q1 = q + 0.05 * p
+        qa, _, ia, _, ea = oss.sv_quasi_newton_projection(q1, jac, gram, 0.05, y)
+        qb, _, ib, _, eb = oss.sv_newton_projection(q1, jac, 0.05, y)
+        assert ia < 50 and ib < 50 and ib <= ia and max(ea, eb) < 1e-9
+        for qq in (qa, qb):
+            assert np.abs(oss.sv_constr_split(*oss.sv_split(qq, dim_y), y)[0]).max() < 1e-9
+        # same retraction direction (span of J_prev^T): the two solvers land on the same point
+        assert np.abs(qa - qb).max() < 1e-7

@@ -169,3 +169,146 @@ def test_state_space_full_size_properties_and_bandwidth():
         ms = timed(fn)
         print(f"state_space.{name}: {ms:.3f} ms per call, "
               f"{alg_bytes / (ms * 1e-3) / 1e9:.0f} GB/s algorithmic")
+
+
+def _sv_setup(dim_y, n, seed):
+    rng = np.random.default_rng(seed)
+    qs, y = oss.sv_on_manifold_states(rng, n, dim_y)
+    return rng, qs, y
+
+
+@pytest.mark.parametrize("dim_y", [1, 2, 25, 300])
+def test_stochastic_volatility_constr_and_blocks_match_restatement(dim_y):
+    import manifold_lifting_b200 as mlb
+
+    n = 41
+    rng, qs, y = _sv_setup(dim_y, n, dim_y)
+    qs = qs + 0.01 * rng.normal(size=qs.shape)  # off the manifold: c != 0
+    qs[:, 3 + dim_y :] = np.where(np.abs(qs[:, 3 + dim_y :]) < 0.05, 0.05, qs[:, 3 + dim_y :])
+    qs[:, 3 + dim_y :] = np.abs(qs[:, 3 + dim_y :]) * np.sign(y)[None]  # y / n > 0
+    model = mlb.state_space.StochasticVolatilityModel(y)
+    ref = [oss.sv_jacob_constr_split_blocks(*oss.sv_split(qs[i], dim_y), y) for i in range(n)]
+    c_ref = np.stack([r[1] for r in ref])
+    _close(model.constr(qs), c_ref, 1e-13)
+    J, c = model.jacob_constr_blocks(qs)
+    _close(c, c_ref, 1e-13)
+    _close(J.dc_du.reshape(n, dim_y, 3), np.stack([r[0][0] for r in ref]), 1e-13)
+    _close(J.dc_dv, np.stack([r[0][1] for r in ref]), 1e-13)
+    _close(J.dc_dn0, np.stack([r[0][2][0] for r in ref]), 1e-13)
+    if dim_y > 1:
+        _close(J.dc_dn1, np.stack([r[0][2][1] for r in ref]), 1e-13)
+    _close(J.dx_dy, np.stack([r[0][3] for r in ref]), 1e-13)
+
+
+@pytest.mark.parametrize("dim_y", [2, 40, 500])
+def test_stochastic_volatility_projection_loops_match_restatement(dim_y):
+    """The reference's quasi-Newton and Newton projection loops (systems.py:190-270) on the
+    stochastic-volatility model: per chain the same iteration count, norms and projected
+    position as the NumPy restatement; the projected points are on the manifold."""
+    import manifold_lifting_b200 as mlb
+
+    ss = mlb.state_space
+    n, dt = 24, 0.02
+    rng, qs, y = _sv_setup(dim_y, n, 100 + dim_y)
+    model = ss.StochasticVolatilityModel(y)
+    J, c0 = model.jacob_constr_blocks(qs)
+    assert float(c0.abs().max()) < 1e-12
+    gram = ss.decompose_gram(J)
+    # position step along a cotangent vector, as the integrator's h2_flow does
+    p = rng.normal(size=qs.shape)
+    Jp = ss.lmult_by_jacob_constr(J, None, None, None, p)
+    p = torch.as_tensor(p).cuda() - ss.rmult_by_jacob_constr(
+        J, None, None, None, ss.lmult_by_inv_gram(J, None, None, None, *gram, Jp))
+    assert float(ss.lmult_by_jacob_constr(J, None, None, None, p).abs().max()) < 1e-8
+    q1 = torch.as_tensor(qs).cuda() + dt * p
+    q1_np = q1.cpu().numpy()
+    jac_np = [oss.sv_jacob_constr_split_blocks(*oss.sv_split(qs[i], dim_y), y)[0] for i in range(n)]
+    for solver in ("quasi_newton", "newton"):
+        if solver == "quasi_newton":
+            out = model.quasi_newton_projection(q1, J, gram, dt)
+            ref = [oss.sv_quasi_newton_projection(q1_np[i], jac_np[i], oss.decompose_gram(*jac_np[i]),
+                                                  dt, y) for i in range(n)]  # fmt: skip
+        else:
+            out = model.newton_projection(q1, J, dt)
+            ref = [oss.sv_newton_projection(q1_np[i], jac_np[i], dt, y) for i in range(n)]
+        q_new, mu, iters, norm_dq, err = out
+        it_ref = np.array([r[2] for r in ref])
+        # counts agree except where a norm sits within rounding of its tolerance
+        same = iters.cpu().numpy() == it_ref
+        assert same.mean() >= 0.9, (solver, iters.cpu().numpy(), it_ref)
+        assert it_ref.max() < 50 and int(iters.max()) < 50
+        qr = np.stack([r[0] for r in ref])
+        mr = np.stack([r[1] for r in ref])
+        assert np.abs(q_new.cpu().numpy()[same] - qr[same]).max() < 1e-10 * max(1.0, np.abs(qr).max())
+        assert np.abs(mu.cpu().numpy()[same] - mr[same]).max() < 1e-8 * max(1.0, np.abs(mr).max())
+        assert float(model.constr(q_new).abs().max()) < 1e-9
+        assert float(err.max()) < 1e-9 and float(norm_dq.max()) < 1e-8
+
+
+def test_stochastic_volatility_projection_flags_failures_per_chain():
+    """A chain that cannot converge (max_iters too small / NaN position) stops by the
+    reference's test without holding up or contaminating the others."""
+    import manifold_lifting_b200 as mlb
+
+    ss = mlb.state_space
+    dim_y, n, dt = 30, 8, 0.05
+    rng, qs, y = _sv_setup(dim_y, n, 5)
+    model = ss.StochasticVolatilityModel(y)
+    J, _ = model.jacob_constr_blocks(qs)
+    gram = ss.decompose_gram(J)
+    q1 = qs + 1e-3 * rng.normal(size=qs.shape)
+    q1[3, 5] = np.nan
+    _, _, iters, norm_dq, err = model.quasi_newton_projection(q1, J, gram, dt, max_iters=50)
+    assert int(iters[3]) == 1 and bool(torch.isnan(err[3]))
+    ok = np.arange(n) != 3
+    assert float(err.cpu().numpy()[ok].max()) < 1e-9
+    _, _, iters2, _, _ = model.quasi_newton_projection(q1, J, gram, dt, max_iters=2)
+    assert int(iters2.max()) <= 2 and int(iters2[0]) == 2
+
+
+def test_stochastic_volatility_projection_full_size():
+    """16,384 chains x dim_y 1,000: every chain lands on the manifold; time per iteration."""
+    import manifold_lifting_b200 as mlb
+    from manifold_lifting_b200 import _lib
+
+    ss = mlb.state_space
+    n, dim_y, dt = 16384, 1000, 0.02
+    rng = np.random.default_rng(11)
+    u_ref = np.array([-0.5, np.log(0.3), 2.0])
+    y = oss.sv_generate_y(u_ref, rng.normal(size=dim_y), oss.sv_observation_noise(rng, dim_y))
+    model = ss.StochasticVolatilityModel(y)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    q = _lib.soa_empty(n, model.dim_q).normal_(generator=g)
+    q[:, 0] = -0.5 + 0.2 * q[:, 0]
+    q[:, 1] = float(np.log(0.3)) + 0.2 * q[:, 1]
+    q[:, 2] = 2.0 + 0.2 * q[:, 2]
+    # lift onto the manifold: simulate x from (u, v), then n = y / exp(x / 2)
+    sigma, phi = q[:, 1].exp(), -1.0 + 2.0 * torch.sigmoid(q[:, 2])
+    x = q[:, 0] + sigma / (1 - phi**2).sqrt() * q[:, 3]
+    yt = torch.as_tensor(y).cuda()
+    for t in range(dim_y):
+        if t > 0:
+            x = q[:, 0] + phi * (x - q[:, 0]) + sigma * q[:, 3 + t]
+        q[:, 3 + dim_y + t] = yt[t] / (x / 2).exp()
+    J, c0 = model.jacob_constr_blocks(q)
+    assert float(c0.abs().max()) < 1e-10
+    gram = ss.decompose_gram(J)
+    p = _lib.soa_empty(n, model.dim_q).normal_(generator=g)
+    p = p - ss.rmult_by_jacob_constr(J, None, None, None, ss.lmult_by_inv_gram(
+        J, None, None, None, *gram, ss.lmult_by_jacob_constr(J, None, None, None, p)))
+    q1 = q + dt * p
+    for name, run in (("quasi_newton", lambda: model.quasi_newton_projection(q1, J, gram, dt)),
+                      ("newton", lambda: model.newton_projection(q1, J, dt))):
+        run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        q_new, mu, iters, norm_dq, err = run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        assert float(model.constr(q_new).abs().max()) < 1e-9
+        assert float(err.max()) < 1e-9 and float(norm_dq.max()) < 1e-8
+        print(f"sv {name}_projection: {n} chains x dim_y {dim_y}: {ms:.2f} ms, "
+              f"{int(iters.max())} rounds (mean {float(iters.double().mean()):.2f} iterations per chain), "
+              f"{n / (ms * 1e-3):.3g} projections/s")
