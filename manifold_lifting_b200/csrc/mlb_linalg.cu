@@ -23,6 +23,25 @@ namespace mlb {
 // per kPre steps instead of once per step.
 constexpr int kPre = 16;
 
+// Keep freed scratch cached in the device's default memory pool: with the default release
+// threshold (0) the pool returns its memory to the driver at the next synchronisation, and
+// a host loop that synchronises once per round (the projection loops of mlb_ssm.cu) pays
+// for a fresh physical allocation of several hundred MB every round.  Also used by
+// mlb_ssm.cu.
+void keep_default_pool_cached() {
+  static const bool done = [] {
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t thr = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    return true;
+  }();
+  (void)done;
+}
+
 // forward elimination of mlift/linalg.py:67-75: w_i = a_{i-1} / b'_{i-1},
 // b'_i = b_i - w_i c_{i-1};  fac rows: [0, dim) b', [dim, 2 dim - 1) w
 __global__ void __launch_bounds__(128)
@@ -206,6 +225,7 @@ int mlb_tridiagonal_solve(int64_t n, int32_t dim, int32_t n_rhs, int64_t ld, con
   const int64_t ldf = (n + 31) / 32 * 32;
   double* fac = nullptr;
   const unsigned g = (unsigned)((n + 127) / 128);
+  keep_default_pool_cached();
   if (n_rhs == 1) {
     MLB_CUDA_OK(cudaMallocAsync((void**)&fac, sizeof(double) * (size_t)dim * (size_t)ldf, s));
     k_tridiag_solve_one<<<g, 128, 0, s>>>(n, dim, ld, a, b, c, d, x, fac, ldf);
