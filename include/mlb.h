@@ -336,6 +336,12 @@ int mlb_ssm_rmult_by_jacob_constr(int64_t n, int32_t dim_y, int32_t dim_u, int64
                                   const mlb_ssm_blocks* J, const double* vct, double* out,
                                   void* stream);
 
+/* systems.py:181-188 and :464-466: mom [dim_u + 2 dim_y][ld] -= J^T (J J^T)^{-1} J mom, in
+ * place (normal-space component removed: the momentum re-projection of the leapfrog step) */
+int mlb_ssm_project_onto_cotangent_space(int64_t n, int32_t dim_y, int32_t dim_u, int64_t ld,
+                                         const mlb_ssm_blocks* J, const double* a,
+                                         const double* b, const double* chol_cap, double* mom,
+                                         void* stream);
 /* Stochastic-volatility model (reference mlift/example_models/stochastic_volatility.py:71-141:
  * constr_split and jacob_constr_split_blocks), `unbounded` prior parametrisation: q
  * [3 + 2 dim_y][ld] = (u = (mu, log sigma, logit((phi + 1) / 2)), v, n), y_obs [dim_y] device

@@ -357,10 +357,12 @@ __global__ void __launch_bounds__(128)
 // ---- systems.py:1177-1187  rmult_by_jacob_constr: J^T vct, vct [Y] -> [Q]
 // one thread per chain walks the observations (the U-sized part is a sum over them, added
 // in observation order: deterministic), rows prefetched P at a time like the sweeps above
-template <int U>
+// SUB: out = base - J^T vct (the cotangent projection p - J^T G^{-1} J p, systems.py:464-466;
+// base may alias out)
+template <int U, bool SUB>
 __global__ void __launch_bounds__(128)
     k_ssm_rmult_jacob(int64_t n, int Y, int64_t ld, SsmBlocks J, const double* vct,
-                      double* out) {
+                      const double* base, double* out) {
   constexpr int P = PrefetchDepth<U>::value;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -387,15 +389,21 @@ __global__ void __launch_bounds__(128)
       if (k < Y) {
 #pragma unroll
         for (int u = 0; u < U; ++u) acc[u] = fma(w[j], du[j][u], acc[u]);
-        ov[(int64_t)k * ld + i] = w[j] * dv[j];
+        double tv = w[j] * dv[j];
         double t = w[j] * n0[j];
         if (k < Y - 1) t += n1[j] * w[j + 1];
+        if (SUB) {
+          tv = base[(int64_t)(U + k) * ld + i] - tv;
+          t = base[(int64_t)(U + Y + k) * ld + i] - t;
+        }
+        ov[(int64_t)k * ld + i] = tv;
         on[(int64_t)k * ld + i] = t;
       }
     }
   }
 #pragma unroll
-  for (int u = 0; u < U; ++u) out[(int64_t)u * ld + i] = acc[u];
+  for (int u = 0; u < U; ++u)
+    out[(int64_t)u * ld + i] = SUB ? base[(int64_t)u * ld + i] - acc[u] : acc[u];
 }
 
 // ---- stochastic-volatility model, mlift/example_models/stochastic_volatility.py:71-141
@@ -630,8 +638,8 @@ int mlb_ssm_rmult_by_jacob_constr(int64_t n, int32_t dim_y, int32_t dim_u, int64
   if (n == 0) return MLB_OK;
   const unsigned g = (unsigned)((n + 127) / 128);
   cudaStream_t s = (cudaStream_t)stream;
-  MLB_SSM_DISPATCH_U(dim_u, k_ssm_rmult_jacob<UU><<<g, 128, 0, s>>>(n, dim_y, ld, dev_blocks(J),
-                                                                   vct, out));
+  MLB_SSM_DISPATCH_U(dim_u, k_ssm_rmult_jacob<UU, false><<<g, 128, 0, s>>>(
+                                n, dim_y, ld, dev_blocks(J), vct, nullptr, out));
   return finish_launch();
 }
 
@@ -680,6 +688,34 @@ int mlb_ssm_projection_update(int64_t n, int32_t dim_q, int32_t dim_y, int64_t l
   }
   cudaFreeAsync(mx, s);
   return rc;
+}
+
+// systems.py:181-188 (normal_space_component) and :464-466 (project_onto_cotangent_space):
+// mom -= J^T (J J^T)^{-1} J mom, as three launches: J mom, the Gram solve, and J^T(.)
+// subtracted from mom in the same pass
+int mlb_ssm_project_onto_cotangent_space(int64_t n, int32_t dim_y, int32_t dim_u, int64_t ld,
+                                         const mlb_ssm_blocks* J, const double* a,
+                                         const double* b, const double* chol_cap, double* mom,
+                                         void* stream) {
+  MLB_ARG(n >= 0 && dim_y >= 1 && dim_y <= 65535 && dim_u >= 1 &&
+          dim_u <= MLB_SSM_MAX_DIM_U && ld >= n);
+  MLB_ARG(blocks_ok(J, dim_y) && b && chol_cap && mom && (dim_y == 1 || a));
+  if (n == 0) return MLB_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  Scratch sc;  // J mom [Y], G^{-1} J mom [Y], sweep scratch [2 Y]
+  if (int rc = sc.alloc((size_t)dim_y * 4, ld, s)) return rc;
+  const size_t row = (size_t)dim_y * (size_t)ld;
+  double *jp = sc.p, *gjp = sc.p + row, *sw = sc.p + 2 * row;
+  const unsigned g = (unsigned)((n + 127) / 128);
+  k_ssm_lmult_jacob<<<dim3(g, (unsigned)dim_y), 128, 0, s>>>(n, dim_y, dim_u, ld, dev_blocks(J),
+                                                            mom, jp);
+  if (int rc = finish_launch()) return rc;
+  MLB_SSM_DISPATCH_U(dim_u, k_ssm_inv_gram<UU><<<g, 128, 0, s>>>(n, dim_y, ld, J->dc_du, a, b,
+                                                                chol_cap, jp, gjp, sw, sw + row));
+  if (int rc = finish_launch()) return rc;
+  MLB_SSM_DISPATCH_U(dim_u, k_ssm_rmult_jacob<UU, true><<<g, 128, 0, s>>>(
+                                n, dim_y, ld, dev_blocks(J), gjp, mom, mom));
+  return finish_launch();
 }
 
 }  // extern "C"

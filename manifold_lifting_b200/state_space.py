@@ -175,6 +175,23 @@ def lmult_by_inv_jacob_product(dc_du_l, dc_dv_l, dc_dn_l, dx_dy_l, dc_du_r, dc_d
     return out
 
 
+def project_onto_cotangent_space(mom, jacob_constr_blocks, gram_components):
+    """mom - J^T (J J^T)^{-1} J mom per chain (systems.py:181-188, 464-466), as a new array."""
+    J = _blocks(jacob_constr_blocks)
+    a, b, chol = gram_components
+    _keep, pa, pb, pc = _gram_ptrs(J, a, b, chol)
+    out = _lib.soa_clone(_lib.to_soa(torch.as_tensor(mom, dtype=torch.float64)))
+    if tuple(out.shape) != (J.n, J.dim_u + 2 * J.dim_y):
+        raise _lib.MlbError(f"expected a [{J.n}, {J.dim_u + 2 * J.dim_y}] momentum array")
+    pm, ld = p_soa(out, J.dim_u + 2 * J.dim_y)
+    if ld != J.ld:
+        raise _lib.MlbError("arrays must share the blocks' leading dimension")
+    cs = J.c_struct()
+    check(lib().mlb_ssm_project_onto_cotangent_space(*_dims(J), C.byref(cs), pa, pb, pc, pm,
+                                                     stream_ptr()))  # fmt: skip
+    return out
+
+
 def log_det_sqrt_gram(dc_du, dc_dv=None, dc_dn=None, dx_dy=None, gram=None):
     """sum log diag(chol_cap) + tridiagonal_pos_def_log_det(a, b) / 2 - sum log|dx_dy| per
     chain, from the blocks (the reference's closure evaluates them from q first,

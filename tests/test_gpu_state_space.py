@@ -312,3 +312,25 @@ def test_stochastic_volatility_projection_full_size():
         print(f"sv {name}_projection: {n} chains x dim_y {dim_y}: {ms:.2f} ms, "
               f"{int(iters.max())} rounds (mean {float(iters.double().mean()):.2f} iterations per chain), "
               f"{n / (ms * 1e-3):.3g} projections/s")
+
+
+@pytest.mark.parametrize("dim_y,dim_u", [(1, 1), (9, 3), (200, 8)])
+def test_state_space_cotangent_projection(dim_y, dim_u):
+    """p - J^T G^{-1} J p: against the restated closures, J p' = 0 afterwards, idempotent."""
+    import manifold_lifting_b200 as mlb
+
+    ss = mlb.state_space
+    rng = np.random.default_rng(50 + dim_y)
+    n = 37
+    chains, arrs = _batch(rng, n, dim_y, dim_u)
+    J = ss.JacobBlocks(*arrs)
+    gram = ss.decompose_gram(J)
+    p = rng.normal(size=(n, dim_u + 2 * dim_y))
+    out = ss.project_onto_cotangent_space(p, J, gram)
+    ref = np.stack([
+        p[i] - oss.rmult_by_jacob_constr(*chains[i], oss.lmult_by_inv_gram(
+            *chains[i], *oss.decompose_gram(*chains[i]),
+            oss.lmult_by_jacob_constr(*chains[i], p[i]))) for i in range(n)])  # fmt: skip
+    _close(out, ref, 1e-12)
+    assert float(ss.lmult_by_jacob_constr(J, None, None, None, out).abs().max()) < 1e-11
+    _close(ss.project_onto_cotangent_space(out, J, gram), out.cpu().numpy(), 1e-12)
