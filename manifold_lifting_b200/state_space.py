@@ -303,3 +303,48 @@ class StochasticVolatilityModel:
 
         return self._projection(q, direction, dt, constraint_tol, position_tol, divergence_tol,
                                 max_iters)  # fmt: skip
+
+    def constrained_position_step(self, q, p, dt, solver="newton", reverse_check_tol=2e-8,
+                                  constraint_tol=1e-9, position_tol=1e-8, divergence_tol=1e10,
+                                  max_iters=50):  # fmt: skip
+        """The position half (`B`) of Mici's constrained leapfrog step for every chain
+        (the part of the step that needs no Hamiltonian gradient):
+        q + dt p -> projection onto the manifold with the Jacobian at q (the solver wrappers'
+        contract, solvers.py:56-95: pos = q', mom -= mu / dt) -> blocks and Gram at the new
+        point -> cotangent projection of the momentum -> reversibility check (position step
+        back with the new momentum, projection with the new Jacobian, maximum norm of the
+        distance to the start against reverse_check_tol).  Returns a dict: pos, mom, status
+        ([n] int32: ST_OK / ST_DIVERGED / ST_NOT_CONVERGED / ST_NON_REVERSIBLE as in
+        include/mlb.h), iters_fwd, iters_rev, jacob_constr_blocks, gram_components at pos."""
+        q0 = _lib.to_soa(torch.as_tensor(q, dtype=torch.float64))
+        p0 = _lib.to_soa(torch.as_tensor(p, dtype=torch.float64))
+        tols = dict(constraint_tol=constraint_tol, position_tol=position_tol,
+                    divergence_tol=divergence_tol, max_iters=max_iters)  # fmt: skip
+
+        def project(q_, J_, gram_, dt_):
+            if solver == "newton":
+                return self.newton_projection(q_, J_, dt_, **tols)
+            if solver == "quasi_newton":
+                return self.quasi_newton_projection(q_, J_, gram_, dt_, **tols)
+            raise _lib.MlbError(f"unknown solver {solver!r}")
+
+        def classify(err, nd):
+            st = torch.full_like(err, _lib.ST_OK, dtype=torch.int32)
+            st[~((err < constraint_tol) & (nd < position_tol))] = _lib.ST_NOT_CONVERGED
+            st[(err > divergence_tol) | torch.isnan(err)] = _lib.ST_DIVERGED
+            return st
+
+        J0, _ = self.jacob_constr_blocks(q0)
+        gram0 = decompose_gram(J0) if solver == "quasi_newton" else None
+        q1, mu, it_f, nd_f, err_f = project(q0 + dt * p0, J0, gram0, dt)
+        status = classify(err_f, nd_f)
+        J1, _ = self.jacob_constr_blocks(q1)
+        gram1 = decompose_gram(J1)
+        p1 = project_onto_cotangent_space(p0 - mu, J1, gram1)
+        qb, _, it_r, nd_r, err_r = project(q1 - dt * p1, J1, gram1, -dt)
+        st_r = classify(err_r, nd_r)
+        rev = (qb - q0).abs().amax(1)
+        st_r[(st_r == _lib.ST_OK) & ~(rev <= reverse_check_tol)] = _lib.ST_NON_REVERSIBLE
+        status = torch.where(status != _lib.ST_OK, status, st_r)
+        return dict(pos=q1, mom=p1, status=status, iters_fwd=it_f, iters_rev=it_r,
+                    jacob_constr_blocks=J1, gram_components=gram1, reverse_error=rev)  # fmt: skip

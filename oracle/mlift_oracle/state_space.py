@@ -37,7 +37,7 @@ def decompose_gram(dc_du, dc_dv, dc_dn, dx_dy):  # systems.py:1189-1197
 def lmult_by_inv_gram(dc_du, dc_dv, dc_dn, dx_dy, a, b, chol_cap_mtx, vct):  # :1199-1210
     return tridiagonal_solve(
         a, b, a,
-        vct - dc_du @ sla.cho_solve((chol_cap_mtx, True), dc_du.T @ tridiagonal_solve(a, b, a, vct)),
+        vct - dc_du @ sla.cho_solve((chol_cap_mtx, True), dc_du.T @ tridiagonal_solve(a, b, a, vct), check_finite=False),
     )  # fmt: skip
 
 
@@ -210,3 +210,40 @@ def sv_on_manifold_states(rng, n_chain, dim_y, y=None):
             x[t] = params["μ"] + params["ϕ"] * (x[t - 1] - params["μ"]) + params["σ"] * v[t]
         qs[i] = np.concatenate((u, v, y / np.exp(x / 2)))
     return qs, y
+
+
+def sv_constrained_position_step(q, p, dt, y, solver="newton", reverse_check_tol=2e-8,
+                                 c_tol=1e-9, p_tol=1e-8, div_tol=1e10, max_iters=50):
+    """Position half of Mici 0.2.1's ConstrainedLeapfrogIntegrator step (restated, SURVEY
+    Appendix A) with the mlift solver wrappers' contract (solvers.py:56-95) on the
+    stochastic-volatility system.  Returns (pos, mom, status, iters_fwd, iters_rev) with
+    status 0 ok / 1 diverged / 2 not converged / 3 non-reversible; on a forward failure the
+    remaining fields are those computed so far."""
+    dim_y = y.shape[0]
+
+    def project(q_, jac_, dt_):
+        if solver == "newton":
+            return sv_newton_projection(q_, jac_, dt_, y, c_tol, p_tol, div_tol, max_iters)
+        return sv_quasi_newton_projection(q_, jac_, decompose_gram(*jac_), dt_, y, c_tol, p_tol,
+                                          div_tol, max_iters)  # fmt: skip
+
+    def classify(err, nd):
+        if err > div_tol or np.isnan(err):
+            return 1
+        return 0 if (err < c_tol and nd < p_tol) else 2
+
+    jac0, _ = sv_jacob_constr_split_blocks(*sv_split(q, dim_y), y)
+    q1, mu, it_f, nd, err = project(q + dt * p, jac0, dt)
+    status = classify(err, nd)
+    if status:
+        return q1, p - mu, status, it_f, 0
+    jac1, _ = sv_jacob_constr_split_blocks(*sv_split(q1, dim_y), y)
+    gram1 = decompose_gram(*jac1)
+    p1 = p - mu
+    p1 = p1 - rmult_by_jacob_constr(
+        *jac1, lmult_by_inv_gram(*jac1, *gram1, lmult_by_jacob_constr(*jac1, p1)))
+    qb, _, it_r, nd, err = project(q1 - dt * p1, jac1, -dt)
+    status = classify(err, nd)
+    if status == 0 and not maximum_norm(qb - q) <= reverse_check_tol:
+        status = 3
+    return q1, p1, status, it_f, it_r
