@@ -411,19 +411,24 @@ __global__ void __launch_bounds__(128)
 // (prior.py:17-42): mu = u0, sigma = exp(u1), phi = -1 + 2 expit(u2).
 // q rows: u [3], v [Y], n [Y].  x_t = 2 log(y_t / n_t);
 // c_0 = mu + sigma v_0 / sqrt(1 - phi^2) - x_0, c_t = mu + phi (x_{t-1} - mu) + sigma v_t - x_t.
-// One thread per chain walks the observations; y_obs is shared by all chains (broadcast
-// loads).  JAC = false: residual only (the quasi-Newton loop, systems.py:204).
+// y_obs is shared by all chains (broadcast loads).  JAC = false: residual only (the
+// quasi-Newton loop, systems.py:204).
 struct SsmBlocksOut {
   double *du, *dv, *n0, *n1, *dxdy;
 };
+
+// Every row depends on the inputs only (x_{t-1} = 2 log(y_{t-1} / n_{t-1}) is recomputed, not
+// carried), so the grid is (chains, chunks of kSvRows observations): at 16,384 chains one
+// thread per chain walking all rows took 0.34 ms (residual) / 0.54 ms (blocks) per call.
+constexpr int kSvRows = 32;
 
 template <bool JAC>
 __global__ void __launch_bounds__(128)
     k_ssm_sv_blocks(int64_t n, int Y, int64_t ld, const double* q, const double* y_obs,
                     double* c, SsmBlocksOut J) {
-  constexpr int P = 8;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const int r0 = blockIdx.y * kSvRows;
   const double mu = q[i], u1 = q[ld + i], u2 = q[2 * ld + i];
   const double sigma = exp(u1), e = 1.0 / (1.0 + exp(-u2));
   const double phi = -1.0 + 2.0 * e;
@@ -432,33 +437,27 @@ __global__ void __launch_bounds__(128)
   const double* v = q + 3 * ld;
   const double* nn = q + (int64_t)(3 + Y) * ld;
   double x_prev = 0.0, n_prev = 1.0;
-  for (int k0 = 0; k0 < Y; k0 += P) {
-    double vv[P], nv[P], yv[P];
-#pragma unroll
-    for (int j = 0; j < P; ++j) {
-      const int k = clampi(k0 + j, 0, Y - 1);
-      vv[j] = v[(int64_t)k * ld + i], nv[j] = nn[(int64_t)k * ld + i], yv[j] = y_obs[k];
+  if (r0 > 0) {
+    n_prev = nn[(int64_t)(r0 - 1) * ld + i];
+    x_prev = 2.0 * log(y_obs[r0 - 1] / n_prev);
+  }
+#pragma unroll 8
+  for (int k = r0; k < min(r0 + kSvRows, Y); ++k) {
+    const double vk = v[(int64_t)k * ld + i], nk = nn[(int64_t)k * ld + i], yk = y_obs[k];
+    const double x = 2.0 * log(yk / nk);
+    const double v0s = vk / somp;  // used at k = 0 only
+    const double xm = x_prev - mu;
+    c[(int64_t)k * ld + i] = k == 0 ? mu + sigma * v0s - x : mu + phi * xm + sigma * vk - x;
+    if (JAC) {
+      J.du[(int64_t)(k * 3 + 0) * ld + i] = k == 0 ? dmu : (1.0 - phi) * dmu;
+      J.du[(int64_t)(k * 3 + 1) * ld + i] = dsigma * (k == 0 ? v0s : vk);
+      J.du[(int64_t)(k * 3 + 2) * ld + i] = k == 0 ? dphi * phi * sigma * v0s / omp : xm * dphi;
+      J.dv[(int64_t)k * ld + i] = k == 0 ? sigma / somp : sigma;
+      J.n0[(int64_t)k * ld + i] = 2.0 / nk;
+      if (k > 0) J.n1[(int64_t)(k - 1) * ld + i] = -2.0 * phi / n_prev;
+      J.dxdy[(int64_t)k * ld + i] = 2.0 / yk;
     }
-#pragma unroll
-    for (int j = 0; j < P; ++j) {
-      const int k = k0 + j;
-      if (k < Y) {
-        const double x = 2.0 * log(yv[j] / nv[j]);
-        const double v0s = vv[j] / somp;  // used at k = 0 only
-        const double xm = x_prev - mu;
-        c[(int64_t)k * ld + i] = k == 0 ? mu + sigma * v0s - x : mu + phi * xm + sigma * vv[j] - x;
-        if (JAC) {
-          J.du[(int64_t)(k * 3 + 0) * ld + i] = k == 0 ? dmu : (1.0 - phi) * dmu;
-          J.du[(int64_t)(k * 3 + 1) * ld + i] = dsigma * (k == 0 ? v0s : vv[j]);
-          J.du[(int64_t)(k * 3 + 2) * ld + i] = k == 0 ? dphi * phi * sigma * v0s / omp : xm * dphi;
-          J.dv[(int64_t)k * ld + i] = k == 0 ? sigma / somp : sigma;
-          J.n0[(int64_t)k * ld + i] = 2.0 / nv[j];
-          if (k > 0) J.n1[(int64_t)(k - 1) * ld + i] = -2.0 * phi / n_prev;
-          J.dxdy[(int64_t)k * ld + i] = 2.0 / yv[j];
-        }
-        x_prev = x, n_prev = nv[j];
-      }
-    }
+    x_prev = x, n_prev = nk;
   }
 }
 
@@ -648,16 +647,17 @@ int mlb_ssm_sv_constr_blocks(int64_t n, int32_t dim_y, int64_t ld, const double*
                              void* stream) {
   MLB_ARG(n >= 0 && dim_y >= 1 && ld >= n && q && y_obs && c);
   MLB_ARG(!J_out || (blocks_ok(J_out, dim_y) && J_out->dx_dy));
+  MLB_ARG(dim_y <= 65535 * kSvRows);
   if (n == 0) return MLB_OK;
-  const unsigned g = (unsigned)((n + 127) / 128);
+  const dim3 gy((unsigned)((n + 127) / 128), (unsigned)((dim_y + kSvRows - 1) / kSvRows));
   cudaStream_t s = (cudaStream_t)stream;
   if (J_out) {
     SsmBlocksOut o{const_cast<double*>(J_out->dc_du), const_cast<double*>(J_out->dc_dv),
                    const_cast<double*>(J_out->dc_dn0), const_cast<double*>(J_out->dc_dn1),
                    const_cast<double*>(J_out->dx_dy)};
-    k_ssm_sv_blocks<true><<<g, 128, 0, s>>>(n, dim_y, ld, q, y_obs, c, o);
+    k_ssm_sv_blocks<true><<<gy, 128, 0, s>>>(n, dim_y, ld, q, y_obs, c, o);
   } else {
-    k_ssm_sv_blocks<false><<<g, 128, 0, s>>>(n, dim_y, ld, q, y_obs, c, SsmBlocksOut{});
+    k_ssm_sv_blocks<false><<<gy, 128, 0, s>>>(n, dim_y, ld, q, y_obs, c, SsmBlocksOut{});
   }
   return finish_launch();
 }
