@@ -110,50 +110,74 @@ __global__ void __launch_bounds__(128)
 }
 
 // shared tail of the two inverse products: out = T^{-1} (vct - du s) given the stored
-// elimination (w, 1 / b') and the upper diagonal cu
+// elimination (w, 1 / b') and the upper diagonal cu.
+// Instruction count matters here: at 16,384 chains these sweeps run with one warp per
+// scheduler and ncu shows them issue-bound (~95 instructions per row in the first version,
+// DESIGN 3.3b).  Hence running pointers with loop-invariant row offsets instead of
+// recomputed 64-bit indices, full blocks of P rows without clamps or predicates, and a
+// scalar loop for the < P remaining rows.
 template <int U, int P>
 MLB_DEV void thomas_apply_lowrank(int Y, int64_t ld, int64_t i, const double* du_p,
                                   const double (&s)[U], const double* vct, const double* wv,
                                   const double* cu, const double* rb, double* out) {
+  const int Yf = Y / P * P;
   double dp = 0.0;
-  for (int k0 = 0; k0 < Y; k0 += P) {
-    double du[P][U], vv[P], ww[P];
+  {
+    const double *pdu = du_p + i, *pv = vct + i, *pw = wv + i;
+    double* po = out + i;
+    for (int k0 = 0; k0 < Yf; k0 += P) {
+      double du[P][U], vv[P], ww[P];
 #pragma unroll
-    for (int j = 0; j < P; ++j) {
-      const int k = clampi(k0 + j, 0, Y - 1);
+      for (int j = 0; j < P; ++j) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) du[j][u] = du_p[(int64_t)(k * U + u) * ld + i];
-      vv[j] = vct[(int64_t)k * ld + i], ww[j] = wv[(int64_t)k * ld + i];
-    }
+        for (int u = 0; u < U; ++u) du[j][u] = pdu[(int64_t)(j * U + u) * ld];
+        vv[j] = pv[(int64_t)j * ld], ww[j] = pw[(int64_t)j * ld];
+      }
 #pragma unroll
-    for (int j = 0; j < P; ++j) {
-      const int k = k0 + j;
-      if (k < Y) {
+      for (int j = 0; j < P; ++j) {
         double d = vv[j];
 #pragma unroll
         for (int u = 0; u < U; ++u) d = fma(-du[j][u], s[u], d);
         dp = d - ww[j] * dp;
-        out[(int64_t)k * ld + i] = dp;
+        po[(int64_t)j * ld] = dp;
       }
+      pdu += (int64_t)P * U * ld, pv += (int64_t)P * ld, pw += (int64_t)P * ld;
+      po += (int64_t)P * ld;
+    }
+    for (int k = Yf; k < Y; ++k) {
+      double d = *pv;
+#pragma unroll
+      for (int u = 0; u < U; ++u) d = fma(-pdu[(int64_t)u * ld], s[u], d);
+      dp = d - *pw * dp;
+      *po = dp;
+      pdu += (int64_t)U * ld, pv += ld, pw += ld, po += ld;
     }
   }
+  // backward: rows Y-1 ... 0; the rows above the last full block first, one at a time
   double x = 0.0;
-  for (int k0 = Y - 1; k0 >= 0; k0 -= P) {
+  double* po = out + (int64_t)(Y - 1) * ld + i;
+  const double* pr = rb + (int64_t)(Y - 1) * ld + i;
+  const double* pc = cu + (int64_t)(Y - 1) * ld + i;  // row Y-1 of cu is never read
+  for (int k = Y - 1; k >= Yf; --k) {
+    const double cv = k < Y - 1 ? *pc : 0.0;
+    x = (*po - cv * x) * *pr;
+    *po = x;
+    po -= ld, pr -= ld, pc -= ld;
+  }
+  for (int k0 = Yf - 1; k0 >= 0; k0 -= P) {
     double dd[P], cv[P], rv[P];
 #pragma unroll
     for (int j = 0; j < P; ++j) {
-      const int k = clampi(k0 - j, 0, Y - 1);
-      dd[j] = out[(int64_t)k * ld + i], rv[j] = rb[(int64_t)k * ld + i];
-      cv[j] = k < Y - 1 ? cu[(int64_t)k * ld + i] : 0.0;
+      dd[j] = po[-(int64_t)j * ld], rv[j] = pr[-(int64_t)j * ld];
+      // only the very first row handled overall (k = Y - 1) has no upper neighbour
+      cv[j] = (Yf == Y && k0 == Y - 1 && j == 0) ? 0.0 : pc[-(int64_t)j * ld];
     }
 #pragma unroll
     for (int j = 0; j < P; ++j) {
-      const int k = k0 - j;
-      if (k >= 0) {
-        x = (dd[j] - cv[j] * x) * rv[j];
-        out[(int64_t)k * ld + i] = x;
-      }
+      x = (dd[j] - cv[j] * x) * rv[j];
+      po[-(int64_t)j * ld] = x;
     }
+    po -= (int64_t)P * ld, pr -= (int64_t)P * ld, pc -= (int64_t)P * ld;
   }
 }
 
