@@ -32,7 +32,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="mlb", choices=("mlb", "reference"))
-    ap.add_argument("--workload", default="hier", choices=("hier", "toy", "fn", "hh"))
+    ap.add_argument("--workload", default="hier", choices=("hier", "toy", "fn", "hh", "sv"))
     ap.add_argument("--n-chain", type=int, default=0,
                     help="chains PER GPU (default 65536; 16384 for fn)")  # fmt: skip
     ap.add_argument("--n-school", type=int, default=8)
@@ -54,9 +54,9 @@ def parse_args():
                          "Metropolis HMC (key `ess_static`)")
     a = ap.parse_args()
     wl = a.workload
-    a.n_chain = a.n_chain or {"fn": 16384, "hh": 1024}.get(wl, 65536)
+    a.n_chain = a.n_chain or {"fn": 16384, "hh": 1024, "sv": 16384}.get(wl, 65536)
     a.n_step = a.n_step or {"fn": 2, "hh": 1}.get(wl, 32)
-    a.step_size = a.step_size or {"fn": 0.01, "hh": 0.002}.get(wl, 0.1)
+    a.step_size = a.step_size or {"fn": 0.01, "hh": 0.002, "sv": 0.02}.get(wl, 0.1)
     return a
 
 
@@ -217,6 +217,8 @@ def run_reference(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload == "sv":
+        return run_reference_sv(args, emit)
     rates, secs = [], []
     for i in range(args.warmup + args.steps):
         r, cores, desc, dt = cpu_oracle_rate(args, target_seconds=1.0,
@@ -677,6 +679,242 @@ def run_mlb(args, emit):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------- state-space workload (extra, `--workload sv`)
+
+
+def run_reference_sv(args, emit):
+    """CPU arm of `--workload sv`: the NumPy restatement (one core) on a bounded sample of
+    chains started on the manifold near the generating parameters."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from mlift_oracle import state_space as oss
+
+    y = sv_synthetic_observations()
+    solver = {"quasi-newton": "quasi_newton", "newton": "newton"}[args.solver]
+    rng = np.random.default_rng(202101)
+    m = args.cpu_sample_chains or 4
+    qs, _ = oss.sv_on_manifold_states(rng, m, SV_DIM_Y, y=y)
+    ps = []
+    for q in qs:
+        jac, _ = oss.sv_jacob_constr_split_blocks(*oss.sv_split(q, SV_DIM_Y), y)
+        p = rng.normal(size=q.size)
+        ps.append(p - oss.rmult_by_jacob_constr(*jac, oss.lmult_by_inv_gram(
+            *jac, *oss.decompose_gram(*jac), oss.lmult_by_jacob_constr(*jac, p))))
+    secs = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        for q, p in zip(qs, ps):
+            oss.sv_constrained_position_step(q, p, args.step_size, y, solver=solver)
+        if i >= args.warmup:
+            secs.append(time.perf_counter() - t0)
+    value = m / float(np.mean(secs))
+    emit({
+        "impl": "reference", "metric": "constrained position half-steps/s (all chains)",
+        "value": value, "unit": "half-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"stochastic-volatility state-space system (dim_y={SV_DIM_Y}), "
+                               "extra workload outside the BASELINE configs",
+                   "step_size": args.step_size, "solver": args.solver},
+        "cpu_baseline": {"value": value, "unit": "half-steps/s", "cores": 1, "kind": "port",
+                         "sample": f"{m} chains x 1 position half-step per bench step, NumPy "
+                                   "restatement, one core"},
+        "e2e": {"value": value, "unit": "half-steps/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    })  # fmt: skip
+
+
+SV_DIM_Y = 1000
+
+
+def sv_synthetic_observations(dim_y=SV_DIM_Y, seed=202101):
+    """Stochastic-volatility observations (stochastic_volatility.py:29-38) at mu = -0.5,
+    sigma = 0.3, phi = 0.76; observation noise kept away from zero (|n| >= 0.2)."""
+    rng = np.random.default_rng(seed)
+    mu, sigma, phi = -0.5, 0.3, -1.0 + 2.0 / (1.0 + np.exp(-2.0))
+    v, z = rng.normal(size=dim_y), rng.normal(size=dim_y)
+    noise = np.where(z < 0, -1.0, 1.0) * (0.2 + np.abs(z))
+    x = np.empty(dim_y)
+    x[0] = mu + sigma / np.sqrt(1 - phi**2) * v[0]
+    for t in range(1, dim_y):
+        x[t] = mu + phi * (x[t - 1] - mu) + sigma * v[t]
+    return np.exp(x / 2) * noise
+
+
+def run_sv(args, emit):
+    """Extra workload outside the BASELINE configs: the position half of
+    the constrained leapfrog step (projection, momentum update + re-projection, reversibility
+    check) for the stochastic-volatility state-space system, dim_y = 1,000, every chain.
+    The Hamiltonian half of these systems is not built, so the unit is a
+    position half-step, not a leapfrog step."""
+    import torch
+    import torch.distributed as dist
+
+    import manifold_lifting_b200 as mlb
+    from manifold_lifting_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the mlb arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    ss = mlb.state_space
+    n, dim_y, dt = args.n_chain, SV_DIM_Y, args.step_size
+    solver = {"quasi-newton": "quasi_newton", "newton": "newton"}.get(args.solver)
+    if solver is None:
+        raise SystemExit("--workload sv supports --solver newton | quasi-newton")
+    y = sv_synthetic_observations()
+    model = ss.StochasticVolatilityModel(y)
+    g = torch.Generator(device="cuda").manual_seed(202101 + rank)
+    q = _lib.soa_empty(n, model.dim_q).normal_(generator=g)
+    q[:, 0] = -0.5 + 0.2 * q[:, 0]
+    q[:, 1] = float(np.log(0.3)) + 0.2 * q[:, 1]
+    q[:, 2] = 2.0 + 0.2 * q[:, 2]
+    sigma, phi = q[:, 1].exp(), -1.0 + 2.0 * torch.sigmoid(q[:, 2])
+    yt = torch.as_tensor(y).cuda()
+    x = q[:, 0] + sigma / (1 - phi**2).sqrt() * q[:, 3]
+    for t in range(dim_y):  # lift onto the manifold: n_t = y_t / exp(x_t / 2)
+        if t > 0:
+            x = q[:, 0] + phi * (x - q[:, 0]) + sigma * q[:, 3 + t]
+        q[:, 3 + dim_y + t] = yt[t] / (x / 2).exp()
+    J, _ = model.jacob_constr_blocks(q)
+    gram = ss.decompose_gram(J)
+    p = ss.project_onto_cotangent_space(
+        _lib.soa_empty(n, model.dim_q).normal_(generator=g), J, gram)
+    del J, gram
+
+    def step():
+        return model.constrained_position_step(q, p, dt, solver=solver)
+
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    barrier()
+    clocks = ClockSampler(local, 0.025)
+    clocks.start()
+    l0 = mlb._lib.lib().mlb_launch_count()
+    ms = 0.0
+    for _ in range(args.steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms += e0.elapsed_time(e1)
+    launches = int(mlb._lib.lib().mlb_launch_count() - l0)
+    clk = clocks.stop()
+    barrier()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ok_frac = float((out["status"] == _lib.ST_OK).double().mean())
+    value = n * world * args.steps / (ms * 1e-3)
+
+    # end to end: pinned host [n, Q] arrays in, positions / momenta / status out
+    # (host arrays in the component-major layout too, so each copy is one contiguous transfer)
+    def pinned():
+        return torch.empty(model.dim_q, n, dtype=torch.float64, pin_memory=True).t()
+
+    qh, ph, qo, po = pinned(), pinned(), pinned(), pinned()
+    qh.copy_(q), ph.copy_(p)
+    e2e_iters = max(2, args.steps // 4)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_iters):
+        o = model.constrained_position_step(qh.cuda(non_blocking=True),
+                                            ph.cuda(non_blocking=True), dt, solver=solver)
+        qo.copy_(o["pos"], non_blocking=True), po.copy_(o["mom"], non_blocking=True)
+        st = o["status"].cpu()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = n * world * e2e_iters / float(te.item())
+
+    # roofline of the dominant kernel, timed alone on this stream
+    Jn, _ = model.jacob_constr_blocks(out["pos"])
+    c = model.constr(q + dt * p)
+    if solver == "newton":
+        kern = lambda: ss.lmult_by_inv_jacob_product(Jn, None, None, None, Jn, None, None, None, c)  # noqa: E731
+        kname, rows = "k_ssm_inv_jacob_product<3>", 2 * 3 + 8
+    else:
+        gn = ss.decompose_gram(Jn)
+        kern = lambda: ss.lmult_by_inv_gram(Jn, None, None, None, *gn, c)  # noqa: E731
+        kname, rows = "k_ssm_inv_gram<3>", 3 + 4
+    kern()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        kern()
+    e1.record()
+    torch.cuda.synchronize()
+    kms = e0.elapsed_time(e1) / 10
+    alg_bytes = 8.0 * n * rows * dim_y
+    try:
+        hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        src = "measured (MEASURED_PEAKS.json)"
+    except Exception:  # noqa: BLE001
+        hbm_peak, src = 6650.0, "fallback (B200_PROFILING.md)"
+    ach = alg_bytes / (kms * 1e-3) / 1e9
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        from mlift_oracle import state_space as oss
+
+        m = args.cpu_sample_chains or 12
+        qs, ps = q[:m].cpu().numpy(), p[:m].cpu().numpy()
+        t0 = time.perf_counter()
+        with np.errstate(all="ignore"):
+            for i in range(m):
+                oss.sv_constrained_position_step(qs[i], ps[i], dt, y, solver=solver)
+        sec = time.perf_counter() - t0
+        cpu = {"value": m / sec, "unit": "half-steps/s", "cores": 1, "kind": "port",
+               "sample": f"{m} chains x 1 position half-step, NumPy restatement "
+                         "(oracle/mlift_oracle/state_space.py), one core", "seconds": sec}  # fmt: skip
+    if rank == 0:
+        emit({
+            "metric": "constrained position half-steps/s (all chains)", "value": value,
+            "unit": "half-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"stochastic-volatility state-space system (dim_u=3, dim_y={dim_y}, "
+                                   f"dim_q={model.dim_q}), {n} chains per GPU, synthetic data; extra "
+                                   "workload outside the BASELINE configs (SURVEY 8f rank 3)",
+                       "unit_of_work": "position half of the constrained leapfrog step: projection, "
+                                       "momentum update + cotangent re-projection, reversibility check",
+                       "step_size": dt, "solver": args.solver, "chains_total": n * world,
+                       "ok_fraction": ok_frac,
+                       "mean_projection_iters": [float(out["iters_fwd"].double().mean()),
+                                                 float(out["iters_rev"].double().mean())],
+                       "l2": "working set (blocks + scratch, > 1 GB) larger than L2"},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": ach / hbm_peak, "traffic": None, "kernel": kname,
+                         "peak_source": src, "ms_per_launch": kms,
+                         "algorithmic_bytes_per_chain": 8.0 * rows * dim_y},
+            "e2e": {"value": e2e_value, "unit": "half-steps/s",
+                    "h2d_bytes_per_step": int(2 * qh.numel() * 8),
+                    "d2h_bytes_per_step": int(2 * qh.numel() * 8 + 4 * n),
+                    "api": "StochasticVolatilityModel.constrained_position_step (pinned host arrays)"},
+            "gpu_launches": launches, "clocks": clk, "cpu_baseline": cpu,
+        })  # fmt: skip
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     a = parse_args()
     # stdout carries exactly ONE JSON line: anything libraries print to fd 1 (e.g. NCCL's
@@ -687,7 +925,8 @@ def main():
     lines = []
     emit = lambda obj: lines.append(json.dumps(obj))  # noqa: E731
     try:
-        run_reference(a, emit) if a.impl == "reference" else run_mlb(a, emit)
+        (run_reference(a, emit) if a.impl == "reference"
+         else run_sv(a, emit) if a.workload == "sv" else run_mlb(a, emit))
     finally:
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
