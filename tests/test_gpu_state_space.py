@@ -370,3 +370,111 @@ def test_stochastic_volatility_constrained_position_step_matches_restatement(sol
     Jp = ss.lmult_by_jacob_constr(out["jacob_constr_blocks"], None, None, None, out["mom"])
     assert float(Jp[good].abs().max()) < 1e-9
     assert float(out["reverse_error"][good].max()) <= 2e-8
+
+
+def _guarded(n, rows, g=3):
+    """[n, rows] component-major view inside a larger array whose g rows before and after
+    are NaN (compute-sanitizer is not available on the GPU pool: out-of-range reads that
+    reach a result and out-of-range writes are caught with these canaries instead)."""
+    from manifold_lifting_b200 import _lib
+
+    big = _lib.soa_empty(n, rows + 2 * g)
+    big.fill_(float("nan"))
+    return big, big[:, g : g + rows]
+
+
+@pytest.mark.parametrize("dim_y,dim_u", [(1, 1), (2, 2), (7, 3), (8, 3), (13, 4), (24, 5), (50, 8)])
+def test_state_space_kernels_stay_inside_their_arrays(dim_y, dim_u):
+    """Every input lives between NaN guard rows, every output is written between guard
+    rows through the C ABI directly: results equal those from plain arrays bit for bit and
+    the guards stay NaN.  dim_y around multiples of the prefetch depths (4, 6, 8)."""
+    import ctypes as C
+
+    import manifold_lifting_b200 as mlb
+    from manifold_lifting_b200 import _lib
+    from manifold_lifting_b200._lib import check, lib, stream_ptr
+
+    ss = mlb.state_space
+    rng = np.random.default_rng(900 + dim_y)
+    n, g = 37, 3
+    _, arrs = _batch(rng, n, dim_y, dim_u)
+    _, arrs_r = _batch(rng, n, dim_y, dim_u)
+    plain, plain_r = ss.JacobBlocks(*arrs), ss.JacobBlocks(*arrs_r)
+
+    def guarded_blocks(src):
+        J = ss.JacobBlocks.__new__(ss.JacobBlocks)
+        J.n, J.dim_y, J.dim_u = n, dim_y, dim_u
+        keep = []
+        for name, rows in (("dc_du", dim_y * dim_u), ("dc_dv", dim_y), ("dc_dn0", dim_y),
+                           ("dc_dn1", dim_y - 1), ("dx_dy", dim_y)):  # fmt: skip
+            if rows == 0:
+                setattr(J, name, None)
+                continue
+            big, view = _guarded(n, rows, g)
+            view.copy_(getattr(src, name))
+            keep.append(big)
+            setattr(J, name, view)
+        return J, keep
+
+    J, keep = guarded_blocks(plain)
+    Jr, keep_r = guarded_blocks(plain_r)
+    vy = torch.as_tensor(rng.normal(size=(n, dim_y)))
+    vq = torch.as_tensor(rng.normal(size=(n, dim_u + 2 * dim_y)))
+    big_vy, gvy = _guarded(n, dim_y, g)
+    gvy.copy_(vy)
+    big_vq, gvq = _guarded(n, dim_u + 2 * dim_y, g)
+    gvq.copy_(vq)
+
+    def same(x, y):
+        assert torch.equal(x, y), float((x - y).abs().max())
+
+    a, b, chol = ss.decompose_gram(plain)
+    a2, b2, chol2 = ss.decompose_gram(J)
+    same(a, a2), same(b, b2), same(chol, chol2)
+    same(ss.lmult_by_jacob_constr(plain, None, None, None, vq),
+         ss.lmult_by_jacob_constr(J, None, None, None, gvq))
+    same(ss.rmult_by_jacob_constr(plain, None, None, None, vy),
+         ss.rmult_by_jacob_constr(J, None, None, None, gvy))
+    same(ss.log_det_sqrt_gram(plain, gram=(a, b, chol)), ss.log_det_sqrt_gram(J, gram=(a, b, chol)))
+    want_g = ss.lmult_by_inv_gram(plain, None, None, None, a, b, chol, vy)
+    want_p = ss.lmult_by_inv_jacob_product(plain, None, None, None, plain_r, None, None, None, vy)
+    want_c = ss.project_onto_cotangent_space(vq, plain, (a, b, chol))
+    # guarded gram inputs and guarded outputs, through the C ABI
+    big_a, ga = _guarded(n, max(dim_y - 1, 1), g)
+    big_b, gb = _guarded(n, dim_y, g)
+    big_c, gc = _guarded(n, dim_u * dim_u, g)
+    if dim_y > 1:
+        ga.copy_(a)
+    gb.copy_(b), gc.copy_(chol.reshape(n, dim_u * dim_u))
+    dims = (C.c_int64(n), C.c_int32(dim_y), C.c_int32(dim_u), C.c_int64(n))
+    ptr = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    cs, cr = J.c_struct(), Jr.c_struct()
+    big_o, go = _guarded(n, dim_y, g)
+    check(lib().mlb_ssm_lmult_by_inv_gram(*dims, C.byref(cs), ptr(ga) if dim_y > 1 else None,
+                                          ptr(gb), ptr(gc), ptr(gvy), ptr(go), stream_ptr()))
+    same(go, want_g)
+    assert bool(torch.isnan(big_o[:, :g]).all()) and bool(torch.isnan(big_o[:, g + dim_y :]).all())
+    big_o2, go2 = _guarded(n, dim_y, g)
+    check(lib().mlb_ssm_lmult_by_inv_jacob_product(*dims, C.byref(cs), C.byref(cr), ptr(gvy),
+                                                   ptr(go2), stream_ptr()))
+    same(go2, want_p)
+    assert bool(torch.isnan(big_o2[:, :g]).all()) and bool(torch.isnan(big_o2[:, g + dim_y :]).all())
+    check(lib().mlb_ssm_project_onto_cotangent_space(
+        *dims, C.byref(cs), ptr(ga) if dim_y > 1 else None, ptr(gb), ptr(gc), ptr(gvq),
+        stream_ptr()))
+    same(gvq, want_c)
+    q_rows = dim_u + 2 * dim_y
+    assert bool(torch.isnan(big_vq[:, :g]).all()) and bool(torch.isnan(big_vq[:, g + q_rows :]).all())
+    # the inputs' guards are untouched as well
+    for big, rows in ((big_vy, dim_y), (big_a, max(dim_y - 1, 1)), (big_b, dim_y)):
+        assert bool(torch.isnan(big[:, :g]).all()) and bool(torch.isnan(big[:, g + rows :]).all())
+    # tridiagonal solve (one right-hand side: the fused kernel) with guarded arrays
+    big_x, gx = _guarded(n, dim_y, g)
+    lower = ga if dim_y > 1 else None
+    check(lib().mlb_tridiagonal_solve(C.c_int64(n), C.c_int32(dim_y), C.c_int32(1), C.c_int64(n),
+                                      ptr(lower) if dim_y > 1 else None, ptr(gb),
+                                      ptr(lower) if dim_y > 1 else None, ptr(gvy), ptr(gx),
+                                      stream_ptr()))
+    same(gx, mlb.linalg.tridiagonal_solve(a, b, a, vy) if dim_y > 1
+         else mlb.linalg.tridiagonal_solve(None, b, None, vy))
+    assert bool(torch.isnan(big_x[:, :g]).all()) and bool(torch.isnan(big_x[:, g + dim_y :]).all())
