@@ -828,14 +828,19 @@ def run_sv(args, emit):
 
     qh, ph, qo, po = pinned(), pinned(), pinned(), pinned()
     qh.copy_(q), ph.copy_(p)
-    e2e_iters = max(2, args.steps // 4)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_iters):
+    e2e_iters = max(3, args.steps // 3)
+
+    def e2e_step():
         o = model.constrained_position_step(qh.cuda(non_blocking=True),
                                             ph.cuda(non_blocking=True), dt, solver=solver)
         qo.copy_(o["pos"], non_blocking=True), po.copy_(o["mom"], non_blocking=True)
-        st = o["status"].cpu()
+        return o["status"].cpu()
+
+    e2e_step()  # untimed: first-use allocations of the staging tensors
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_iters):
+        e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
