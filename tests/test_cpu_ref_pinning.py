@@ -1,0 +1,178 @@
+"""The oracles against outputs of the REFERENCE'S OWN SOURCE (tests/golden/ref_*.npz).
+
+The fixtures were written by tests/golden/make_ref_golden.py, which imports
+/root/reference/mlift unmodified on top of the torch-fp64 `jax` / `mici` stand-ins of
+oracle/ref_shim.  Here the closed-form C++ oracle (oracle/c, the bulk checker of the GPU
+tests) and, where cheap, the torch restatement (oracle/mlift_oracle) are held to them:
+the 13 callables of mlift/systems.py:328-346, the three projection loops (:190-326)
+including iteration counts and failure statuses, and whole constrained leapfrog steps.
+
+Tolerance: 1e-10 relative (north-star) unless a comment says otherwise.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import c_oracle as co
+from _cases import rel_err
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-10
+
+
+def load(name):
+    path = os.path.join(GOLD, f"ref_{name}.npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not generated")
+    return np.load(path)
+
+
+def hier_model(g):
+    return co.OracleModel.hier(g["y_obs"], g["sigma"], str(g["parametrization"]))
+
+
+def check_ops(cm, g, hier, tol=TOL, tol_grad=TOL, tol_solve=TOL):
+    """The 13 callables (chains as rows).  `tol_solve` applies to results of solves with
+    the (possibly ill-conditioned) capacitance matrix."""
+    q, qp = g["ops_q"], g["ops_q_prev"]
+    vq, wy = g["ops_vec_q"], g["ops_vec_y"]
+    jac, c = cm.jacob_constr_blocks(q)
+    assert rel_err(cm.constr(q), g["ops_c"]) < tol
+    assert rel_err(c, g["ops_c"]) < tol
+    assert rel_err(jac[0], g["ops_dy_du"]) < tol
+    if hier:
+        assert rel_err(jac[1], g["ops_dy_dv"]) < tol
+    assert rel_err(jac[2], g["ops_dy_dn"]) < tol
+    gram = cm.decompose_gram(jac)
+    assert rel_err(gram[0], g["ops_chol"]) < tol_solve
+    assert rel_err(gram[1], g["ops_d"]) < tol
+    assert rel_err(cm.log_det_sqrt_gram(q), g["ops_logdet"]) < tol
+    grad, val = cm.grad_log_det_sqrt_gram(q)
+    assert rel_err(val, g["ops_logdet"]) < tol
+    assert rel_err(grad, g["ops_grad_logdet"]) < tol_grad
+    nld, gnld = cm.neg_log_dens(q)
+    assert rel_err(nld, g["ops_nld"]) < tol
+    assert rel_err(gnld, g["ops_grad_nld"]) < tol
+    assert rel_err(nld + val, g["ops_h1"]) < tol
+    assert rel_err(gnld + grad, g["ops_dh1_dpos"]) < tol_grad
+    assert rel_err(cm.lmult_by_jacob_constr(jac, vq), g["ops_jv"]) < tol
+    assert rel_err(cm.rmult_by_jacob_constr(jac, wy), g["ops_jtw"]) < tol
+    assert rel_err(cm.lmult_by_pinv_jacob_constr(jac, gram, wy), g["ops_pinv_w"]) < tol_solve
+    assert rel_err(cm.normal_space_component(jac, gram, vq), g["ops_nsc_v"]) < tol_solve
+    jac_prev, _ = cm.jacob_constr_blocks(qp)
+    assert rel_err(cm.lmult_by_inv_jacob_product(jac, jac_prev, wy), g["ops_ijp_w"]) < tol_solve
+    proj = vq - cm.normal_space_component(jac, gram, vq)
+    assert rel_err(proj, g["ops_proj_v"]) < tol_solve
+
+
+def check_loops(cm, g, norms=("max",), tol=TOL, tol_mu=TOL):
+    """`system._quasi_newton_projection / _newton_projection / ..._with_line_search` called
+    directly: projected position, mu / dt, iteration count, last norms, constraint calls."""
+    dt = float(g["loop_dt"])
+    for nn in norms:
+        for sid in (0, 1, 2):
+            opts = co.solver_opts(sid, norm=co.NORM_MAX if nn == "max" else co.NORM_EUCLID)
+            r = cm.solve_projection(g[f"loop_{nn}_q_start"], g["loop_q_prev"], dt, opts)
+            it = g[f"loop_{nn}_iters_{sid}"].astype(int)
+            assert (r["iters"] == it).all(), (nn, sid, r["iters"], it)
+            ok = np.isfinite(g[f"loop_{nn}_err_{sid}"])
+            assert rel_err(r["q"][ok], g[f"loop_{nn}_q_{sid}"][ok]) < tol
+            assert rel_err(r["mu"][ok], g[f"loop_{nn}_mu_{sid}"][ok]) < tol_mu
+            # last norms are O(tolerance) numbers: compare absolutely at rounding level
+            assert np.allclose(r["err"][ok], g[f"loop_{nn}_err_{sid}"][ok], rtol=1e-6, atol=1e-13)
+            assert np.allclose(r["norm_dq"][ok], g[f"loop_{nn}_norm_dq_{sid}"][ok], rtol=1e-6,
+                               atol=1e-13)  # fmt: skip
+            if sid == 2:
+                assert (r["n_constr"] == g[f"loop_{nn}_n_constr_2"].astype(int)).all()
+
+
+def check_steps(cm, g, tag="step", tol=TOL, tol_p=TOL, solver_ids=None, **opt_kw):
+    """Whole constrained leapfrog steps, one at a time, against the reference-driven
+    trajectories: q, p, h, (forward, reverse) iteration counts, failure status."""
+    dt, n_step = float(g[f"{tag}_dt"]), int(g[f"{tag}_n_step"])
+    for sid in g[f"{tag}_solvers"] if solver_ids is None else solver_ids:
+        sid = int(sid)
+        q, p = g[f"{tag}_q0"].copy(), g[f"{tag}_p0"].copy()
+        status = g[f"{tag}_status_{sid}"]
+        n_done = g[f"{tag}_n_done_{sid}"]
+        alive = np.ones(len(q), bool)
+        for s in range(n_step):
+            r = cm.leapfrog_steps(q, p, dt, 1, co.solver_opts(sid, **opt_kw))
+            done = alive & (n_done > s)
+            fails = alive & (n_done == s)
+            assert (r["status"][done] == 0).all(), (tag, sid, s, r["status"], status)
+            assert (r["status"][fails] == status[fails]).all(), (tag, sid, s, r["status"],
+                                                                 status)  # fmt: skip
+            assert rel_err(r["q"][done], g[f"{tag}_q_{sid}"][done, s]) < tol
+            assert rel_err(r["p"][done], g[f"{tag}_p_{sid}"][done, s]) < tol_p
+            assert rel_err(r["h_final"][done], g[f"{tag}_h_{sid}"][done, s]) < tol
+            its = g[f"{tag}_iters_{sid}"][done, s]
+            assert (r["iters_fwd"][done] == its[:, 0]).all(), (sid, s, r["iters_fwd"], its)
+            assert (r["iters_rev"][done] == its[:, 1]).all(), (sid, s, r["iters_rev"], its)
+            if s == 0:
+                assert rel_err(r["h_init"], g[f"{tag}_h0"]) < tol
+            alive = done
+            q, p = r["q"], r["p"]
+
+
+@pytest.mark.parametrize("name", ["hier_unbounded", "hier_normal", "hier16_unbounded"])
+def test_hier_c_oracle_matches_reference_source(name):
+    g = load(name)
+    cm = hier_model(g)
+    check_ops(cm, g, hier=True)
+    check_loops(cm, g, norms=("max", "l2"))
+    check_steps(cm, g)
+    check_steps(cm, g, tag="fail")
+
+
+@pytest.mark.parametrize("name", ["hier_unbounded", "hier_normal"])
+def test_hier_autodiff_restatement_matches_reference_source(name):
+    """oracle/mlift_oracle (torch autodiff restatement) on the same fixture: callables and
+    one step per solver for a few chains."""
+    import torch
+
+    from _cases import hier_case
+    from mlift_oracle import solvers as osolvers
+    from mlift_oracle.mici import ChainState, ConstrainedLeapfrogIntegrator
+
+    g = load(name)
+    _, osys, _ = hier_case(str(g["parametrization"]), g["y_obs"], g["sigma"])
+    for i in range(4):
+        st = ChainState(g["ops_q"][i])
+        jb = osys.jacob_constr_blocks(st)
+        for a, k in zip(jb, ("ops_dy_du", "ops_dy_dv", "ops_dy_dn")):
+            assert rel_err(np.asarray(a), g[k][i]) < TOL
+        assert rel_err(np.asarray(osys.constr(st)), g["ops_c"][i]) < TOL
+        assert rel_err(float(osys.log_det_sqrt_gram(st)), g["ops_logdet"][i]) < TOL
+        assert rel_err(np.asarray(osys.grad_log_det_sqrt_gram(st)), g["ops_grad_logdet"][i]) < TOL
+        assert rel_err(float(osys.neg_log_dens(st)), g["ops_nld"][i]) < TOL
+        assert rel_err(np.asarray(osys.grad_neg_log_dens(st)), g["ops_grad_nld"][i]) < TOL
+        proj = osys.project_onto_cotangent_space(torch.as_tensor(g["ops_vec_q"][i].copy()), st)
+        assert rel_err(np.asarray(proj), g["ops_proj_v"][i]) < TOL
+    fns = {0: osolvers.solve_projection_onto_manifold_quasi_newton,
+           1: osolvers.solve_projection_onto_manifold_newton,
+           2: osolvers.solve_projection_onto_manifold_newton_with_line_search}  # fmt: skip
+    for sid, fn in fns.items():
+        for i in (0, 7, 12):
+            integ = ConstrainedLeapfrogIntegrator(
+                osys, float(g["step_dt"]), projection_solver=fn,
+                projection_solver_kwargs=dict(constraint_tol=1e-9, position_tol=1e-8,
+                                              max_iters=50))  # fmt: skip
+            s1 = integ.step(ChainState(g["step_q0"][i], g["step_p0"][i]))
+            assert rel_err(np.asarray(s1.pos), g[f"step_q_{sid}"][i, 0]) < TOL
+            assert rel_err(np.asarray(s1.mom), g[f"step_p_{sid}"][i, 0]) < TOL
+            assert tuple(integ.last_iters) == tuple(g[f"step_iters_{sid}"][i, 0])
+
+
+def test_tridiagonal_restatement_matches_reference_source():
+    """oracle/mlift_oracle/linalg.py vs mlift/linalg.py:46-114 run from source."""
+    from mlift_oracle import linalg as ol
+
+    g = load("linalg")
+    for k in range(int(g["n_case"])):
+        a, b, c, d = (g[f"{n}_{k}"] for n in "abcd")
+        assert rel_err(np.asarray(ol.tridiagonal_solve(a, b, c, d)), g[f"x_{k}"]) < 1e-12
+        assert rel_err(float(ol.tridiagonal_pos_def_log_det(a, b)), g[f"logdet_{k}"]) < 1e-12
+        t = np.diag(a, -1) + np.diag(b) + np.diag(c, 1)
+        assert rel_err(np.linalg.solve(t, d), g[f"x_{k}"]) < 1e-12
