@@ -66,7 +66,7 @@ def check_ops(cm, g, hier, tol=TOL, tol_grad=TOL, tol_solve=TOL):
     assert rel_err(proj, g["ops_proj_v"]) < tol_solve
 
 
-def check_loops(cm, g, norms=("max",), tol=TOL, tol_mu=TOL):
+def check_loops(cm, g, norms=("max",), tol=TOL, tol_mu=TOL, atol_norm=1e-13):
     """`system._quasi_newton_projection / _newton_projection / ..._with_line_search` called
     directly: projected position, mu / dt, iteration count, last norms, constraint calls."""
     dt = float(g["loop_dt"])
@@ -80,9 +80,11 @@ def check_loops(cm, g, norms=("max",), tol=TOL, tol_mu=TOL):
             assert rel_err(r["q"][ok], g[f"loop_{nn}_q_{sid}"][ok]) < tol
             assert rel_err(r["mu"][ok], g[f"loop_{nn}_mu_{sid}"][ok]) < tol_mu
             # last norms are O(tolerance) numbers: compare absolutely at rounding level
-            assert np.allclose(r["err"][ok], g[f"loop_{nn}_err_{sid}"][ok], rtol=1e-6, atol=1e-13)
+            # (|dc| ~ |J| |dq|: 1e-13 for eight-schools, 1e-10 for the ODE models)
+            assert np.allclose(r["err"][ok], g[f"loop_{nn}_err_{sid}"][ok], rtol=1e-6,
+                               atol=atol_norm)  # fmt: skip
             assert np.allclose(r["norm_dq"][ok], g[f"loop_{nn}_norm_dq_{sid}"][ok], rtol=1e-6,
-                               atol=1e-13)  # fmt: skip
+                               atol=atol_norm)  # fmt: skip
             if sid == 2:
                 assert (r["n_constr"] == g[f"loop_{nn}_n_constr_2"].astype(int)).all()
 
@@ -176,3 +178,94 @@ def test_tridiagonal_restatement_matches_reference_source():
         assert rel_err(float(ol.tridiagonal_pos_def_log_det(a, b)), g[f"logdet_{k}"]) < 1e-12
         t = np.diag(a, -1) + np.diag(b) + np.diag(c, 1)
         assert rel_err(np.linalg.solve(t, d), g[f"x_{k}"]) < 1e-12
+
+
+def fn_model(par):
+    from _cases import fn_data
+
+    g, y_obs = fn_data()
+    return co.OracleModel.fn(y_obs, g["t_seq"], g["dt"], par)
+
+
+def hh_model(par):
+    from _cases import hh_data
+
+    g, y_obs = hh_data()
+    return co.OracleModel.hh(y_obs, g, par)
+
+
+def report(cm, g, hier=False):
+    """Agreement actually reached, per quantity (printed with -s; used to set the
+    tolerances below)."""
+    q = g["ops_q"]
+    jac, c = cm.jacob_constr_blocks(q)
+    gram = cm.decompose_gram(jac)
+    grad, val = cm.grad_log_det_sqrt_gram(q)
+    out = dict(c=rel_err(c, g["ops_c"]), dy_du=rel_err(jac[0], g["ops_dy_du"]),
+               chol=rel_err(gram[0], g["ops_chol"]), logdet=rel_err(val, g["ops_logdet"]),
+               grad=rel_err(grad, g["ops_grad_logdet"]),
+               pinv=rel_err(cm.lmult_by_pinv_jacob_constr(jac, gram, g["ops_vec_y"]),
+                            g["ops_pinv_w"]),
+               nsc=rel_err(cm.normal_space_component(jac, gram, g["ops_vec_q"]),
+                           g["ops_nsc_v"]))  # fmt: skip
+    return out
+
+
+# Ill-conditioning, measured not argued: the capacitance matrix I + A^T A / sigma^2 has
+# condition number ~1e10 (FN) / ~1e12 (HH), so anything that went through a solve with it
+# (Cholesky factor, pseudo-inverse, momenta) carries cond * eps: the reference source run
+# on torch's LAPACK and the closed-form C++ oracle agree on those to 1e-9..1e-8 (FN) while
+# residuals, Jacobians, log-determinants, projected POSITIONS, Hamiltonians and iteration
+# counts agree to 1e-10 or better.
+@pytest.mark.parametrize("par", ["unbounded", "normal"])
+def test_fn_c_oracle_matches_reference_source(par):
+    g = load(f"fn_{par}")
+    cm = fn_model(par)
+    check_ops(cm, g, hier=False, tol=TOL, tol_grad=1e-8, tol_solve=1e-7)
+    check_loops(cm, g, tol=TOL, tol_mu=TOL, atol_norm=1e-10)
+    check_steps(cm, g, tol=TOL, tol_p=1e-7)
+
+
+@pytest.mark.parametrize("par", ["normal", "unbounded"])
+def test_hh_c_oracle_matches_reference_source(par):
+    g = load(f"hh_{par}")
+    cm = hh_model(par)
+    check_ops(cm, g, hier=False, tol=1e-9, tol_grad=1e-7, tol_solve=1e-5)
+    check_loops(cm, g, tol=TOL, tol_mu=1e-7, atol_norm=1e-8)
+    check_steps(cm, g, tol=TOL, tol_p=1e-5)
+
+
+@pytest.mark.parametrize("tag", ["closed", "auto"])
+def test_state_space_restatement_matches_reference_source(tag):
+    """oracle/mlift_oracle/state_space.py (the checker of the `mlb_ssm_*` kernels) against
+    PartiallyInvertibleStateSpaceModelSystem + the stochastic-volatility model run from the
+    reference's source (systems.py:1084-1254, stochastic_volatility.py:71-141), with the
+    model's closed-form blocks (`closed`) and the class's autodiff default (`auto`)."""
+    from mlift_oracle import state_space as ss
+
+    g = load("sv")
+    y = g["y_obs"]
+    dim_y = y.size
+    for i in range(g[f"{tag}_q"].shape[0]):
+        q, qp = g[f"{tag}_q"][i], g[f"{tag}_q_prev"][i]
+        vq, wy = g[f"{tag}_vec_q"][i], g[f"{tag}_vec_y"][i]
+        u, v, n = ss.sv_split(q, dim_y)
+        blocks, c = ss.sv_jacob_constr_split_blocks(u, v, n, y)
+        assert rel_err(c, g[f"{tag}_c"][i]) < 1e-12
+        assert rel_err(ss.sv_constr_split(u, v, n, y)[0], g[f"{tag}_c"][i]) < 1e-12
+        dc_du, dc_dv, dc_dn, dx_dy = blocks
+        for a, k in ((dc_du, "dc_du"), (dc_dv, "dc_dv"), (dc_dn[0], "dc_dn0"),
+                     (dc_dn[1], "dc_dn1"), (dx_dy, "dx_dy")):  # fmt: skip
+            assert rel_err(a, g[f"{tag}_{k}"][i]) < 1e-12, k
+        a, b, chol = ss.decompose_gram(*blocks)
+        assert rel_err(a, g[f"{tag}_a"][i]) < 1e-12 and rel_err(b, g[f"{tag}_b"][i]) < 1e-12
+        assert rel_err(chol, g[f"{tag}_chol"][i]) < 1e-11
+        assert rel_err(ss.log_det_sqrt_gram(*blocks), g[f"{tag}_logdet"][i]) < 1e-12
+        assert rel_err(ss.lmult_by_jacob_constr(*blocks, vq), g[f"{tag}_jv"][i]) < 1e-12
+        assert rel_err(ss.rmult_by_jacob_constr(*blocks, wy), g[f"{tag}_jtw"][i]) < 1e-12
+        pinv = ss.rmult_by_jacob_constr(*blocks, ss.lmult_by_inv_gram(*blocks, a, b, chol, wy))
+        assert rel_err(pinv, g[f"{tag}_pinv_w"][i]) < 1e-11
+        up, vp, np_ = ss.sv_split(qp, dim_y)
+        blocks_p, _ = ss.sv_jacob_constr_split_blocks(up, vp, np_, y)
+        ijp = ss.lmult_by_inv_jacob_product(*blocks, *blocks_p, wy)
+        assert rel_err(ijp, g[f"{tag}_ijp_w"][i]) < 1e-11
