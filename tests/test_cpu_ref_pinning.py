@@ -66,7 +66,7 @@ def check_ops(cm, g, hier, tol=TOL, tol_grad=TOL, tol_solve=TOL):
     assert rel_err(proj, g["ops_proj_v"]) < tol_solve
 
 
-def check_loops(cm, g, norms=("max",), tol=TOL, tol_mu=TOL, atol_norm=1e-13):
+def check_loops(cm, g, norms=("max",), tol=TOL, tol_mu=TOL, atol_norm=1e-12):
     """`system._quasi_newton_projection / _newton_projection / ..._with_line_search` called
     directly: projected position, mu / dt, iteration count, last norms, constraint calls."""
     dt = float(g["loop_dt"])
