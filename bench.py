@@ -5,10 +5,16 @@ leapfrog steps/s summed over all chains).
   python bench.py --gpus N --steps K --warmup W            # CUDA arm (this repo)
   python bench.py --impl reference --gpus N --steps K ...   # CPU arm (oracle port)
 
-A bench "step" is ONE launch of the fused trajectory kernel: `--n-step` constrained
-leapfrog steps (A-B-A with projection and reversibility check) for every chain.
+A bench "step" is ONE `mlb_leapfrog_steps` call: `--n-step` constrained leapfrog steps
+(A-B-A with projection and reversibility check) for every chain.
 `value` = chains * n_step * K / (sum of the K CUDA-event intervals, max over ranks).
-Prints ONE JSON line on rank 0.  Data are synthetic (SURVEY.md 8d config 3).
+Prints ONE JSON line on rank 0.  Data are synthetic (SURVEY.md 8d).
+
+Default = BASELINE.json config 3 as written: the eight-schools-shaped model with 65,536
+chains IN TOTAL, split into contiguous blocks of 65,536 / N chains per GPU ("scaling":
+"strong").  The same line carries `weak` (65,536 chains per GPU, N > 1 only) and `legs`:
+short runs of the other BASELINE configs - toy (65,536), FitzHugh-Nagumo (16,384) and
+Hodgkin-Huxley (8,192 in total) - each with its own roofline / cpu_baseline / e2e.
 """
 import argparse
 import ctypes as C
@@ -34,7 +40,11 @@ def parse_args():
     ap.add_argument("--impl", default="mlb", choices=("mlb", "reference"))
     ap.add_argument("--workload", default="hier", choices=("hier", "toy", "fn", "hh", "sv"))
     ap.add_argument("--n-chain", type=int, default=0,
-                    help="chains PER GPU (default 65536; 16384 for fn)")  # fmt: skip
+                    help="chains IN TOTAL under --scaling strong (default 65536; 16384 fn, "
+                         "8192 hh), PER GPU under --scaling weak")  # fmt: skip
+    ap.add_argument("--scaling", default="strong", choices=("strong", "weak"))
+    ap.add_argument("--no-legs", action="store_true",
+                    help="skip the extra legs (toy / fn / hh and the weak-scaling run)")
     ap.add_argument("--n-school", type=int, default=8)
     ap.add_argument("--n-step", type=int, default=0,
                     help="leapfrog steps per launch (default 32; 2 for fn)")  # fmt: skip
@@ -53,11 +63,40 @@ def parse_args():
                          "default, utils.py:286-288; key `ess`) and / or static-trajectory "
                          "Metropolis HMC (key `ess_static`)")
     a = ap.parse_args()
-    wl = a.workload
-    a.n_chain = a.n_chain or {"fn": 16384, "hh": 1024, "sv": 16384}.get(wl, 65536)
+    return with_workload_defaults(a, a.workload)
+
+
+def with_workload_defaults(a, wl, **override):
+    """Copy of the arguments with the per-workload defaults filled in (BASELINE configs)."""
+    a = argparse.Namespace(**{**vars(a), "workload": wl, **override})
+    a.n_chain = a.n_chain or {"fn": 16384, "hh": 8192, "sv": 16384}.get(wl, 65536)
     a.n_step = a.n_step or {"fn": 2, "hh": 1}.get(wl, 32)
     a.step_size = a.step_size or {"fn": 0.01, "hh": 0.002, "sv": 0.02}.get(wl, 0.1)
     return a
+
+
+def local_chains(args, world):
+    """(chains on each rank, chains in total): contiguous blocks of total / N under strong
+    scaling, the full count per GPU under weak scaling."""
+    if args.scaling == "weak":
+        return args.n_chain, args.n_chain * world
+    if args.n_chain % world:
+        raise SystemExit(f"--n-chain {args.n_chain} is not divisible by {world} GPUs")
+    return args.n_chain // world, args.n_chain
+
+
+def workload_config(args, world):
+    """The `config` object: what is run, from the arguments alone, so that the CUDA arm and
+    the reference arm print the SAME dict (measured quantities go under `measured`)."""
+    n_local, total = local_chains(args, world)
+    return {
+        "workload": workload_name(args), "chains_total": total, "chains_per_gpu": n_local,
+        "n_step": args.n_step, "step_size": args.step_size, "solver": args.solver,
+        "constraint_tol": 1e-9, "position_tol": 1e-8, "reverse_check_tol": 2e-8,
+        "max_iters": 50,
+        "l2": "state reset and L2 flushed (256 MiB memset) between timed steps, outside the "
+              "CUDA-event intervals",
+    }  # fmt: skip
 
 
 # ------------------------------------------------------------------ workload (host)
@@ -152,15 +191,14 @@ def make_inputs(args, n_chain, chain0):
 def workload_name(args):
     if args.workload == "hier":
         return (f"eight-schools-shaped hierarchical model (J={args.n_school}, dim_q="
-                f"{2 + 2 * args.n_school}), {args.n_chain} chains per GPU, synthetic data")  # fmt: skip
+                f"{2 + 2 * args.n_school}), synthetic data")  # fmt: skip
     if args.workload == "fn":
         return (f"FitzHugh-Nagumo ODE model (RK4 dt=0.05, 200 obs, dim_q=209), "
-                f"{args.n_chain} chains per GPU, synthetic observations")  # fmt: skip
+                f"synthetic observations")  # fmt: skip
     if args.workload == "hh":
         return (f"Hodgkin-Huxley current-stimulus model (1100 exp-Euler steps, 1001 obs, "
-                f"dim_q=1008, normal parametrisation), {args.n_chain} chains per GPU, "
-                f"synthetic observations")  # fmt: skip
-    return f"toy 2-D model (sigma=0.1), {args.n_chain} chains per GPU"
+                f"dim_q=1008, normal parametrisation), synthetic observations")  # fmt: skip
+    return "toy 2-D model (sigma=0.1, dim_q=3)"
 
 
 # ------------------------------------------------------------------ CPU (oracle) leg
@@ -214,7 +252,12 @@ def cpu_oracle_rate(args, target_seconds=12.0, sample_chains=0):
 
 
 def run_reference(args, emit):
+    """`--impl reference`: the reference's CPU implementation of the path - here the C++
+    oracle port on all host cores (JAX / Mici are not installable offline) - on the CUDA
+    arm's config, metric and unit; each bench step is a bounded sample of the workload.
+    Under torchrun rank 0 alone runs it; the other ranks exit without work."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     if args.workload == "sv":
@@ -230,12 +273,11 @@ def run_reference(args, emit):
         "impl": "reference", "metric": "constrained leapfrog steps/s (all chains)",
         "value": value, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(args), "n_step": args.n_step,
-                   "step_size": args.step_size, "solver": args.solver,
-                   "note": "reference arm = CPU oracle port on host cores (JAX/Mici are "
-                           "not installable offline); each bench step is a bounded sample"},
+        "config": workload_config(args, max(world, args.gpus)),
+        "note": "reference arm = CPU oracle port on host cores (JAX/Mici are not installable "
+                "offline); each bench step is a bounded sample of the config's workload",
         "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port",
                          "sample": desc},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0,
@@ -448,9 +490,6 @@ def run_mlb(args, emit):
     import torch
     import torch.distributed as dist
 
-    import manifold_lifting_b200 as mlb
-    from manifold_lifting_b200 import _lib, flops
-
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -462,8 +501,49 @@ def run_mlb(args, emit):
         from manifold_lifting_b200 import parallel as _par
 
         bound_cpus = _par.bind_to_gpu_cpus(local)
-    if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = {"rank": rank, "world": world, "local": local, "bound_cpus": bound_cpus}
+
+    line = measure(args, ctx, full=True)
+    if not args.no_legs:
+        # the other BASELINE configs, a few steps each, same keys (no ESS legs)
+        k_leg = max(2, min(args.steps, 5))
+        if world > 1 and args.scaling == "strong":
+            weak = measure(with_workload_defaults(args, args.workload, scaling="weak",
+                                                  n_chain=local_chains(args, 1)[0], steps=k_leg),
+                           ctx, full=False)  # fmt: skip
+            if rank == 0:
+                line["weak"] = {k: weak[k] for k in ("value", "unit", "ms_per_step", "e2e",
+                                                     "config", "roofline")}  # fmt: skip
+        legs = {}
+        for wl in ("toy", "fn", "hh"):
+            if wl == args.workload:
+                continue
+            a = with_workload_defaults(args, wl, n_chain=0, n_step=0, step_size=0.0,
+                                       steps=k_leg, scaling="strong")
+            leg = measure(a, ctx, full=False)
+            if rank == 0:
+                legs[wl] = leg
+        if rank == 0:
+            line["legs"] = legs
+    if rank == 0:
+        emit(line)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def measure(args, ctx, full):
+    """One workload on this process's GPU (all ranks call it together): device-timed value,
+    the one-step-per-launch HBM view, end to end through the host-buffer entry point, the
+    CPU oracle on rank 0; `full` adds the ESS legs.  Returns the JSON object on rank 0."""
+    import torch
+    import torch.distributed as dist
+
+    import manifold_lifting_b200 as mlb
+    from manifold_lifting_b200 import _lib, flops
+
+    rank, world, local = ctx["rank"], ctx["world"], ctx["local"]
 
     def barrier():
         torch.cuda.synchronize()
@@ -471,8 +551,10 @@ def run_mlb(args, emit):
             dist.barrier()
             torch.cuda.synchronize()
 
-    n, n_step, K, W = args.n_chain, args.n_step, args.steps, max(args.warmup, 3)
+    n, total = local_chains(args, world)
+    n_step, K, W = args.n_step, args.steps, max(args.warmup, 3)
     data, q_host, p_host = make_inputs(args, n, rank * n)
+    y_obs = consts = None
     if args.workload == "hier":
         model = mlb.models.EightSchoolsModel(*data)
         system = mlb.HierarchicalLatentVariableModelSystem(model, model.data, model.dim_u)
@@ -581,6 +663,7 @@ def run_mlb(args, emit):
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    line = None
     if rank == 0:
         total_ms, e2e_time, ms1_mean = (float(x) for x in red)
         steps_all, e2e_all, done1_all = (float(x) for x in tot)
@@ -612,18 +695,15 @@ def run_mlb(args, emit):
         line = {
             "metric": "constrained leapfrog steps/s (all chains)", "value": value,
             "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {
-                "workload": workload_name(args), "n_step": n_step,
-                "step_size": args.step_size, "solver": args.solver,
-                "constraint_tol": 1e-9, "position_tol": 1e-8, "reverse_check_tol": 2e-8,
-                "chains_total": n * world, "mean_projection_iters_per_step": mean_iters,
-                "cpus_bound_per_rank": bound_cpus or None,
+            "config": workload_config(args, world),
+            "measured": {
+                "mean_projection_iters_per_step": mean_iters,
                 "failed_chain_fraction": failed,
-                "timing": "sum of per-step CUDA-event intervals on the launch stream; "
-                          "state reset and L2 flushed (256 MiB memset) between steps, "
-                          "outside the intervals; max over ranks",
+                "cpus_bound_per_rank": ctx["bound_cpus"] or None,
+                "timing": "sum of per-step CUDA-event intervals on the launch stream, max "
+                          "over ranks",
             },
             "roofline": {
                 "bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
@@ -632,6 +712,7 @@ def run_mlb(args, emit):
                 "traffic_source": traffic.get("source"),
                 "kernel": kernel_name,
                 "algorithmic_flops_per_chain_step": flops_step,
+                "chains_this_gpu": n,
                 "peak_source": "DFMA-loop microbenchmark run live in this process "
                                "(MEASURED_PEAKS.json has no fp64 entry)",
             },
@@ -645,22 +726,25 @@ def run_mlb(args, emit):
             "e2e": {"value": e2e_all / e2e_time, "unit": "steps/s",
                     "h2d_bytes_per_step": 2 * n * Q * 8,
                     "d2h_bytes_per_step": 2 * n * Q * 8 + 2 * n * 4,
+                    "h2d_gbs_per_rank": 2 * n * Q * 8 / e2e_time / 1e9,
+                    "d2h_gbs_per_rank": (2 * n * Q * 8 + 2 * n * 4) / e2e_time / 1e9,
                     "api": "mlb_leapfrog_steps_host (pinned host [n, Q] buffers in/out)"},
             "gpu_launches": int(launches),
             "clocks": clk,
         }  # fmt: skip
-        if not args.no_cpu_baseline and world == 1:
-            r, cores, desc, secs = cpu_oracle_rate(args, 12.0, args.cpu_sample_chains)
+        if not args.no_cpu_baseline:
+            r, cores, desc, secs = cpu_oracle_rate(args, 12.0 if full else 4.0,
+                                                   args.cpu_sample_chains)  # fmt: skip
             line["cpu_baseline"] = {"value": r, "unit": "steps/s", "cores": cores,
                                     "kind": "port", "sample": desc, "seconds": secs}  # fmt: skip
     ess = {}
-    if not args.no_ess and args.workload in ("hier", "toy"):
+    if full and not args.no_ess and args.workload in ("hier", "toy"):
         for key, nuts in (("ess", True), ("ess_static", False)):
             if args.ess_sampler in ("both", "nuts" if nuts else "static"):
                 ess[key] = ess_leg(args, mlb, model, system, q0, rank, world, n,
                                    with_cpu=not args.no_cpu_baseline and world == 1,
                                    nuts=nuts)  # fmt: skip
-    elif not args.no_ess and args.workload in ("fn", "hh"):
+    elif full and not args.no_ess and args.workload in ("fn", "hh"):
         # static sampler by default; the host-driven dynamic sampler (a transition costs as
         # many lock-step rounds as the largest tree of the batch) with --ess-sampler nuts
         for key, nuts in (("ess", True), ("ess_static", False)):
@@ -673,10 +757,9 @@ def run_mlb(args, emit):
                     else (lambda co: co.OracleModel.hh(y_obs, consts, "normal")))  # fmt: skip
     if rank == 0:
         line.update({k: v for k, v in ess.items() if v is not None})
-        emit(line)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    del q, p, q0, p0, flush, qh, ph
+    torch.cuda.empty_cache()
+    return line
 
 
 # ------------------------------------------------- state-space workload (extra, `--workload sv`)

@@ -78,8 +78,8 @@ struct Blocks {
     for (int i = 0; i < Y; ++i) {
       double dv = FAM == FAM_HIER ? J.dv[i] : 0.0;
       G.d[i] = fma(dv, dv, J.dn[i] * J.dn[i]);
-      G.rd[i] = rcp_fast(G.d[i]);
     }
+    rcp_many<Y>(G.d, G.rd);
     if (DENSE) {
 #pragma unroll
       for (int i = 0; i < Y; ++i)
@@ -141,8 +141,8 @@ struct Blocks {
     for (int i = 0; i < Y; ++i) {
       double dv = FAM == FAM_HIER ? Jl.dv[i] * Jr.dv[i] : 0.0;
       dprod[i] = fma(Jl.dn[i], Jr.dn[i], dv);
-      rd[i] = rcp_fast(dprod[i]);
     }
+    rcp_many<Y>(dprod, rd);
     bool ok;
     if (DENSE) {
       double mat[K][K], b[K];

@@ -14,6 +14,9 @@
 #pragma once
 #include "mlb_models.cuh"
 
+#ifndef MLB_FUSE_KICKS
+#define MLB_FUSE_KICKS 1  // one kick + projection at interior step boundaries (see below)
+#endif
 #ifndef MLB_HI_NORM
 #define MLB_HI_NORM 1  // high-word maximum norm in the fused solver loops (0: exact always)
 #endif
@@ -260,6 +263,14 @@ MLB_DEV TrajOut run_trajectory_ev(const typename M::Params& P, double (&qw)[M::Q
   t.h_init = t.h_last = nan("");
   int sub = PROJECT_FIRST ? -1 : 0;
   bool first = true;
+  // Interior step boundaries (kFuseKicks): the closing half kick + projection of step s and
+  // the opening half kick + projection of step s + 1 act at the same point, and the
+  // cotangent projection is linear and idempotent, so P(P(p - dt/2 g) - dt/2 g) =
+  // P(p - dt g): one kick and one projection instead of two (what Mici's integrator does
+  // step by step differs by rounding only).  The committed momentum is then the one BEFORE
+  // the kick (`half_pending`); the failure path finishes the half kick before restoring.
+  constexpr bool kFuseKicks = MLB_FUSE_KICKS && !CHECK_H && !PROJECT_FIRST;
+  bool half_pending = false;
 #pragma unroll
   for (int k = 0; k < Q; ++k) cq[k * kStride] = qw[k], cp[k * kStride] = pw[k];
 #pragma unroll 1
@@ -274,9 +285,15 @@ MLB_DEV TrajOut run_trajectory_ev(const typename M::Params& P, double (&qw)[M::Q
       }
       if (!PROJECT_FIRST && n_step <= 0) break;
     }
-    const bool kick = (sub == 0) || (sub == 2);
+    const bool fuse = kFuseKicks && sub == 2 && t.done + 1 < n_step;
+    if (fuse) {
 #pragma unroll
-    for (int k = 0; k < Q; ++k) pw[k] = kick ? fma(-0.5 * dt, C.g[k], pw[k]) : pw[k];
+      for (int k = 0; k < Q; ++k) cq[k * kStride] = qw[k], cp[k * kStride] = pw[k];
+      half_pending = true;
+    }
+    const double kick = fuse ? -dt : ((sub == 0) || (sub == 2)) ? -0.5 * dt : 0.0;
+#pragma unroll
+    for (int k = 0; k < Q; ++k) pw[k] = kick != 0.0 ? fma(kick, C.g[k], pw[k]) : pw[k];
     B::project_cotangent(C.J, C.G, pw);
     if (PROJECT_FIRST && sub == -1) {
       t.h_init = t.h_last = hamiltonian<M>(C, pw);
@@ -286,9 +303,13 @@ MLB_DEV TrajOut run_trajectory_ev(const typename M::Params& P, double (&qw)[M::Q
       sub = 0;
       continue;
     }
-    if (sub == 2) {  // step complete: commit
+    if (fuse) {  // step complete and the next one already opened
+      t.done += 1;
+      sub = 0;
+    } else if (sub == 2) {  // step complete: commit
 #pragma unroll
       for (int k = 0; k < Q; ++k) cq[k * kStride] = qw[k], cp[k * kStride] = pw[k];
+      half_pending = false;
       t.h_last = hamiltonian<M>(C, pw);
       t.done += 1;
       if (CHECK_H && fabs(t.h_last - t.h_init) > max_delta_h) {
@@ -343,6 +364,13 @@ MLB_DEV TrajOut run_trajectory_ev(const typename M::Params& P, double (&qw)[M::Q
     // a failed step leaves the chain at its last committed state
 #pragma unroll
     for (int k = 0; k < Q; ++k) qw[k] = cq[k * kStride], pw[k] = cp[k * kStride];
+    if (kFuseKicks && half_pending) {  // finish the committed step's closing half kick
+      evaluate_at<M>(P, qw, C);
+#pragma unroll
+      for (int k = 0; k < Q; ++k) pw[k] = fma(-0.5 * dt, C.g[k], pw[k]);
+      B::project_cotangent(C.J, C.G, pw);
+      t.h_last = hamiltonian<M>(C, pw);
+    }
   }
   return t;
 }

@@ -35,6 +35,32 @@ MLB_DEV double rcp_fast(double x) {
   return fma(y, e, y);
 }
 
+// Reciprocals of N values with one hardware reciprocal per group of four (Montgomery's
+// trick: 1/a = (bcd) / (abcd)): 9 multiplications + one refined reciprocal per group instead
+// of four refined reciprocals (20 instructions, four MUFU).  Each result carries ~3 roundings
+// instead of one; the product of a group must stay inside the fp64 range (callers pass
+// values whose fourth power is finite; otherwise the group comes out NaN and the chain is
+// flagged like any other non-finite solve).
+#ifndef MLB_RCP_BATCH
+#define MLB_RCP_BATCH 0
+#endif
+template <int N>
+MLB_DEV void rcp_many(const double (&x)[N], double (&r)[N]) {
+  if (MLB_RCP_BATCH && N % 4 == 0) {
+#pragma unroll
+    for (int g = 0; g < N; g += 4) {
+      const double ab = x[g] * x[g + 1], cd = x[g + 2] * x[g + 3];
+      const double inv = rcp_fast(ab * cd);
+      const double rab = inv * cd, rcd = inv * ab;
+      r[g] = rab * x[g + 1], r[g + 1] = rab * x[g];
+      r[g + 2] = rcd * x[g + 3], r[g + 3] = rcd * x[g + 2];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) r[i] = rcp_fast(x[i]);
+  }
+}
+
 // s > 0: returns sqrt(s), writes 1 / sqrt(s)
 MLB_DEV double sqrt_rsqrt_fast(double s, double& rs) {
   double r;

