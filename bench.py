@@ -70,7 +70,7 @@ def with_workload_defaults(a, wl, **override):
     """Copy of the arguments with the per-workload defaults filled in (BASELINE configs)."""
     a = argparse.Namespace(**{**vars(a), "workload": wl, **override})
     a.n_chain = a.n_chain or {"fn": 16384, "hh": 8192, "sv": 16384}.get(wl, 65536)
-    a.n_step = a.n_step or {"fn": 2, "hh": 1}.get(wl, 32)
+    a.n_step = a.n_step or {"fn": 4, "hh": 4}.get(wl, 32)
     a.step_size = a.step_size or {"fn": 0.01, "hh": 0.002, "sv": 0.02}.get(wl, 0.1)
     return a
 

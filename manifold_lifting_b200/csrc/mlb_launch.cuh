@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "mlb_chmc.cuh"
+#include "mlb_hier_lean.cuh"
 
 namespace mlb { struct ModelOps; }
 
@@ -304,6 +305,29 @@ __global__ void __launch_bounds__(kBlock, MLB_LF_MIN_BLOCKS)
   if (h_final) h_final[i] = t.h_last;
 }
 
+// Shared-memory-parked form of k_leapfrog_steps (mlb_hier_lean.cuh): same device functions,
+// 128 registers, 7 CTAs per SM.  Used when it turns two waves of the register-resident
+// kernel into one (see Launch::steps).
+template <class M, int SOLVER>
+__global__ void __maxnreg__(128)
+    k_leapfrog_steps_lean(const __grid_constant__ typename M::Params P, int64_t n, int64_t es,
+                          int64_t cs, double* q, double* p, double dt, const double* dt_pc,
+                          int n_step, Opts o, int32_t* status, int32_t* n_done,
+                          int32_t* iters_fwd, int32_t* iters_rev, double* h_init,
+                          double* h_final) {
+  extern __shared__ double lean_columns[];  // [LeanCol::ROWS][kBlock]
+  MLB_CHAIN_INDEX();
+  const LeanCol<M, kBlock> S{lean_columns + threadIdx.x};
+  const TrajOut t = run_trajectory_lean<M, SOLVER, kBlock>(
+      P, S, q + i * cs, p + i * cs, es, n_step, dt_pc ? dt_pc[i] : dt, o);
+  status[i] = t.status;
+  if (n_done) n_done[i] = t.done;
+  if (iters_fwd) iters_fwd[i] = t.it_fwd;
+  if (iters_rev) iters_rev[i] = t.it_rev;
+  if (h_init) h_init[i] = t.h_init;
+  if (h_final) h_final[i] = t.h_last;
+}
+
 struct SampleArgs {
   double dt, max_delta_h;
   int n_step, n_iter, trace_every, trace_dim;
@@ -520,6 +544,17 @@ int dispatch_solver(int solver, F&& f) {
 template <class M>
 struct Launch {
   static auto P(const mlb_model* m) { return ParamsOf<M>::make(m); }
+  // hierarchical Woodbury models whose parked column leaves room for 7 CTAs per SM
+  static constexpr bool kHasLean = M::B::FAM == FAM_HIER && !M::B::DENSE && M::Y <= 8;
+  static int64_t sm_count() {
+    static const int v = [] {
+      int dev = 0, n = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+      return n > 0 ? n : 148;
+    }();
+    return v;
+  }
   static int constr(const mlb_model* m, int64_t n, int64_t ld, const double* q, double* c,
                     cudaStream_t s) {
     k_constr<M><<<grid_for(n), kBlock, 0, s>>>(P(m), n, ld, q, c);
@@ -578,9 +613,32 @@ struct Launch {
   static int steps(const mlb_model* m, int solver, int64_t n, int64_t ld, const Opts& o,
                    const StepsIO& io, cudaStream_t s) {
     return dispatch_solver(solver, [&]<int S>() {
+      const int64_t es = io.row_major ? 1 : ld, cs = io.row_major ? (int64_t)M::Q : 1;
+      if constexpr (kHasLean) {
+        // the parked form holds 7 CTAs per SM against 4: taken when the batch is more than
+        // one wave of the register-resident kernel but fits one wave of the parked one
+        // (65,536 chains on 148 SMs: 0.600 -> 0.568 ms; at other sizes it is slower,
+        // profiles/r4k_exp_lean.txt)
+        const int64_t sms = sm_count();
+        if (n > sms * 4 * kBlock && n <= sms * 7 * kBlock && S <= MLB_SOLVER_NEWTON_LS) {
+          constexpr int smem = (int)sizeof(double) * LeanCol<M, kBlock>::ROWS * kBlock;
+          static const bool configured = [] {
+            cudaFuncSetAttribute(k_leapfrog_steps_lean<M, S>,
+                                 cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            return cudaFuncSetAttribute(k_leapfrog_steps_lean<M, S>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        smem) == cudaSuccess;
+          }();
+          if (configured) {
+            k_leapfrog_steps_lean<M, S><<<grid_for(n), kBlock, smem, s>>>(
+                P(m), n, es, cs, io.q, io.p, io.dt, io.dt_pc, io.n_step, o, io.status, io.n_done,
+                io.iters_fwd, io.iters_rev, io.h_init, io.h_final);
+            return finish_launch();
+          }
+        }
+      }
       k_leapfrog_steps<M, S><<<grid_for(n), kBlock, 0, s>>>(
-          P(m), n, io.row_major ? 1 : ld, io.row_major ? (int64_t)M::Q : 1, io.q, io.p, io.dt,
-          io.dt_pc, io.n_step, o, io.status, io.n_done,
+          P(m), n, es, cs, io.q, io.p, io.dt, io.dt_pc, io.n_step, o, io.status, io.n_done,
           io.iters_fwd, io.iters_rev, io.h_init, io.h_final);
       return finish_launch();
     });

@@ -20,11 +20,19 @@
 
 namespace mlb {
 
+#ifndef MLB_FN_ROLE_DIRS_WIDE
+#define MLB_FN_ROLE_DIRS_WIDE 2
+#endif
+#ifndef MLB_FN_NG_WIDE
+#define MLB_FN_NG_WIDE 6
+#endif
 template <int PARAM>
 struct FnOde {
   static constexpr int U = 9, ND = 8, NPAIR = ND * (ND + 1) / 2, SIGMA = 6;
   static constexpr int NG = 6, PAIRS_PER_GROUP = NPAIR / NG;  // second-order pass split
   static constexpr int ROLE_DIRS = 2, N_ROLE = ND / ROLE_DIRS;  // Jacobian sweep split
+  static constexpr int ROLE_DIRS_WIDE = MLB_FN_ROLE_DIRS_WIDE, WIDE_MIN_CHAINS = 8192;
+  static constexpr int NG_WIDE = MLB_FN_NG_WIDE;
   static constexpr int GATE_WARPS = 1;  // no cooperative sweep: the RK4 stages are short
   template <int NS1, int NP>
   static constexpr int xch_doubles() { return 0; }

@@ -34,12 +34,27 @@ enum {
 };
 static_assert(HH_NCONST <= kOdeConsts, "constants array too small");
 
+#ifndef MLB_HH_ROLE_DIRS
+#define MLB_HH_ROLE_DIRS 1
+#endif
+#ifndef MLB_HH_ROLE_DIRS_WIDE
+#define MLB_HH_ROLE_DIRS_WIDE 3
+#endif
+#ifndef MLB_HH_NG
+#define MLB_HH_NG 7
+#endif
+#ifndef MLB_HH_GATE_WARPS
+#define MLB_HH_GATE_WARPS 4
+#endif
 template <int PARAM>
 struct HhOde {
   static constexpr int U = 7, ND = 6, NPAIR = ND * (ND + 1) / 2, SIGMA = 6;
-  static constexpr int NG = 7, PAIRS_PER_GROUP = NPAIR / NG;
-  static constexpr int ROLE_DIRS = 1, N_ROLE = ND / ROLE_DIRS;  // Jacobian sweep split
-  static constexpr int GATE_WARPS = 4;  // warps sharing one chain batch in a cooperative sweep
+  static constexpr int NG = MLB_HH_NG, PAIRS_PER_GROUP = NPAIR / NG;
+  static constexpr int ROLE_DIRS = MLB_HH_ROLE_DIRS, N_ROLE = ND / ROLE_DIRS;  // Jacobian sweep split
+  // launches of more than WIDE_MIN_CHAINS chains take ROLE_DIRS_WIDE directions per role
+  static constexpr int ROLE_DIRS_WIDE = MLB_HH_ROLE_DIRS_WIDE, WIDE_MIN_CHAINS = 3072;
+  static constexpr int NG_WIDE = 1;  // second-order sweep of a full GPU: all 21 pairs per thread
+  static constexpr int GATE_WARPS = MLB_HH_GATE_WARPS;  // warps sharing one chain batch in a cooperative sweep
   static_assert(NPAIR % NG == 0, "pair groups must be equal-sized");
   static MLB_DEV int dir_u(int d) { return d; }
   static MLB_DEV int u_dir(int a) { return a < ND ? a : -1; }  // inverse (-1: sigma)

@@ -395,10 +395,12 @@ struct Stream {
     }(std::make_integer_sequence<int, M::NG>{});
   }
 
-  template <int G, int GW = 1>
+  // NP pairs per group (default: the model's NG groups; the wide form of the phased driver
+  // takes more pairs per thread, see kp_second_order)
+  template <int G, int GW = 1, int NP = M::PAIRS_PER_GROUP>
   MLB_DEV static void second_order_group(const OdeData& D, const double (&u)[U], const Col& B,
                                          double (&gu)[U], double* xch = nullptr) {
-    constexpr int NP = M::PAIRS_PER_GROUP, P0 = G * NP;
+    constexpr int P0 = G * NP;
     double h[M::ND];
 #pragma unroll
     for (int d = 0; d < M::ND; ++d) h[d] = 0.0;

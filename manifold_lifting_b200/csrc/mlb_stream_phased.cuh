@@ -18,6 +18,8 @@
 //   * arithmetic is that of the monolithic kernel (same device functions), so the two
 //     paths agree bitwise and share the parity tests.
 #pragma once
+#include <cstdlib>
+
 #include "mlb_stream_launch.cuh"
 
 namespace mlb {
@@ -40,9 +42,13 @@ struct PhasedLayout {
   double* base;
   int64_t lds;
   int U, Y, NGND;
-  int64_t rows_main() const { return StreamScratch::rows(U, Y); }
-  int64_t rows_total() const {
-    return rows_main() + NGND + CD_DBL_ROWS + (CT_INT_ROWS + 1) / 2 + 1;
+  __host__ __device__ int64_t rows_main() const { return StreamScratch::rows(U, Y); }
+  // + one row for the list of still-iterating chains (lds int32 used) + one for the counter
+  __host__ __device__ int64_t rows_total() const {
+    return rows_main() + NGND + CD_DBL_ROWS + (CT_INT_ROWS + 1) / 2 + 2;
+  }
+  __host__ __device__ int32_t* list() const {
+    return reinterpret_cast<int32_t*>(base + (rows_total() - 2) * lds);
   }
   __host__ __device__ Phased at(int64_t i) const {
     Phased p;
@@ -83,6 +89,13 @@ MLB_DEV ChunkCtx chunk_ctx(int64_t n, int Y) {
   c.k0 = c.wj * CH;
   c.k1 = c.k0 + CH < Y ? c.k0 + CH : Y;
   if (c.k0 > Y) c.k0 = Y;
+  return c;
+}
+// the same for slot blockIdx.x * 32 + lane of the list of still-iterating chains
+template <int NCH>
+MLB_DEV ChunkCtx chunk_ctx_listed(const int32_t* list, int64_t n_act, int Y) {
+  ChunkCtx c = chunk_ctx<NCH>(n_act, Y);
+  c.i = c.in_range ? list[c.i] : 0;
   return c;
 }
 // rows [k0, k1) of the Q position / momentum rows for warp wj of a (32, NCH) CTA
@@ -150,6 +163,45 @@ MLB_DEV void cta_bcast_from_warp0(double (&v)[R], double* sh) {
   if (i >= n) return;                                               \
   const Phased P = L.at(i)
 
+// thread -> chain through the list of still-iterating chains (solver-loop kernels)
+#define MLB_PH_INDEX_LISTED()                                        \
+  const int64_t t_ = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; \
+  if (t_ >= n_act) return;                                           \
+  const int64_t i = L.list()[t_];                                    \
+  const Phased P = L.at(i)
+
+// Compaction of the still-iterating chains (CT_ACTIVE != 0) into L.list(), ascending, and
+// their number into *counter: the sweeps of the solver loop are launched over that list
+// only, so their cost follows the number of chains that still iterate instead of the
+// slowest chain of the batch (Newton iteration counts of a batch spread from 2 to 12+).
+// One CTA walks the n flags in tiles of 1,024 (ballot + warp totals in shared memory):
+// microseconds against the millisecond sweeps, and the order is deterministic.
+template <class M>
+__global__ void __launch_bounds__(1024) kp_compact(PhasedLayout L, int64_t n, int* counter) {
+  __shared__ int warp_tot[32];
+  __shared__ int base_sh;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int32_t* act = L.at(0).ct + (int64_t)CT_ACTIVE * L.lds;
+  int32_t* list = L.list();
+  if (threadIdx.x == 0) base_sh = 0;
+  __syncthreads();
+  for (int64_t t0 = 0; t0 < n; t0 += 1024) {
+    const int64_t i = t0 + threadIdx.x;
+    const bool f = i < n && act[i] != 0;
+    const unsigned b = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) warp_tot[w] = __popc(b);
+    __syncthreads();
+    int before = 0;
+    for (int k = 0; k < w; ++k) before += warp_tot[k];
+    const int base = base_sh;
+    if (f) list[base + before + __popc(b & ((1u << lane) - 1u))] = (int32_t)i;
+    __syncthreads();
+    if (threadIdx.x == 1023) base_sh = base + before + __popc(b);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *counter = base_sh;
+}
+
 template <class M, int NCH>
 __global__ void __launch_bounds__(32 * NCH)
     kp_begin(PhasedLayout L, int64_t n, int64_t ld, const double* q, const double* p,
@@ -175,30 +227,67 @@ __global__ void __launch_bounds__(32 * NCH)
 // trial qs) and the destination blocks (Jc at an evaluation, Jt inside Newton).
 // (blockDim.y = M::GATE_WARPS warps share the chain batch of a cooperative sweep; the
 // lanes that leave early are the same in each of them, so the barriers stay consistent)
-template <class M, bool EVAL>
+template <class M, bool EVAL, int R>
 __global__ void __launch_bounds__(kStreamBlock * M::GATE_WARPS)
     kp_jacob(const __grid_constant__ OdeData D, PhasedLayout L, int64_t n, int64_t ld,
              const double* q) {
   extern __shared__ double xch[];
-  MLB_PH_INDEX();
+  // n: chains of the batch (EVAL) / length of the list of still-iterating chains
+  const int64_t t_ = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t_ >= n) return;
+  const int64_t i = EVAL ? t_ : (int64_t)L.list()[t_];
+  const Phased P = L.at(i);
   if (!P.I(EVAL ? CT_ALIVE : CT_ACTIVE, i)) return;
   const Col src = EVAL ? col(q, ld, i) : P.S.qs;
   const Col dst = EVAL ? P.S.Jc : P.S.Jt;
   const Col c = EVAL ? Col{nullptr, 0} : P.S.c;
-  constexpr int R = M::ROLE_DIRS;
+  // R sensitivity directions per role (gridDim.y = ND / R roles)
   [&]<int... K>(std::integer_sequence<int, K...>) {
     ((blockIdx.y == K
           ? Stream<M>::template jacob_role<K * R, R, K == 0, M::GATE_WARPS>(D, src, dst, c, xch)
           : (void)0),
      ...);
-  }(std::make_integer_sequence<int, M::N_ROLE>{});
+  }(std::make_integer_sequence<int, M::ND / R>{});
+}
+
+// Launch of a Jacobian sweep over `cnt` chains.  The split of the ND sensitivity directions
+// over roles trades latency for redundant work (every role re-integrates the state itself):
+// M::ROLE_DIRS directions per role while the launch is small (latency-bound: more, shorter
+// threads), M::ROLE_DIRS_WIDE once it fills the GPU (throughput-bound: fewer copies of the
+// primal recurrence).  Measured on HH (profiles/r4j_hh_variants*.txt): 8,192 chains 107 ->
+// 77 ms per step with 3 directions per role, 1,024 chains 33.5 -> 41 ms.
+// launch size above which the sweeps take their wide form (MLB_WIDE_MIN_CHAINS overrides
+// the model's default: tuning / tests)
+template <class M>
+inline int64_t wide_min_chains() {
+  static const int64_t v = [] {
+    const char* e = std::getenv("MLB_WIDE_MIN_CHAINS");
+    return e ? (int64_t)std::atoll(e) : (int64_t)M::WIDE_MIN_CHAINS;
+  }();
+  return v;
+}
+
+template <class M, bool EVAL>
+int launch_jacob(const OdeData& D, const PhasedLayout& L, int64_t cnt, int64_t ld,
+                 const double* q, cudaStream_t s) {
+  const dim3 sblk(kStreamBlock, M::GATE_WARPS);
+  if (M::ROLE_DIRS_WIDE != M::ROLE_DIRS && cnt > wide_min_chains<M>()) {
+    constexpr int R = M::ROLE_DIRS_WIDE;
+    constexpr size_t sh = sizeof(double) * M::template xch_doubles<R, 0>();
+    kp_jacob<M, EVAL, R><<<dim3(sgrid(cnt), M::ND / R), sblk, sh, s>>>(D, L, cnt, ld, q);
+  } else {
+    constexpr int R = M::ROLE_DIRS;
+    constexpr size_t sh = sizeof(double) * M::template xch_doubles<R, 0>();
+    kp_jacob<M, EVAL, R><<<dim3(sgrid(cnt), M::ND / R), sblk, sh, s>>>(D, L, cnt, ld, q);
+  }
+  return finish_launch();
 }
 
 // residual sweep at the trial position (quasi-Newton)
 template <class M>
 __global__ void __launch_bounds__(kStreamBlock)
-    kp_constr(const __grid_constant__ OdeData D, PhasedLayout L, int64_t n) {
-  MLB_PH_INDEX();
+    kp_constr(const __grid_constant__ OdeData D, PhasedLayout L, int64_t n_act) {
+  MLB_PH_INDEX_LISTED();
   if (!P.I(CT_ACTIVE, i)) return;
   double u[M::U];
   Stream<M>::load_u(P.S.qs, u);
@@ -328,24 +417,44 @@ __global__ void __launch_bounds__(32 * NCH)
 // second-order sweep, one pair group per blockIdx.y; partial gradients to hpart
 // (not cooperative: with ten doubles per gating variable to exchange and the potential's
 // jet arithmetic repeated in every warp, four gate warps measured 4.8 ms against 3.1 ms)
-template <class M>
+template <class M, int NGX>
 __global__ void __launch_bounds__(kStreamBlock)
     kp_second_order(const __grid_constant__ OdeData D, PhasedLayout L, int64_t n, int64_t ld,
                     const double* q) {
   MLB_PH_INDEX();
   if (!P.I(CT_ALIVE, i)) return;
   constexpr int U = M::U;
+  static_assert(M::NPAIR % NGX == 0 && NGX <= M::NG, "pair groups must be equal-sized");
   double u[U], h[U];
   Stream<M>::load_u(col(q, ld, i), u);
 #pragma unroll
   for (int a = 0; a < U; ++a) h[a] = 0.0;
+  // NGX groups of NPAIR / NGX pairs (gridDim.y = NGX)
   [&]<int... G>(std::integer_sequence<int, G...>) {
     ((blockIdx.y == G
-          ? Stream<M>::template second_order_group<G>(D, u, P.S.Jt, h) : (void)0),
+          ? Stream<M>::template second_order_group<G, 1, M::NPAIR / NGX>(D, u, P.S.Jt, h)
+          : (void)0),
      ...);
-  }(std::make_integer_sequence<int, M::NG>{});
+  }(std::make_integer_sequence<int, NGX>{});
 #pragma unroll
   for (int d = 0; d < M::ND; ++d) P.hpart[(int)blockIdx.y * M::ND + d] = h[M::dir_u(d)];
+  if (NGX < M::NG && blockIdx.y == 0) {  // the consumer adds up all M::NG partials
+    for (int k = NGX * M::ND; k < M::NG * M::ND; ++k) P.hpart[k] = 0.0;
+  }
+}
+
+// Second-order sweep over the batch: M::NG pair groups (one thread each) for a small batch,
+// M::NG_WIDE for one that fills the GPU (every group re-integrates the state and all first-
+// order sensitivities, so fewer groups = less redundant work, more latency per thread).
+template <class M>
+int launch_second_order(const OdeData& D, const PhasedLayout& L, int64_t n, int64_t ld,
+                        const double* q, cudaStream_t s) {
+  if (M::NG_WIDE != M::NG && n > wide_min_chains<M>()) {
+    kp_second_order<M, M::NG_WIDE><<<dim3(sgrid(n), M::NG_WIDE), kStreamBlock, 0, s>>>(D, L, n, ld, q);
+  } else {
+    kp_second_order<M, M::NG><<<dim3(sgrid(n), M::NG), kStreamBlock, 0, s>>>(D, L, n, ld, q);
+  }
+  return finish_launch();
 }
 
 // [finish a fresh evaluation: add the second-order partials] [half kick] cotangent
@@ -460,14 +569,13 @@ __global__ void __launch_bounds__(32 * NCH)
 template <class M, int NCH>
 __global__ void __launch_bounds__(32 * NCH)
     kp_solve_begin(PhasedLayout L, int64_t n, int64_t ld, const double* q, const double* p,
-                   double dt, const double* dt_pc, double sign, int max_iters, int* counter) {
+                   double dt, const double* dt_pc, double sign, int max_iters) {
   MLB_PH_INDEX();
   const int alive = P.I(CT_ALIVE, i);  // (not written by this kernel)
   const bool go = alive && max_iters > 0;
   if (threadIdx.y == 0) {
     P.I(CT_ACTIVE, i) = go, P.I(CT_ITERS, i) = 0, P.I(CT_NCONSTR, i) = 0;
     P.Dv(CD_NDQ, i) = INFINITY, P.Dv(CD_ERR, i) = -1.0;
-    if (go) atomicAdd(counter, 1);
   }
   if (!alive) return;
   const int Q = L.U + L.Y;
@@ -484,15 +592,15 @@ __global__ void __launch_bounds__(32 * NCH)
 // observation-chunked
 template <class M, int SOLVER, int NCH>
 __global__ void __launch_bounds__(32 * NCH)
-    kp_update(PhasedLayout L, int64_t n, Opts o, int* counter) {
+    kp_update(PhasedLayout L, int64_t n_act, Opts o) {
   using S = Stream<M>;
   constexpr int U = M::U;
   constexpr bool QN = SOLVER == MLB_SOLVER_QUASI_NEWTON;
   constexpr int NA = QN ? U : U * U + U;  // [mat U x U,] rhs U
   extern __shared__ double sh[];
   const int Y = L.Y;
-  const ChunkCtx cx = chunk_ctx<NCH>(n, Y);
-  const int64_t i = cx.in_range ? cx.i : 0;
+  const ChunkCtx cx = chunk_ctx_listed<NCH>(L.list(), n_act, Y);
+  const int64_t i = cx.i;
   const Phased P = L.at(i);
   const bool live = cx.in_range && P.I(CT_ACTIVE, i);
   const Col q = P.S.qs, mu = P.S.mu, c = P.S.c, jp = P.S.Jc;
@@ -578,9 +686,7 @@ __global__ void __launch_bounds__(32 * NCH)
     const double ndq = norm_finish(nacc, o.norm), err = norm_finish(eacc, o.norm);
     const int iters = P.I(CT_ITERS, i) + 1;
     P.I(CT_ITERS, i) = iters, P.Dv(CD_NDQ, i) = ndq, P.Dv(CD_ERR, i) = err;
-    const bool again = keep_iterating(iters, ndq, err, o);
-    P.I(CT_ACTIVE, i) = again;
-    if (again) atomicAdd(counter, 1);
+    P.I(CT_ACTIVE, i) = keep_iterating(iters, ndq, err, o);
   }
 }
 
@@ -666,9 +772,7 @@ int phased_leapfrog_steps(const mlb_model* m, const OdeData& D, int64_t n, int64
     return MLB_ERR_CUDA;
   }
   int* host_count = m->pinned_word;
-  const dim3 blk(kStreamBlock), g1(sgrid(n)), g_role(sgrid(n), M::N_ROLE), g_grp(sgrid(n), M::NG);
-  const dim3 sblk(kStreamBlock, M::GATE_WARPS);  // cooperative sweeps
-  constexpr size_t sh_jac = sizeof(double) * M::template xch_doubles<M::ROLE_DIRS, 0>();
+  const dim3 blk(kStreamBlock), g1(sgrid(n));
   constexpr int NCH = kChunkWarps;
   const dim3 cblk(32, NCH);
   // dynamic shared memory of the chunked kernels: [rows][32] doubles
@@ -694,9 +798,9 @@ int phased_leapfrog_steps(const mlb_model* m, const OdeData& D, int64_t n, int64
     for (int sub = 0; sub < 3; ++sub) {
       const bool fresh = first || sub == 1;
       if (fresh) {  // evaluate at the working position
-        MLB_KP((kp_jacob<M, true><<<g_role, sblk, sh_jac, s>>>(D, L, n, ld, io.q)));
+        if ((rc = launch_jacob<M, true>(D, L, n, ld, io.q, s)) != MLB_OK) return rc;
         MLB_KP((kp_eval_mid<M, NCH><<<g1, cblk, sh_eval, s>>>(D, L, n, ld, io.q, io.p)));
-        MLB_KP((kp_second_order<M><<<g_grp, blk, 0, s>>>(D, L, n, ld, io.q)));
+        if ((rc = launch_second_order<M>(D, L, n, ld, io.q, s)) != MLB_OK) return rc;
       }
       bool fresh_g = fresh;  // the second-order partials are added to the gradient once
       if (first && io.project_first) {  // momentum refresh: project, then h_init
@@ -719,14 +823,17 @@ int phased_leapfrog_steps(const mlb_model* m, const OdeData& D, int64_t n, int64
       if (sub == 2) break;
       const double sign = sub == 0 ? 1.0 : -1.0;
       MLB_KP((kp_solve_begin<M, NCH><<<g1, cblk, 0, s>>>(L, n, ld, io.q, io.p, io.dt, io.dt_pc, sign,
-                                                   o.max_iters, counter)));
+                                                   o.max_iters)));
+      MLB_KP((kp_compact<M><<<1, 1024, 0, s>>>(L, n, counter)));
       int active = read_counter();
-      while (active > 0) {
+      while (active > 0) {  // sweeps over the still-iterating chains only
+        const dim3 ga(sgrid(active));
         if (SOLVER == MLB_SOLVER_QUASI_NEWTON)
-          MLB_KP((kp_constr<M><<<g1, blk, 0, s>>>(D, L, n)));
+          MLB_KP((kp_constr<M><<<ga, blk, 0, s>>>(D, L, active)));
         else
-          MLB_KP((kp_jacob<M, false><<<g_role, sblk, sh_jac, s>>>(D, L, n, ld, io.q)));
-        MLB_KP((kp_update<M, SOLVER, NCH><<<g1, cblk, sh_upd, s>>>(L, n, o, counter)));
+          { if ((rc = launch_jacob<M, false>(D, L, active, ld, io.q, s)) != MLB_OK) return rc; }
+        MLB_KP((kp_update<M, SOLVER, NCH><<<ga, cblk, sh_upd, s>>>(L, active, o)));
+        MLB_KP((kp_compact<M><<<1, 1024, 0, s>>>(L, n, counter)));
         active = read_counter();
       }
       if (active < 0) {

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../manifold_lifting_b200/csrc/mlb_chmc.cuh"
+#include "../manifold_lifting_b200/csrc/mlb_hier_lean.cuh"
 
 #ifndef KBLOCK
 #define KBLOCK 64
@@ -45,6 +46,22 @@ __global__ void __launch_bounds__(KBLOCK, MINB)
       P, qv, pv, &commit[0][threadIdx.x], &commit[Q][threadIdx.x], n_step, dt, o, 0.0);
 #pragma unroll
   for (int k = 0; k < Q; ++k) q[k * ld + i] = qv[k], p[k * ld + i] = pv[k];
+  status[i] = r.status, n_done[i] = r.done, itf[i] = r.it_fwd, itr[i] = r.it_rev;
+}
+
+#ifndef LEANREG
+#define LEANREG 144
+#endif
+__global__ void __maxnreg__(LEANREG)
+    k_lean(const __grid_constant__ M::Params P, int64_t n, int64_t ld, double* q, double* p,
+           double dt, int n_step, Opts o, const int32_t* order, int32_t* status, int32_t* n_done,
+           int32_t* itf, int32_t* itr) {
+  extern __shared__ double lean_sh[];
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int64_t i = order ? order[t] : t;
+  LeanCol<M, KBLOCK> S{lean_sh + threadIdx.x};
+  const TrajOut r = run_trajectory_lean<M, SOLVER, KBLOCK>(P, S, q + i, p + i, ld, n_step, dt, o);
   status[i] = r.status, n_done[i] = r.done, itf[i] = r.it_fwd, itr[i] = r.it_rev;
 }
 
@@ -104,6 +121,12 @@ int main(int argc, char** argv) {
   char* flush;
   CK(cudaMalloc(&flush, 256 << 20));
   const unsigned grid = (unsigned)((n + KBLOCK - 1) / KBLOCK);
+#ifdef LEAN
+  CK(cudaFuncSetAttribute(k_lean, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  CK(cudaFuncSetAttribute(k_lean, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)(sizeof(double) * LeanCol<M, KBLOCK>::ROWS * KBLOCK)));
+  { int nb = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_lean, KBLOCK, sizeof(double) * LeanCol<M, KBLOCK>::ROWS * KBLOCK); printf("lean occupancy: %d CTAs/SM\n", nb); }
+#endif
   auto launch = [&](const double* psrc, const int32_t* ord) {
     CK(cudaMemcpy(dq, dq0, bytes, cudaMemcpyDeviceToDevice));
     CK(cudaMemcpy(dp, psrc, bytes, cudaMemcpyDeviceToDevice));
@@ -111,7 +134,12 @@ int main(int argc, char** argv) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0), cudaEventCreate(&e1);
     cudaEventRecord(e0);
+#ifdef LEAN
+    k_lean<<<grid, KBLOCK, sizeof(double) * LeanCol<M, KBLOCK>::ROWS * KBLOCK>>>(
+        P, n, ld, dq, dp, dt, n_step, o, ord, st, nd, itf, itr);
+#else
     k_lf<<<grid, KBLOCK>>>(P, n, ld, dq, dp, dt, n_step, o, ord, st, nd, itf, itr);
+#endif
     cudaEventRecord(e1);
     CK(cudaDeviceSynchronize());
     float ms;
@@ -147,7 +175,11 @@ int main(int argc, char** argv) {
   for (int64_t i = 0; i < n; ++i) its += hf[i] + hr[i], done += hd[i], fail += hs[i] != 0;
   for (size_t k = 0; k < q.size(); ++k) cs += q[k], cp += p[k];
   cudaFuncAttributes fa;
+#ifdef LEAN
+  cudaFuncGetAttributes(&fa, k_lean);
+#else
   cudaFuncGetAttributes(&fa, k_lf);
+#endif
   printf("n=%lld n_step=%d order=%d kblock=%d regs=%d local=%zuB | mean %.4f ms best %.4f ms | "
          "%.3e steps/s | iters/step %.3f failed %lld | checksum q %.10e p %.10e\n",
          (long long)n, n_step, order_mode, KBLOCK, fa.numRegs, fa.localSizeBytes, tot / reps, best,

@@ -348,8 +348,12 @@ def test_host_buffer_entry_point_chunk_pipeline():
         assert (i32[0] == cpu(dev.status)).all() and (i32[1] == cpu(dev.n_done)).all()
         assert (i32[2] == cpu(dev.iters_fwd)).all() and (i32[3] == cpu(dev.iters_rev)).all()
         assert np.array_equal(qh, cpu(dev.pos)) and np.array_equal(ph, cpu(dev.mom))
-        assert np.array_equal(f64[0], cpu(dev.h_init))
-        assert np.array_equal(f64[1], cpu(dev.h_final), equal_nan=True)
+        # positions / momenta / counts are bit-identical; the Hamiltonians come from two
+        # kernels (the 40,000-chain device call takes the shared-memory-parked form, the
+        # 16,384-chain chunks the register-resident one) whose compilers fuse the final
+        # nld + log det + |p|^2 / 2 additions differently: last-bit agreement
+        assert np.allclose(f64[0], cpu(dev.h_init), rtol=1e-14, atol=0)
+        assert np.allclose(f64[1], cpu(dev.h_final), rtol=1e-14, atol=0, equal_nan=True)
 
 
 def test_full_size_properties_65536_chains():
