@@ -82,12 +82,63 @@ class DualAveragingStepSizeAdapter:
         return _lib.AdaptOpts(self.adapt_stat_target, self.log_step_size_reg_coefficient,
                               self.iter_decay_coeff, self.iter_offset)  # fmt: skip
 
+    max_init_step_size_iters = 100
+
+    def find_init_step_size(self, chain_state, system, integrator, rng=None):
+        """Mici 0.2.1 `DualAveragingStepSizeAdapter._find_and_set_init_step_size`, run for
+        every chain at once (the reference harness constructs the integrator without a
+        step size, example_models/utils.py:317-327, and relies on this search): start from
+        step size 1, take ONE step from the initial state, and halve (if
+        |h_init - h(step)| > log 2, is NaN or the step raised an integrator error) or
+        double the step size until the comparison with log 2 flips.  Returns the per-chain
+        step sizes [n_chain]; chains that never flip within `max_init_step_size_iters`
+        raise `AdaptationError` as Mici does."""
+        from .errors import AdaptationError
+
+        state = chain_state.copy()
+        if getattr(state, "mom", None) is None:
+            gen = rng if rng is not None else torch.Generator(device="cuda").manual_seed(0)
+            state.mom = system.sample_momentum(state, gen)
+        n = state.n_chain
+        eps = torch.ones(n, dtype=torch.float64, device="cuda")
+        too_big = torch.zeros(n, dtype=torch.bool, device="cuda")
+        done = torch.zeros(n, dtype=torch.bool, device="cuda")
+        log2 = math.log(2.0)
+        for s in range(self.max_init_step_size_iters):
+            out = integrator.steps(state, 1, step_size=eps, raise_on_failure=False)
+            if s == 0 and bool(torch.isnan(out.h_init).any()):
+                raise AdaptationError("Hamiltonian evaluating to NaN at initial state.")
+            failed = out.status != 0
+            delta_h = (out.h_init - out.h_final).abs()
+            nan = torch.isnan(delta_h) & ~failed
+            over = delta_h > log2
+            if s == 0:
+                too_big = nan | over
+            too_big = torch.where(nan | failed, torch.ones_like(too_big), too_big)
+            flipped = ~failed & ~nan & ((too_big & ~over) | (~too_big & over))
+            done |= flipped
+            if bool(done.all()):
+                return eps
+            scale = torch.where(too_big, 0.5, 2.0).to(torch.float64)
+            eps = torch.where(done, eps, eps * scale)
+        raise AdaptationError(
+            f"Could not find reasonable initial step size in {self.max_init_step_size_iters} "
+            f"iterations for {int((~done).sum())} of {n} chains. A very large final step "
+            "size may indicate that the target distribution is improper.")
+
     def initialize(self, chain_state, transition):
         n = chain_state.n_chain
-        eps = float(transition.integrator.step_size)
+        integrator = transition.integrator
         a = torch.zeros(_lib.ADAPT_ROWS, n, dtype=torch.float64, device="cuda")
-        a[3] = math.log(10 * eps)
-        a[4] = eps
+        if integrator.step_size is None:
+            eps = self.find_init_step_size(chain_state, transition.system, integrator)
+            integrator.step_size = float(eps.mean())
+            a[3] = torch.log(10 * eps)
+            a[4] = eps
+        else:
+            eps = float(integrator.step_size_scalar())
+            a[3] = math.log(10 * eps)
+            a[4] = eps
         return a
 
     def finalize(self, adapt_state, chain_states, transition, rngs=None):

@@ -200,14 +200,20 @@ struct Eval {
   double nld, logdet;
 };
 
+// want_val = false skips the VALUES of the log-determinant and of the prior density (dim_y / 2
+// + 2 fp64 logarithms for the Woodbury family: measured 16 % of a 32-step eight-schools
+// launch, profiles/r5b_h_alive.txt); E.nld / E.logdet are then not meaningful.  The
+// leapfrog step itself never reads them (systems.py:394-405 uses dh1_dpos only): only the
+// Hamiltonian at the ends of a trajectory does.
 template <class M>
-MLB_DEV bool evaluate_at(const typename M::Params& P, const double (&q)[M::Q], Eval<M>& E) {
+MLB_DEV bool evaluate_at(const typename M::Params& P, const double (&q)[M::Q], Eval<M>& E,
+                         bool want_val = true) {
   double c[M::Y];
   const typename M::Par par = M::params(q[0], q[1]);  // shared by everything below
   M::jacob(P, q, par, E.J, c);
   M::B::decompose_gram(E.J, E.G);
-  E.logdet = M::B::log_det_sqrt_gram(E.G);
-  E.nld = M::nld(P, q, par, E.g);
+  E.logdet = want_val ? M::B::log_det_sqrt_gram(E.G) : 0.0;
+  E.nld = M::nld(P, q, par, E.g, want_val);
   M::add_grad_logdet(P, q, par, E.J, E.G, E.g);
   return E.G.ok;
 }
@@ -255,7 +261,7 @@ template <class M, int SOLVER, bool PROJECT_FIRST, bool CHECK_H, int kStride>
 MLB_DEV TrajOut run_trajectory_ev(const typename M::Params& P, double (&qw)[M::Q],
                                   double (&pw)[M::Q], double* cq, double* cp, int n_step,
                                   double dt, const Opts& o, double max_delta_h, Eval<M>& C,
-                                  bool have_eval) {
+                                  bool have_eval, bool want_h = true) {
   using B = typename M::B;
   constexpr int Q = M::Q;
   TrajOut t;
@@ -276,7 +282,12 @@ MLB_DEV TrajOut run_trajectory_ev(const typename M::Params& P, double (&qw)[M::Q
 #pragma unroll 1
   for (;;) {
     if (first || sub == 1) {  // trajectory start / new position after the forward solve
-      const bool ok = (first && have_eval) ? C.G.ok : evaluate_at<M>(P, qw, C);
+      // energy values: at the trajectory's first point, at every point when the energy is
+      // tested per step, otherwise at the last point only (interior commits with fused
+      // kicks never form the Hamiltonian)
+      const bool want_val =
+          want_h && (first || CHECK_H || !kFuseKicks || t.done + 1 >= n_step);
+      const bool ok = (first && have_eval) ? C.G.ok : evaluate_at<M>(P, qw, C, want_val);
       if (first && !PROJECT_FIRST) t.h_init = t.h_last = hamiltonian<M>(C, pw);
       first = false;
       if (!ok) {
@@ -378,10 +389,11 @@ MLB_DEV TrajOut run_trajectory_ev(const typename M::Params& P, double (&qw)[M::Q
 template <class M, int SOLVER, bool PROJECT_FIRST, bool CHECK_H, int kStride>
 MLB_DEV TrajOut run_trajectory(const typename M::Params& P, double (&qw)[M::Q],
                                double (&pw)[M::Q], double* cq, double* cp, int n_step,
-                               double dt, const Opts& o, double max_delta_h) {
+                               double dt, const Opts& o, double max_delta_h,
+                               bool want_h = true) {
   Eval<M> C;
   return run_trajectory_ev<M, SOLVER, PROJECT_FIRST, CHECK_H, kStride>(
-      P, qw, pw, cq, cp, n_step, dt, o, max_delta_h, C, false);
+      P, qw, pw, cq, cp, n_step, dt, o, max_delta_h, C, false, want_h);
 }
 
 }  // namespace mlb

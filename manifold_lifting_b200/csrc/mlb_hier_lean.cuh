@@ -63,12 +63,13 @@ struct HierLean {
 
   // evaluation at the parked position: parks tau, dtau, Gram factor, 1 / d and the part of
   // dh1/dq that is not the position itself (d nld / d n_i = n_i); returns nld + log det
-  static MLB_DEV bool evaluate(const typename M::Params& P, C S, double& h1) {
+  static MLB_DEV bool evaluate(const typename M::Params& P, C S, double& h1,
+                               bool want_val = true) {
     double q[Q];
 #pragma unroll
     for (int k = 0; k < Q; ++k) q[k] = S[C::SQ + k];
     Eval<M> E;
-    const bool ok = evaluate_at<M>(P, q, E);
+    const bool ok = evaluate_at<M>(P, q, E, want_val);
     h1 = E.nld + E.logdet;
 #pragma unroll
     for (int k = 0; k < 2 + Y; ++k) S[C::SG + k] = E.g[k];
@@ -110,7 +111,7 @@ struct HierLean {
 template <class M, int SOLVER, int KB>
 MLB_DEV TrajOut run_trajectory_lean(const typename M::Params& P, LeanCol<M, KB> S, double* gq,
                                     double* gp, int64_t es, int n_step, double dt,
-                                    const Opts& o) {
+                                    const Opts& o, bool want_h = true) {
   using H = HierLean<M, SOLVER, KB>;
   using B = typename M::B;
   using C = LeanCol<M, KB>;
@@ -123,7 +124,7 @@ MLB_DEV TrajOut run_trajectory_lean(const typename M::Params& P, LeanCol<M, KB> 
   double h1;
   bool half_pending = false;  // the committed momentum still lacks its closing half kick
   {
-    const bool ok = H::evaluate(P, S, h1);
+    const bool ok = H::evaluate(P, S, h1, want_h);
     double ke = 0.0;
 #pragma unroll
     for (int k = 0; k < Q; ++k) ke = fma(S[C::SP + k], S[C::SP + k], ke);
@@ -134,7 +135,8 @@ MLB_DEV TrajOut run_trajectory_lean(const typename M::Params& P, LeanCol<M, KB> 
   int sub = 0;
   while (t.status == MLB_ST_OK && t.done < n_step) {
     if (sub == 1) {  // new position after the forward solve
-      if (!H::evaluate(P, S, h1)) {
+      // energy values at the last point only (see evaluate_at)
+      if (!H::evaluate(P, S, h1, want_h && (!MLB_FUSE_KICKS || t.done + 1 >= n_step))) {
         t.status = MLB_ST_LINALG;
         break;
       }
@@ -211,7 +213,7 @@ MLB_DEV TrajOut run_trajectory_lean(const typename M::Params& P, LeanCol<M, KB> 
     // the chain stays at its last committed step: finish that step's closing half kick
 #pragma unroll
     for (int k = 0; k < Q; ++k) S[C::SQ + k] = gq[k * es], S[C::SP + k] = gp[k * es];
-    H::evaluate(P, S, h1);
+    H::evaluate(P, S, h1, want_h);
     MLB_LEAN_FENCE();
     const double ke = H::kick_project(P, S, -0.5 * dt);
     t.h_last = h1 + ke;

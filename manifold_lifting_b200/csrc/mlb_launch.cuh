@@ -294,7 +294,8 @@ __global__ void __launch_bounds__(kBlock, MLB_LF_MIN_BLOCKS)
   load_vec<Q>(pv, p, es, cs, i);
   const double dti = dt_pc ? dt_pc[i] : dt;
   const TrajOut t = run_trajectory<M, SOLVER, false, false, kBlock>(
-      P, qv, pv, &commit[0][threadIdx.x], &commit[Q][threadIdx.x], n_step, dti, o, 0.0);
+      P, qv, pv, &commit[0][threadIdx.x], &commit[Q][threadIdx.x], n_step, dti, o, 0.0,
+      h_init != nullptr || h_final != nullptr);
   store_vec<Q>(qv, q, es, cs, i);
   store_vec<Q>(pv, p, es, cs, i);
   status[i] = t.status;
@@ -319,7 +320,8 @@ __global__ void __maxnreg__(128)
   MLB_CHAIN_INDEX();
   const LeanCol<M, kBlock> S{lean_columns + threadIdx.x};
   const TrajOut t = run_trajectory_lean<M, SOLVER, kBlock>(
-      P, S, q + i * cs, p + i * cs, es, n_step, dt_pc ? dt_pc[i] : dt, o);
+      P, S, q + i * cs, p + i * cs, es, n_step, dt_pc ? dt_pc[i] : dt, o,
+      h_init != nullptr || h_final != nullptr);
   status[i] = t.status;
   if (n_done) n_done[i] = t.done;
   if (iters_fwd) iters_fwd[i] = t.it_fwd;

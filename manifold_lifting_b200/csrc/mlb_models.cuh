@@ -40,7 +40,8 @@ struct ToyModel {
                             double (&c)[Y]) {
     jacob(P, q, J, c);
   }
-  static MLB_DEV double nld(const Params&, const double (&q)[Q], const Par&, double (&g)[Q]) {
+  static MLB_DEV double nld(const Params&, const double (&q)[Q], const Par&, double (&g)[Q],
+                            bool = true) {
     g[0] = q[0], g[1] = q[1], g[2] = q[2];
     return 0.5 * (q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
   }
@@ -113,8 +114,10 @@ struct HierModel {
     }
   }
   // extended prior nld (eight_schools.py:49-53) with gradient
+  // want_val = false: gradient only (the value costs a log1p; the fused trajectory needs it
+  // at its first and last point only)
   static MLB_DEV double nld(const Params&, const double (&q)[Q], const Par& p,
-                            double (&g)[Q]) {
+                            double (&g)[Q], bool want_val = true) {
     double val;
     if (PARAM == MLB_PARAM_UNBOUNDED) {
       // normal(0,5) on u0; half-Cauchy(5) pulled back through tau = exp(u1):
@@ -122,7 +125,7 @@ struct HierModel {
       // log(d tau / d u1) = log(exp(u1)) = u1
       double r = p.tau * 0.2, r2 = r * r;
       double s = q[0] * 0.2;
-      val = 0.5 * s * s + log1p(r2) - q[1];
+      val = 0.5 * s * s + (want_val ? log1p(r2) : 0.0) - q[1];
       g[0] = q[0] * 0.04;
       g[1] = fma(2.0 * r2, rcp_fast(1.0 + r2), -1.0);
     } else {

@@ -46,10 +46,15 @@ class StaticMetropolisHMC:
         n = q.shape[0]
         opts = integ.solver_opts()
         pq, ld = p_soa(q, sysm.dim_q)
-        dt = integ.step_size
+        if integ.step_size is None:
+            raise ValueError(
+                "integrator.step_size is None: pass a step size or run a warm-up phase with "
+                "a DualAveragingStepSizeAdapter (which searches for an initial one)")
+        # a per-chain tensor of step sizes enters through its mean, as in the dynamic
+        # sampler (per-chain values only live in the adapter's state during warm-up)
         check(lib().mlb_hmc_sample(
             sysm._h, C.c_int64(n), C.c_int64(ld), pq,
-            C.c_double(float(dt) if not isinstance(dt, torch.Tensor) else 0.0),
+            C.c_double(integ.step_size_scalar()),
             C.c_int32(self.n_step), C.c_int32(n_iter), C.byref(opts),
             C.c_double(self.max_delta_h), C.c_uint64(self.seed), C.c_uint64(chain_offset),
             C.c_uint32(self.iteration), p_vec(mom_noise), p_vec(unif), p_vec(adapt),

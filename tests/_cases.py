@@ -156,3 +156,32 @@ def mc_standard_error(x):
 
 
 __all__ = [n for n in dir() if not n.startswith("__")]
+
+
+def woodbury_projection_truth(dy_du, dy_dn, v, dps=50):
+    """Extended-precision (mpmath, `dps` digits) normal-space component J^T (J J^T)^-1 J v of
+    ONE chain for an additive-noise system, J = [dy_du, diag(dy_dn)] (systems.py:564-654),
+    with the fp64 Jacobian entries taken as exact data.  Returns (truth as float64 [Q],
+    condition number of the capacitance matrix I + A^T D^-1 A)."""
+    import mpmath as mp
+
+    mp.mp.dps = dps
+    Y, U = dy_du.shape
+    A = [[mp.mpf(float(dy_du[i, a])) for a in range(U)] for i in range(Y)]
+    dn = [mp.mpf(float(x)) for x in dy_dn]
+    vu = [mp.mpf(float(x)) for x in v[:U]]
+    vn = [mp.mpf(float(x)) for x in v[U:]]
+    rd = [1 / (d * d) for d in dn]  # D^-1
+    w = [sum(A[i][a] * vu[a] for a in range(U)) + dn[i] * vn[i] for i in range(Y)]  # J v
+    C = mp.matrix(U, U)
+    for a in range(U):
+        for b in range(a, U):
+            s = sum(A[i][a] * rd[i] * A[i][b] for i in range(Y))
+            C[a, b] = C[b, a] = s
+        C[a, a] += 1
+    rhs = mp.matrix([sum(A[i][a] * rd[i] * w[i] for i in range(Y)) for a in range(U)])
+    z = mp.lu_solve(C, rhs)
+    x = [rd[i] * (w[i] - sum(A[i][a] * z[a] for a in range(U))) for i in range(Y)]  # G^-1 J v
+    out = [sum(A[i][a] * x[i] for i in range(Y)) for a in range(U)] + [dn[i] * x[i] for i in range(Y)]
+    Cf = np.array([[float(C[a, b]) for b in range(U)] for a in range(U)])
+    return np.array([float(t) for t in out]), float(np.linalg.cond(Cf))

@@ -197,6 +197,32 @@ def test_fused_leapfrog_steps_match_oracle(kind, par, solver):
         assert rel_err(cpu(out.pos)[bad], ref["q"][bad]) < TOL
 
 
+@pytest.mark.parametrize("kind,par", CASES)
+@pytest.mark.parametrize("n,n_step", [(1025, 3), (40000, 2)])
+def test_steps_without_energy_outputs_are_bitwise_identical(kind, par, n, n_step):
+    """`h_init` / `h_final` not requested (the bench's call): the kernels skip the VALUES of
+    log det / prior density at interior points; positions, momenta, statuses and iteration
+    counts must not move by a bit.  40,000 chains take the shared-memory-parked kernel form
+    for the hierarchical model, 1,025 the register-resident one."""
+    mlb = _mlb()
+    _, _, cm, gm, gs, q = make_case(kind, par, n)
+    p = tangent_momentum(cm, q)
+    integ = mlb.integrators.ConstrainedLeapfrogIntegrator(
+        gs, 0.15, projection_solver=mlb.jitted_solve_projection_onto_manifold_newton,
+        projection_solver_kwargs=dict(constraint_tol=1e-9, position_tol=1e-8, max_iters=50))
+    a = integ.steps(mlb.states.ChainState(q, p), n_step)
+    b = integ.steps(mlb.states.ChainState(q, p), n_step, energies=False)
+    assert b.h_init is None and b.h_final is None
+    assert torch.equal(a.pos, b.pos) and torch.equal(a.mom, b.mom)
+    assert torch.equal(a.status, b.status) and torch.equal(a.n_done, b.n_done)
+    assert torch.equal(a.iters_fwd, b.iters_fwd) and torch.equal(a.iters_rev, b.iters_rev)
+    ok = cpu(a.status) == 0
+    ref = cm.leapfrog_steps(q, p, 0.15, n_step, co.solver_opts(co.SOLVER_NEWTON))
+    both = ok & (ref["status"] == 0)
+    assert rel_err(cpu(a.h_final)[both], ref["h_final"][both]) < TOL
+    assert rel_err(cpu(a.h_init), ref["h_init"]) < TOL
+
+
 @pytest.mark.parametrize("kind,par", [("hier", "unbounded"), ("toy", None)])
 def test_unfused_step_equals_fused_step(kind, par):
     """Driving the system method by method (as Mici does) gives the fused kernel's

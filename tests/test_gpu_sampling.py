@@ -327,3 +327,69 @@ def test_fitzhugh_nagumo_chains_concentrate_on_the_generating_parameters():
     assert abs(gd.mean() - (FN_U_TRUE[2] + FN_U_TRUE[3])) < 0.25, gd.mean()
     # noise scale: log sigma near log 0.1
     assert abs(mean[6] - FN_U_TRUE[6]) < 0.3
+
+
+def test_initial_step_size_search_matches_the_scalar_procedure():
+    """The reference harness builds the integrator WITHOUT a step size
+    (example_models/utils.py:317-327) and Mici's dual-averaging adapter searches for one
+    (start at 1; halve / double until |dh| of one step crosses log 2, integrator errors
+    count as too big).  The batched search must give every chain what that scalar procedure
+    gives when re-enacted with the CPU oracle on the same initial state and momentum, and a
+    warm-up started that way must reach the target accept rate."""
+    import manifold_lifting_b200 as mlb
+
+    model = mlb.models.EightSchoolsModel(EIGHT_SCHOOLS_Y, EIGHT_SCHOOLS_SIGMA)
+    system = mlb.HierarchicalLatentVariableModelSystem(model, model.data, model.dim_u)
+    cm = co.OracleModel.hier(EIGHT_SCHOOLS_Y, EIGHT_SCHOOLS_SIGMA)
+    n = 512
+    rng = np.random.default_rng(3)
+    q0 = model.sample_initial_states(rng, n)
+    q0[:, 0] = np.clip(q0[:, 0], -8, 8)
+    q0[:, 1] = np.clip(q0[:, 1], -1.5, 2.5)
+    par = model.generate_params(q0[:, :2])
+    q0[:, 10:] = ((EIGHT_SCHOOLS_Y[None] - par["μ"][:, None] - par["τ"][:, None] * q0[:, 2:10])
+                  / EIGHT_SCHOOLS_SIGMA[None])  # fmt: skip
+    integ = mlb.integrators.ConstrainedLeapfrogIntegrator(
+        system, projection_solver=mlb.jitted_solve_projection_onto_manifold_newton,
+        projection_solver_kwargs=dict(constraint_tol=1e-9, position_tol=1e-8, max_iters=50))
+    assert integ.step_size is None
+    state = mlb.states.ChainState(q0)
+    state.mom = system.sample_momentum(state, rng)
+    adapter = mlb.adapters.DualAveragingStepSizeAdapter(0.8)
+    eps = adapter.find_init_step_size(state, system, integ).cpu().numpy()
+    # scalar re-enactment, chain by chain, with the CPU oracle's single step
+    p0 = state.mom.cpu().numpy()
+    opts = co.solver_opts(co.SOLVER_NEWTON)
+    want = np.ones(n)
+    undecided = np.ones(n, bool)
+    too_big = np.zeros(n, bool)
+    for s in range(100):
+        idx = np.nonzero(undecided)[0]
+        if idx.size == 0:
+            break
+        for e in np.unique(want[idx]):
+            sel = idx[want[idx] == e]
+            r = cm.leapfrog_steps(q0[sel], p0[sel], float(e), 1, opts)
+            failed = r["status"] != 0
+            dh = np.abs(r["h_init"] - r["h_final"])
+            nan = np.isnan(dh) & ~failed
+            over = dh > np.log(2.0)
+            if s == 0:
+                too_big[sel] = nan | over
+            too_big[sel] |= nan | failed
+            flipped = ~failed & ~nan & ((too_big[sel] & ~over) | (~too_big[sel] & over))
+            undecided[sel[flipped]] = False
+            keep = sel[~flipped]
+            want[keep] *= np.where(too_big[keep], 0.5, 2.0)
+    assert not undecided.any()
+    # a |dh| within rounding of log 2 may flip one comparison: allow a handful of chains
+    assert (eps == want).mean() > 0.99, (eps != want).sum()
+    assert set(np.unique(np.log2(eps))) <= set(range(-12, 6))
+    # reference-style run: no step size given, the warm-up finds and adapts it
+    sampler = mlb.samplers.StaticMetropolisHMC(system, integ, n_step=8, seed=2)
+    _, _, stats = sampler.sample_chains(150, 100, q0, adapters=[adapter], trace_dim=2)
+    assert integ.step_size is not None and 0.05 < float(integ.step_size) < 5.0
+    assert 0.6 < float(stats["accept_stat"].mean()) < 0.95
+    with pytest.raises(ValueError):
+        integ2 = mlb.integrators.ConstrainedLeapfrogIntegrator(system)
+        mlb.samplers.StaticMetropolisHMC(system, integ2, n_step=2).sample_chains(0, 1, q0)
