@@ -442,7 +442,16 @@ int mlb_leapfrog_steps_host(const mlb_model* m, int64_t n, double* q, double* p,
   // streaming (ODE) family keeps one chunk and transposes on the device: its batches are
   // small and its kernels long.
   const bool small_state = m->model == MLB_MODEL_TOY || m->model == MLB_MODEL_HIER;
-  const int64_t chunk = small_state ? 16384 : n;
+  // chunk size: four chunks in flight (one per stream), between 2,048 and 16,384 chains -
+  // 16,384 measured best for 65,536 chains; below that the fused kernel's
+  // duration no longer depends on the chunk size (one warp per scheduler: the latency of a
+  // single chain's trajectory), so smaller chunks only shorten the exposed first H2D / last
+  // D2H copy
+  int64_t chunk = n;
+  if (small_state) {
+    chunk = ((n + 3) / 4 + 63) / 64 * 64;
+    chunk = chunk < 2048 ? 2048 : chunk > 16384 ? 16384 : chunk;
+  }
   const int n_chunk = (int)((n + chunk - 1) / chunk);
   // per chunk: row-major state (2 vec), component-major state (2 vec, ODE family only),
   // per-chain outputs; the staging area lives in the model handle and only grows: no
@@ -485,7 +494,9 @@ int mlb_leapfrog_steps_host(const mlb_model* m, int64_t n, double* q, double* p,
         if ((rc = mlb_aos_to_soa(nc, Q, d_aos_q, d_q, nc, s)) != MLB_OK) break;
         if ((rc = mlb_aos_to_soa(nc, Q, d_aos_p, d_p, nc, s)) != MLB_OK) break;
       }
-      StepsIO io{d_q, d_p, dt, nullptr, n_step, d_status, d_done, d_itf, d_itr, d_h0, d_h1};
+      // energies only if asked for: their logarithms are not free (mlb_chmc.cuh::evaluate_at)
+      StepsIO io{d_q, d_p, dt, nullptr, n_step, d_status, d_done, d_itf, d_itr,
+                 h_init ? d_h0 : nullptr, h_final ? d_h1 : nullptr};
       io.row_major = small_state;
       if ((rc = m->ops->steps(m, opts->solver, nc, nc, o, io, s)) != MLB_OK) break;
       if (!small_state) {

@@ -9,9 +9,14 @@ What is restated and what is not verifiable here: ArviZ and Mici are absent from
 sd, hdi_3% / hdi_97% = narrowest 94 % interval of the pooled draws, mcse_mean, mcse_sd,
 ess_bulk, ess_tail, r_hat; `parallel.py` holds the ESS / R-hat estimators) and are checked
 in tests/test_cpu_outputs.py against their defining properties on draws with known
-answers; the per-chain file names follow Mici's memory-mapped traces as recalled
-(`trace_{chain}_{name}.npy`, `stats_{chain}_{name}.npy`) and are a convention of this
-package until they can be compared with a Mici installation.
+answers.  The per-chain file names are Mici 0.2.1's (`force_memmap=True,
+memmap_path=output_dir`, utils.py:449-450): `trace_{chain}_{name}.npy` and, for the
+statistics Mici nests per transition (`stats["integration"]["accept_stat"]`,
+monitor_stats of utils.py:335-340), `stats_{chain}_{transition}_{name}.npy` - as recalled
+from Mici's `_generate_memmap_filename` (its source is not in the reference tree).  Nothing
+in the reference READS these files (grep: the harness's own products are `summary.json`,
+`final_chain_states.pkl` and, for the Euclidean baseline only, `final_metric.npy`), so the
+names matter to users' own post-processing only.
 """
 import json
 import math
@@ -33,7 +38,15 @@ def save_traces(output_dir, traces, stats=None, chain_offset=0):
     One `.npy` per chain and name (`np.load(..., mmap_mode="r")` maps them)."""
     os.makedirs(output_dir, exist_ok=True)
     paths = []
-    for kind, group in (("trace", traces), ("stats", stats or {})):
+    flat_stats = {}
+    for name, arr in (stats or {}).items():
+        if isinstance(arr, dict):  # Mici nests statistics per transition
+            flat_stats.update({f"{name}_{k}": v for k, v in arr.items()})
+        elif isinstance(name, tuple):
+            flat_stats["_".join(name)] = arr
+        else:
+            flat_stats[name] = arr
+    for kind, group in (("trace", traces), ("stats", flat_stats)):
         for name, arr in group.items():
             a = _np(arr)
             for i in range(a.shape[0]):

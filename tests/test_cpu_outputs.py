@@ -2,6 +2,7 @@
 summary columns against their defining properties on draws with known answers.  ArviZ is
 not installable here, so the columns are checked by what they must equal, not against it."""
 import json
+import os
 import pickle
 
 import numpy as np
@@ -57,6 +58,11 @@ def test_files_written_like_the_reference_harness(tmp_path):
     out = str(tmp_path)
     paths = outputs.save_traces(out, traces, stats)
     assert len(paths) == 3 * 3 + 3
+    # Mici nests monitored statistics per transition: stats_{chain}_{transition}_{name}.npy
+    nested = outputs.save_traces(out, {}, {"integration": {"accept_stat": rng.uniform(size=(3, 50)),
+                                                          "convergence_error": np.zeros((3, 50))}})
+    assert sorted(os.path.basename(p) for p in nested)[:2] == [
+        "stats_0_integration_accept_stat.npy", "stats_0_integration_convergence_error.npy"]
     back = outputs.load_traces(out, ["u", "tau"], 3)
     assert isinstance(back["u"][1], np.memmap) and np.array_equal(back["u"][1], traces["u"][1])
     rows, summ = outputs.compute_and_save_summary(out, ["u", "tau"], traces,

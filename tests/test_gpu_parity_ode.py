@@ -445,3 +445,42 @@ def test_phased_path_matches_single_kernel(model, solver):
     bad = cpu(a.status) != 0
     if bad.any():
         assert scaled_err(cpu(a.pos)[bad], cpu(b.pos)[bad]) < tol_q
+
+
+@pytest.mark.parametrize("model", ["fn", "hh"])
+def test_projection_error_against_extended_precision_truth(model):
+    """is the CUDA path's disagreement with the CPU oracle on the
+    ill-conditioned Woodbury projections an ERROR of the kernels, or the noise floor of the
+    reference's formulation?  Both are compared with 50-digit mpmath arithmetic on the same
+    fp64 Jacobian blocks (the GPU's, handed to the oracle as well): the kernels' distance
+    from the truth must be no worse than a small multiple of the CPU oracle's."""
+    from _cases import woodbury_projection_truth
+
+    if model == "hh":
+        mlb, g, cm, gm, gs = hh_case()
+        q = hh_states(cm, g, 8)
+    else:
+        mlb, g, cm, gm, gs = fn_case()
+        q = fn_states(cm, 8)
+    jac, _ = gs._jacob_constr_blocks(q)
+    gram = gs._decompose_gram(jac)
+    ojac_own, _ = cm.jacob_constr_blocks(q)
+    ojac = (cpu(jac[0]).copy(), ojac_own[1], cpu(jac[1]).copy())  # the GPU's blocks
+    ogram = cm.decompose_gram(ojac)
+    v = np.random.default_rng(1).standard_normal(q.shape)
+    got_gpu = cpu(gs._normal_space_component(jac, gram, v))
+    got_cpu = cm.normal_space_component(ojac, ogram, v)
+    e_gpu, e_cpu, conds = [], [], []
+    for i in range(q.shape[0]):
+        truth, cond = woodbury_projection_truth(ojac[0][i], ojac[2][i], v[i])
+        s = np.abs(truth).max()
+        e_gpu.append(np.abs(got_gpu[i] - truth).max() / s)
+        e_cpu.append(np.abs(got_cpu[i] - truth).max() / s)
+        conds.append(cond)
+    e_gpu, e_cpu, conds = np.array(e_gpu), np.array(e_cpu), np.array(conds)
+    print(f"{model}: cond(C) up to {conds.max():.1e}; |gpu - truth| {e_gpu.max():.1e}, "
+          f"|cpu oracle - truth| {e_cpu.max():.1e}, |gpu - cpu| "
+          f"{scaled_err(got_gpu, got_cpu):.1e}")
+    eps = np.finfo(float).eps
+    assert (e_gpu < 50 * conds * eps).all()
+    assert e_gpu.max() <= 4.0 * e_cpu.max() + 1e-13
