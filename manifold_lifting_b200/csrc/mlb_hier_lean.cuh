@@ -111,7 +111,8 @@ struct HierLean {
 template <class M, int SOLVER, int KB>
 MLB_DEV TrajOut run_trajectory_lean(const typename M::Params& P, LeanCol<M, KB> S, double* gq,
                                     double* gp, int64_t es, int n_step, double dt,
-                                    const Opts& o, bool want_h = true) {
+                                    const Opts& o, bool want_h = true,
+                                    bool preloaded = false) {
   using H = HierLean<M, SOLVER, KB>;
   using B = typename M::B;
   using C = LeanCol<M, KB>;
@@ -119,8 +120,10 @@ MLB_DEV TrajOut run_trajectory_lean(const typename M::Params& P, LeanCol<M, KB> 
   TrajOut t;
   t.status = MLB_ST_OK, t.done = 0, t.it_fwd = 0, t.it_rev = 0;
   t.h_init = t.h_last = nan("");
+  if (!preloaded) {  // else the kernel staged (q, p) into the column by bulk copies
 #pragma unroll
-  for (int k = 0; k < Q; ++k) S[C::SQ + k] = gq[k * es], S[C::SP + k] = gp[k * es];
+    for (int k = 0; k < Q; ++k) S[C::SQ + k] = gq[k * es], S[C::SP + k] = gp[k * es];
+  }
   double h1;
   bool half_pending = false;  // the committed momentum still lacks its closing half kick
   {

@@ -17,6 +17,7 @@
 
 #include "mlb_chmc.cuh"
 #include "mlb_hier_lean.cuh"
+#include "mlb_tma.cuh"
 
 namespace mlb { struct ModelOps; }
 
@@ -280,6 +281,16 @@ __global__ void __launch_bounds__(kBlock)
 
 // ----------------------------------------------------------------- fused drivers
 
+// State staging (north-star: "chain state staged through shared memory via TMA"): when the
+// CTA's [2 Q][kBlock] tile of a component-major state is whole and 16-byte aligned, ONE
+// thread fetches it with 2 Q bulk asynchronous copies (cp.async.bulk, mbarrier completion)
+// straight into the shared-memory tile that holds the last committed state anyway, and the
+// final state leaves the same way; ragged / row-major / unaligned tiles take per-thread
+// loads and stores.  MLB_TMA_STATE=0 compiles the copies out (A/B: profiles/r5e_*).
+#ifndef MLB_TMA_STATE
+#define MLB_TMA_STATE 1
+#endif
+
 template <class M, int SOLVER>
 __global__ void __launch_bounds__(kBlock, MLB_LF_MIN_BLOCKS)
     k_leapfrog_steps(const __grid_constant__ typename M::Params P, int64_t n, int64_t es,
@@ -287,28 +298,68 @@ __global__ void __launch_bounds__(kBlock, MLB_LF_MIN_BLOCKS)
                      Opts o, int32_t* status, int32_t* n_done, int32_t* iters_fwd,
                      int32_t* iters_rev, double* h_init, double* h_final) {
   constexpr int Q = M::Q;
-  __shared__ double commit[2 * Q][kBlock];  // last committed (q, p) of each chain
+  __shared__ __align__(128) double commit[2 * Q][kBlock];  // last committed (q, p) of each chain
+  __shared__ uint64_t bar;
+  const int64_t i0 = (int64_t)blockIdx.x * kBlock;
+  const bool tile = MLB_TMA_STATE && i0 + kBlock <= n && bulk_tile_ok(q, es, cs) &&
+                    bulk_tile_ok(p, es, cs);  // uniform over the CTA
+  if (tile) {
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&bar, 2 * Q * kBlock * (int)sizeof(double));
+#pragma unroll 1
+      for (int k = 0; k < Q; ++k) {
+        bulk_g2s(&commit[k][0], q + k * es + i0, kBlock * sizeof(double), &bar);
+        bulk_g2s(&commit[Q + k][0], p + k * es + i0, kBlock * sizeof(double), &bar);
+      }
+    }
+  }
   MLB_CHAIN_INDEX();
   double qv[Q], pv[Q];
-  load_vec<Q>(qv, q, es, cs, i);
-  load_vec<Q>(pv, p, es, cs, i);
+  if (tile) {
+    mbar_wait(&bar, 0);
+#pragma unroll
+    for (int k = 0; k < Q; ++k) qv[k] = commit[k][threadIdx.x], pv[k] = commit[Q + k][threadIdx.x];
+  } else {
+    load_vec<Q>(qv, q, es, cs, i);
+    load_vec<Q>(pv, p, es, cs, i);
+  }
   const double dti = dt_pc ? dt_pc[i] : dt;
   const TrajOut t = run_trajectory<M, SOLVER, false, false, kBlock>(
       P, qv, pv, &commit[0][threadIdx.x], &commit[Q][threadIdx.x], n_step, dti, o, 0.0,
       h_init != nullptr || h_final != nullptr);
-  store_vec<Q>(qv, q, es, cs, i);
-  store_vec<Q>(pv, p, es, cs, i);
+  if (tile) {
+#pragma unroll
+    for (int k = 0; k < Q; ++k) commit[k][threadIdx.x] = qv[k], commit[Q + k][threadIdx.x] = pv[k];
+    fence_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll 1
+      for (int k = 0; k < Q; ++k) {
+        bulk_s2g(q + k * es + i0, &commit[k][0], kBlock * sizeof(double));
+        bulk_s2g(p + k * es + i0, &commit[Q + k][0], kBlock * sizeof(double));
+      }
+      bulk_commit();
+    }
+  } else {
+    store_vec<Q>(qv, q, es, cs, i);
+    store_vec<Q>(pv, p, es, cs, i);
+  }
   status[i] = t.status;
   if (n_done) n_done[i] = t.done;
   if (iters_fwd) iters_fwd[i] = t.it_fwd;
   if (iters_rev) iters_rev[i] = t.it_rev;
   if (h_init) h_init[i] = t.h_init;
   if (h_final) h_final[i] = t.h_last;
+  if (tile && threadIdx.x == 0) bulk_wait_read();  // the tile must outlive the copies' reads
 }
 
 // Shared-memory-parked form of k_leapfrog_steps (mlb_hier_lean.cuh): same device functions,
 // 128 registers, 7 CTAs per SM.  Used when it turns two waves of the register-resident
-// kernel into one (see Launch::steps).
+// kernel into one (see Launch::steps).  The initial state goes into the parked columns by
+// bulk asynchronous copies as above (the committed state of this form is the global arrays
+// themselves, written step by step, so nothing is left to store at the end).
 template <class M, int SOLVER>
 __global__ void __maxnreg__(128)
     k_leapfrog_steps_lean(const __grid_constant__ typename M::Params P, int64_t n, int64_t es,
@@ -316,12 +367,32 @@ __global__ void __maxnreg__(128)
                           int n_step, Opts o, int32_t* status, int32_t* n_done,
                           int32_t* iters_fwd, int32_t* iters_rev, double* h_init,
                           double* h_final) {
-  extern __shared__ double lean_columns[];  // [LeanCol::ROWS][kBlock]
+  extern __shared__ __align__(128) double lean_columns[];  // [LeanCol::ROWS][kBlock]
+  __shared__ uint64_t bar;
+  constexpr int Q = M::Q;
+  using LC = LeanCol<M, kBlock>;
+  static_assert(LC::SQ == 0 && LC::SP == Q, "state rows lead the column");
+  const int64_t i0 = (int64_t)blockIdx.x * kBlock;
+  const bool tile = MLB_TMA_STATE && i0 + kBlock <= n && bulk_tile_ok(q, es, cs) &&
+                    bulk_tile_ok(p, es, cs);
+  if (tile) {
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&bar, 2 * Q * kBlock * (int)sizeof(double));
+#pragma unroll 1
+      for (int k = 0; k < Q; ++k) {
+        bulk_g2s(lean_columns + (LC::SQ + k) * kBlock, q + k * es + i0, kBlock * sizeof(double), &bar);
+        bulk_g2s(lean_columns + (LC::SP + k) * kBlock, p + k * es + i0, kBlock * sizeof(double), &bar);
+      }
+    }
+  }
   MLB_CHAIN_INDEX();
-  const LeanCol<M, kBlock> S{lean_columns + threadIdx.x};
+  if (tile) mbar_wait(&bar, 0);
+  const LC S{lean_columns + threadIdx.x};
   const TrajOut t = run_trajectory_lean<M, SOLVER, kBlock>(
       P, S, q + i * cs, p + i * cs, es, n_step, dt_pc ? dt_pc[i] : dt, o,
-      h_init != nullptr || h_final != nullptr);
+      h_init != nullptr || h_final != nullptr, tile);
   status[i] = t.status;
   if (n_done) n_done[i] = t.done;
   if (iters_fwd) iters_fwd[i] = t.it_fwd;
