@@ -350,6 +350,24 @@ int mlb_ssm_project_onto_cotangent_space(int64_t n, int32_t dim_y, int32_t dim_u
 int mlb_ssm_sv_constr_blocks(int64_t n, int32_t dim_y, int64_t ld, const double* q,
                              const double* y_obs, double* c, const mlb_ssm_blocks* J_out,
                              void* stream);
+/* What the gradient of log_det_sqrt_gram needs from the Gram matrix G = J J^T (the reference
+ * takes that gradient by reverse-mode autodiff of systems.py:1233-1243, jit table
+ * systems.py:332-334; in closed form d(1/2 log det G) = sum over the non-zero pattern of J of
+ * (G^{-1} J)_{tj} dJ_{tj}): inv_gram_dc_du [dim_y * dim_u][ld] = G^{-1} dc_du (row t * dim_u +
+ * u), inv_gram_diag [dim_y][ld] = diag(G^{-1}), inv_gram_offdiag [dim_y - 1][ld] =
+ * (G^{-1})_{t,t+1}; a, b, chol_cap from mlb_ssm_decompose_gram. */
+int mlb_ssm_band_inv_gram(int64_t n, int32_t dim_y, int32_t dim_u, int64_t ld,
+                          const mlb_ssm_blocks* J, const double* a, const double* b,
+                          const double* chol_cap, double* inv_gram_dc_du, double* inv_gram_diag,
+                          double* inv_gram_offdiag, void* stream);
+/* Stochastic-volatility model: grad [3 + 2 dim_y][ld] = d log_det_sqrt_gram / dq, the
+ * contraction of the weights above with the derivatives of the entries of
+ * jacob_constr_split_blocks (stochastic_volatility.py:92-141); J = the blocks at q. */
+int mlb_ssm_sv_grad_log_det_sqrt_gram(int64_t n, int32_t dim_y, int64_t ld, const double* q,
+                                      const double* y_obs, const mlb_ssm_blocks* J,
+                                      const double* inv_gram_dc_du, const double* inv_gram_diag,
+                                      const double* inv_gram_offdiag, double* grad,
+                                      void* stream);
 /* Bookkeeping of one iteration of the projection loops (systems.py:203-227, 243-269) for the
  * chains with active[i] != 0: error = |c|_max, mu += delta_q, q -= delta_q, n_iters += 1,
  * norm_delta_q = |delta_q|_max, then active[i] = !(n_iters >= max_iters || error >

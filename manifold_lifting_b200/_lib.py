@@ -38,7 +38,8 @@ EXPORTS = (
     "mlb_ssm_decompose_gram", "mlb_ssm_lmult_by_inv_gram",
     "mlb_ssm_lmult_by_inv_jacob_product", "mlb_ssm_log_det_sqrt_gram",
     "mlb_ssm_lmult_by_jacob_constr", "mlb_ssm_rmult_by_jacob_constr",
-    "mlb_ssm_sv_constr_blocks", "mlb_ssm_projection_update",
+    "mlb_ssm_sv_constr_blocks", "mlb_ssm_projection_update", "mlb_ssm_band_inv_gram",
+    "mlb_ssm_sv_grad_log_det_sqrt_gram",
     "mlb_ssm_project_onto_cotangent_space",
 )  # fmt: skip
 

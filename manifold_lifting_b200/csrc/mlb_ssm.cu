@@ -550,6 +550,165 @@ static bool blocks_ok(const mlb_ssm_blocks* J, int Y) {
 }
 
 // scratch rows in units of [ld] doubles
+// ---- band of the inverse Gram matrix and G^{-1} dc_du: what the gradient of
+// log_det_sqrt_gram needs.  The reference differentiates systems.py:1233-1243 by reverse mode
+// (jit table systems.py:332-334); in closed form d(1/2 log det G) = tr(G^{-1} J dJ^T) = the sum
+// over the NON-ZERO PATTERN of J = [dc_du, diag(dc_dv), bidiag(dc_dn0, dc_dn1)] of
+// (G^{-1} J)_{tj} dJ_{tj}, which takes G^{-1} dc_du [Y x U] and the diagonal / first
+// off-diagonal of G^{-1} only.  With G = T + dc_du dc_du^T, Z = T^{-1} dc_du and the
+// capacitance matrix C = I + dc_du^T Z (Woodbury):
+//   G^{-1} dc_du = Z C^{-1},  G^{-1} = T^{-1} - Z C^{-1} Z^T,
+// and the band of T^{-1} = L^{-T} D^{-1} L^{-1} follows from the backward recurrences
+//   S_{t,t} = 1 / b'_t + w_{t+1}^2 S_{t+1,t+1},  S_{t,t+1} = -w_{t+1} S_{t+1,t+1}.
+// One forward sweep (elimination; d' = L^{-1} dc_du parked in the ru output, 1 / b' in the gd
+// output: no scratch) and one backward sweep that overwrites them row by row:
+//   z_t = (d'_t - a_t z_{t+1}) / b'_t,  r_t = C^{-1} z_t  -> ru[t],
+//   gd[t] = S_tt - r_t . z_t,  go[t] = S_{t,t+1} - r_t . z_{t+1}.
+template <int U>
+__global__ void __launch_bounds__(128)
+    k_ssm_band_inv_gram(int64_t n, int Y, int64_t ld, const double* du_p, const double* a,
+                        const double* b, const double* chol, double* ru, double* gd,
+                        double* go) {
+  constexpr int P = PrefetchDepth<U>::value;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double rbp = 0.0, dp[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) dp[u] = 0.0;
+  for (int k0 = 0; k0 < Y; k0 += P) {
+    double du[P][U], av[P], bv[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const int k = clampi(k0 + j, 0, Y - 1);
+#pragma unroll
+      for (int u = 0; u < U; ++u) du[j][u] = du_p[(int64_t)(k * U + u) * ld + i];
+      av[j] = k > 0 ? a[(int64_t)(k - 1) * ld + i] : 0.0;
+      bv[j] = b[(int64_t)k * ld + i];
+    }
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const int k = k0 + j;
+      if (k < Y) {
+        const double w = av[j] * rbp;
+        rbp = 1.0 / (bv[j] - w * av[j]);
+        gd[(int64_t)k * ld + i] = rbp;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          dp[u] = du[j][u] - w * dp[u];
+          ru[(int64_t)(k * U + u) * ld + i] = dp[u];
+        }
+      }
+    }
+  }
+  // C^{-1} = L^{-T} L^{-1} explicitly (U <= 8, registers)
+  double L[U][U], rdiag[U], ci[U][U];
+#pragma unroll
+  for (int r = 0; r < U; ++r) {
+#pragma unroll
+    for (int c = 0; c < U; ++c) L[r][c] = chol[(int64_t)(r * U + c) * ld + i];
+    rdiag[r] = 1.0 / L[r][r];
+  }
+#pragma unroll
+  for (int c = 0; c < U; ++c) {
+    double e[U];
+#pragma unroll
+    for (int r = 0; r < U; ++r) e[r] = r == c ? 1.0 : 0.0;
+    chol_solve<U>(L, rdiag, e);
+#pragma unroll
+    for (int r = 0; r < U; ++r) ci[r][c] = e[r];
+  }
+  double z_next[U], s_next = 0.0;
+#pragma unroll
+  for (int u = 0; u < U; ++u) z_next[u] = 0.0;
+#pragma unroll 1
+  for (int k = Y - 1; k >= 0; --k) {
+    const double rb = gd[(int64_t)k * ld + i];
+    const double ak = k < Y - 1 ? a[(int64_t)k * ld + i] : 0.0;
+    const double w = ak * rb;  // multiplier of row k + 1
+    double z[U], r[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) z[u] = (ru[(int64_t)(k * U + u) * ld + i] - ak * z_next[u]) * rb;
+    const double s_off = -w * s_next, s_diag = rb - w * s_off;
+    double qd = 0.0, qo = 0.0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      double acc = 0.0;
+#pragma unroll
+      for (int c = 0; c < U; ++c) acc = fma(ci[u][c], z[c], acc);
+      r[u] = acc;
+      qd = fma(acc, z[u], qd);
+      qo = fma(acc, z_next[u], qo);
+      ru[(int64_t)(k * U + u) * ld + i] = acc;
+    }
+    gd[(int64_t)k * ld + i] = s_diag - qd;
+    if (k < Y - 1) go[(int64_t)k * ld + i] = s_off - qo;
+#pragma unroll
+    for (int u = 0; u < U; ++u) z_next[u] = z[u];
+    s_next = s_diag;
+  }
+}
+
+// ---- gradient of log_det_sqrt_gram for the stochastic-volatility model: contraction of
+// the weights above with the derivatives of the Jacobian entries of
+// stochastic_volatility.py:92-141 (mu = u0, sigma = exp(u1), phi = 2 expit(u2) - 1; dx_dy =
+// 2 / y does not depend on q).  One chain per thread, one pass over the rows.
+__global__ void __launch_bounds__(128)
+    k_ssm_sv_grad_log_det(int64_t n, int Y, int64_t ld, const double* q, const double* y_obs,
+                          SsmBlocks J, const double* ru, const double* gd, const double* go,
+                          double* grad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double mu = q[i], u1 = q[ld + i], u2 = q[2 * ld + i];
+  const double sigma = exp(u1), e = 1.0 / (1.0 + exp(-u2));
+  const double phi = -1.0 + 2.0 * e, dphi = 2.0 * e * (1.0 - e), ddphi = dphi * (1.0 - 2.0 * e);
+  const double omp = 1.0 - phi * phi, s1 = sqrt(omp), rs = 1.0 / s1, rs3 = rs / omp,
+               rs5 = rs3 / omp;
+  const double* v = q + 3 * ld;
+  const double* nn = q + (int64_t)(3 + Y) * ld;
+  double* gv = grad + 3 * ld;
+  double* gn = grad + (int64_t)(3 + Y) * ld;
+  double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+  double gd_k = gd[i];
+  double x_prev = 0.0;
+#pragma unroll 1
+  for (int k = 0; k < Y; ++k) {
+    const double vk = v[(int64_t)k * ld + i], nk = nn[(int64_t)k * ld + i];
+    const double rn = 1.0 / nk;
+    const double r0 = ru[(int64_t)(k * 3 + 0) * ld + i], r1 = ru[(int64_t)(k * 3 + 1) * ld + i],
+                 r2 = ru[(int64_t)(k * 3 + 2) * ld + i];
+    const double wdv = gd_k * J.dv[(int64_t)k * ld + i];
+    const double dn0 = J.n0[(int64_t)k * ld + i];
+    const bool inner = k < Y - 1;
+    const double dn1 = inner ? J.n1[(int64_t)k * ld + i] : 0.0;
+    const double go_k = inner ? go[(int64_t)k * ld + i] : 0.0;
+    const double gd_n = inner ? gd[(int64_t)(k + 1) * ld + i] : 0.0;
+    const double r2_next = inner ? ru[(int64_t)((k + 1) * 3 + 2) * ld + i] : 0.0;
+    const double w0 = gd_k * dn0 + go_k * dn1, w1 = go_k * dn0 + gd_n * dn1;
+    if (k == 0) {
+      g1 += r1 * sigma * vk * rs + r2 * dphi * phi * sigma * vk * rs3 + wdv * sigma * rs;
+      g2 += r1 * sigma * vk * phi * dphi * rs3 +
+            r2 * sigma * vk * (ddphi * phi * rs3 + dphi * dphi * rs3 +
+                               3.0 * phi * phi * dphi * dphi * rs5) +
+            wdv * sigma * phi * dphi * rs3;
+      gv[i] = r1 * sigma * rs + r2 * dphi * phi * sigma * rs3;
+    } else {
+      g0 -= dphi * r2;
+      g1 += sigma * (r1 * vk + wdv);
+      g2 += -dphi * r0 + ddphi * r2 * (x_prev - mu);
+      gv[(int64_t)k * ld + i] = sigma * r1;
+    }
+    double gnk = w0 * (-2.0 * rn * rn);
+    if (inner) {
+      g2 -= 2.0 * dphi * w1 * rn;
+      gnk += r2_next * dphi * (-2.0 * rn) + w1 * 2.0 * phi * rn * rn;
+    }
+    gn[(int64_t)k * ld + i] = gnk;
+    x_prev = 2.0 * log(y_obs[k] * rn);
+    gd_k = gd_n;
+  }
+  grad[i] = g0, grad[ld + i] = g1, grad[2 * ld + i] = g2;
+}
+
 struct Scratch {
   double* p = nullptr;
   cudaStream_t s;
@@ -638,6 +797,36 @@ int mlb_ssm_log_det_sqrt_gram(int64_t n, int32_t dim_y, int32_t dim_u, int64_t l
   if (n == 0) return MLB_OK;
   k_ssm_log_det<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
       n, dim_y, dim_u, ld, a, b, chol_cap, J->dx_dy, out);
+  return finish_launch();
+}
+
+int mlb_ssm_band_inv_gram(int64_t n, int32_t dim_y, int32_t dim_u, int64_t ld,
+                          const mlb_ssm_blocks* J, const double* a, const double* b,
+                          const double* chol_cap, double* inv_gram_dc_du, double* inv_gram_diag,
+                          double* inv_gram_offdiag, void* stream) {
+  MLB_ARG(n >= 0 && dim_y >= 1 && dim_u >= 1 && dim_u <= MLB_SSM_MAX_DIM_U && ld >= n);
+  MLB_ARG(J && J->dc_du && b && chol_cap && inv_gram_dc_du && inv_gram_diag &&
+          (dim_y == 1 || (a && inv_gram_offdiag)));
+  if (n == 0) return MLB_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned g = (unsigned)((n + 127) / 128);
+  MLB_SSM_DISPATCH_U(dim_u, k_ssm_band_inv_gram<UU><<<g, 128, 0, s>>>(
+                                n, dim_y, ld, J->dc_du, a, b, chol_cap, inv_gram_dc_du,
+                                inv_gram_diag, inv_gram_offdiag));
+  return finish_launch();
+}
+
+int mlb_ssm_sv_grad_log_det_sqrt_gram(int64_t n, int32_t dim_y, int64_t ld, const double* q,
+                                      const double* y_obs, const mlb_ssm_blocks* J,
+                                      const double* inv_gram_dc_du, const double* inv_gram_diag,
+                                      const double* inv_gram_offdiag, double* grad,
+                                      void* stream) {
+  MLB_ARG(n >= 0 && dim_y >= 1 && ld >= n && q && y_obs && blocks_ok(J, dim_y));
+  MLB_ARG(inv_gram_dc_du && inv_gram_diag && grad && (dim_y == 1 || inv_gram_offdiag));
+  if (n == 0) return MLB_OK;
+  k_ssm_sv_grad_log_det<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      n, dim_y, ld, q, y_obs, dev_blocks(J), inv_gram_dc_du, inv_gram_diag, inv_gram_offdiag,
+      grad);
   return finish_launch();
 }
 

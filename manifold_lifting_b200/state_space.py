@@ -208,6 +208,24 @@ def log_det_sqrt_gram(dc_du, dc_dv=None, dc_dn=None, dx_dy=None, gram=None):
     return out
 
 
+def band_of_inv_gram(jacob_constr_blocks, gram_components):
+    """(G^-1 dc_du [n, dim_y, dim_u], diag(G^-1) [n, dim_y], first off-diagonal of G^-1
+    [n, dim_y - 1]) for G = J J^T: the weights of the Jacobian's non-zero pattern in
+    d(1/2 log det G) = sum (G^-1 J)_tj dJ_tj, i.e. what the gradient of
+    log_det_sqrt_gram (systems.py:1233-1243, differentiated by jax.value_and_grad in the
+    reference, systems.py:332-334) needs from the linear algebra."""
+    J = _blocks(jacob_constr_blocks)
+    a, b, chol = gram_components
+    _keep, pa, pb, pc = _gram_ptrs(J, a, b, chol)
+    ru = _lib.soa_empty(J.n, J.dim_y * J.dim_u)
+    gd = _lib.soa_empty(J.n, J.dim_y)
+    go = _lib.soa_empty(J.n, max(J.dim_y - 1, 1))
+    cs = J.c_struct()
+    check(lib().mlb_ssm_band_inv_gram(*_dims(J), C.byref(cs), pa, pb, pc, p_soa(ru)[0],
+                                      p_soa(gd)[0], p_soa(go)[0], stream_ptr()))  # fmt: skip
+    return ru, gd, go[:, : J.dim_y - 1]
+
+
 class StochasticVolatilityModel:
     """Constraint side of the reference's stochastic-volatility model
     (stochastic_volatility.py:71-141), `unbounded` prior parametrisation: q = (u, v, n) with
@@ -348,3 +366,81 @@ class StochasticVolatilityModel:
         status = torch.where(status != _lib.ST_OK, status, st_r)
         return dict(pos=q1, mom=p1, status=status, iters_fwd=it_f, iters_rev=it_r,
                     jacob_constr_blocks=J1, gram_components=gram1, reverse_error=rev)  # fmt: skip
+
+
+    # ------------------------------------------------------------ Hamiltonian side
+    def log_det_sqrt_gram(self, q):
+        """systems.py:1233-1243 at q: (value [n], (c, jacob_constr_blocks, gram_components))."""
+        J, c = self.jacob_constr_blocks(q)
+        gram = decompose_gram(J)
+        return log_det_sqrt_gram(J, gram=gram), (c, J, gram)
+
+    def val_and_grad_log_det_sqrt_gram(self, q, aux=None):
+        """`jax.value_and_grad(log_det_sqrt_gram, has_aux=True)` of the reference's jit table
+        (systems.py:332-334) for this model, in closed form: ((value, aux), grad [n, dim_q]).
+        `aux` = (c, blocks, gram) already evaluated at q (then nothing is recomputed)."""
+        t, pq, ld = self._q(q)
+        n = t.shape[0]
+        if aux is None:
+            val, aux = self.log_det_sqrt_gram(t)
+        else:
+            val = log_det_sqrt_gram(aux[1], gram=aux[2])
+        _, J, gram = aux
+        ru, gd, go = band_of_inv_gram(J, gram)
+        grad = _lib.soa_empty(n, self.dim_q)
+        cs = J.c_struct()
+        if p_soa(ru)[1] != ld:
+            raise _lib.MlbError("arrays must share the position array's leading dimension")
+        check(lib().mlb_ssm_sv_grad_log_det_sqrt_gram(
+            C.c_int64(n), C.c_int32(self.dim_y), C.c_int64(ld), pq,
+            C.c_void_p(self.y_obs.data_ptr()), C.byref(cs), p_soa(ru)[0], p_soa(gd)[0],
+            p_soa(go)[0] if go.shape[1] > 0 else None, p_soa(grad)[0], stream_ptr()))  # fmt: skip
+        return (val, aux), grad
+
+    def neg_log_dens(self, q):
+        """Extended prior: standard normal on (u, v, n) (systems.py:37-42, the default
+        `standard_normal_neg_log_dens` the reference passes for this model)."""
+        t = _lib.to_soa(torch.as_tensor(q, dtype=torch.float64))
+        return 0.5 * (t * t).sum(1)
+
+    def h1(self, q, aux=None):
+        """systems.py:360-366: neg_log_dens + log_det_sqrt_gram."""
+        val = (self.log_det_sqrt_gram(q)[0] if aux is None
+               else log_det_sqrt_gram(aux[1], gram=aux[2]))  # fmt: skip
+        return self.neg_log_dens(q) + val
+
+    def dh1_dpos(self, q, aux=None):
+        """systems.py:368-379: grad neg_log_dens (= q) + grad log_det_sqrt_gram; returns
+        (gradient [n, dim_q], (value of log_det_sqrt_gram, aux))."""
+        (val, aux), grad = self.val_and_grad_log_det_sqrt_gram(q, aux)
+        return grad + _lib.to_soa(torch.as_tensor(q, dtype=torch.float64)), (val, aux)
+
+    def h(self, q, p, aux=None):
+        pt = _lib.to_soa(torch.as_tensor(p, dtype=torch.float64))
+        return self.h1(q, aux) + 0.5 * (pt * pt).sum(1)
+
+    def leapfrog_step(self, q, p, dt, solver="newton", reverse_check_tol=2e-8, **tols):
+        """One constrained leapfrog step A(dt/2) B(dt) A(dt/2) of Mici's
+        ConstrainedLeapfrogIntegrator for every chain: half kick with
+        dh1_dpos + cotangent projection at q, the position half (`constrained_position_step`),
+        half kick + cotangent projection at the new point.  Chains whose position half fails
+        keep (q, p) and carry the failure status.  Returns a dict: pos, mom, status, iters_fwd,
+        iters_rev, h_init, h_final."""
+        q0 = _lib.to_soa(torch.as_tensor(q, dtype=torch.float64))
+        p0 = _lib.to_soa(torch.as_tensor(p, dtype=torch.float64))
+        g0, (ld0, aux0) = self.dh1_dpos(q0)
+        h_init = self.neg_log_dens(q0) + ld0 + 0.5 * (p0 * p0).sum(1)
+        _, J0, gram0 = aux0
+        p_half = project_onto_cotangent_space(p0 - 0.5 * dt * g0, J0, gram0)
+        mid = self.constrained_position_step(q0, p_half, dt, solver=solver,
+                                             reverse_check_tol=reverse_check_tol, **tols)  # fmt: skip
+        q1, J1, gram1 = mid["pos"], mid["jacob_constr_blocks"], mid["gram_components"]
+        g1, (ld1, _) = self.dh1_dpos(q1, aux=(None, J1, gram1))
+        p1 = project_onto_cotangent_space(mid["mom"] - 0.5 * dt * g1, J1, gram1)
+        ok = (mid["status"] == _lib.ST_OK)[:, None]
+        pos = torch.where(ok, q1, q0)
+        mom = torch.where(ok, p1, p0)
+        h_final = torch.where(ok[:, 0], self.neg_log_dens(q1) + ld1 + 0.5 * (p1 * p1).sum(1),
+                              h_init)  # fmt: skip
+        return dict(pos=pos, mom=mom, status=mid["status"], iters_fwd=mid["iters_fwd"],
+                    iters_rev=mid["iters_rev"], h_init=h_init, h_final=h_final)  # fmt: skip

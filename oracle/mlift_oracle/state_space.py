@@ -247,3 +247,88 @@ def sv_constrained_position_step(q, p, dt, y, solver="newton", reverse_check_tol
     if status == 0 and not maximum_norm(qb - q) <= reverse_check_tol:
         status = 3
     return q1, p1, status, it_f, it_r
+
+
+# ---- gradient of log_det_sqrt_gram for the stochastic-volatility model.  The reference
+# takes it by reverse-mode autodiff of systems.py:1233-1243 (`jax.value_and_grad`, jit table
+# systems.py:332-334); restated here in closed form:
+#   d(1/2 log det G) = tr(G^-1 J dJ^T) = sum over the Jacobian's non-zero pattern of
+#   (G^-1 J)_{tj} dJ_{tj},   J = [dc_du, diag(dc_dv), bidiag(dc_dn0, dc_dn1)],
+# with the derivatives of the entries of stochastic_volatility.py:92-141 taken by hand
+# (dx_dy = 2 / y does not depend on q).  Dense G^-1: this is the small-size checker; pinned
+# to the reference's autodiff by tests/golden/ref_sv.npz (`closed_grad_logdet`).
+def sv_param_derivatives(u):
+    e = 1.0 / (1.0 + np.exp(-u[2]))
+    sigma, phi = np.exp(u[1]), -1.0 + 2.0 * e
+    dphi = 2.0 * e * (1.0 - e)
+    return {"mu": u[0], "sigma": sigma, "phi": phi, "dphi": dphi,
+            "ddphi": dphi * (1.0 - 2.0 * e)}  # fmt: skip
+
+
+def sv_grad_log_det_sqrt_gram(q, y):
+    dim_y = y.shape[0]
+    u, v, n = sv_split(q, dim_y)
+    (dc_du, dc_dv, (dn0, dn1), dx_dy), _ = sv_jacob_constr_split_blocks(u, v, n, y)
+    jac = dense_jacobian(dc_du, dc_dv, (dn0, dn1), dx_dy)
+    ginv = np.linalg.inv(jac @ jac.T)
+    gd, go = np.diag(ginv), np.diag(ginv, 1)
+    ru = ginv @ dc_du  # weights of the dc_du entries
+    wdv = gd * dc_dv  # ... of dc_dv
+    w0 = gd * dn0 + np.concatenate((go * dn1, [0.0]))  # ... of dc_dn0
+    w1 = go * dn0[:-1] + gd[1:] * dn1  # ... of dc_dn1
+    p = sv_param_derivatives(u)
+    mu, sigma, phi, dphi, ddphi = p["mu"], p["sigma"], p["phi"], p["dphi"], p["ddphi"]
+    s = np.sqrt(1.0 - phi * phi)
+    x = 2.0 * np.log(y / n)
+    g_u = np.zeros(3)
+    g_v = np.zeros(dim_y)
+    g_n = np.zeros(dim_y)
+    # rows t >= 1
+    g_u[0] = -dphi * ru[1:, 2].sum()
+    g_u[1] = sigma * (ru[1:, 1] * v[1:]).sum() + sigma * wdv[1:].sum()
+    g_u[2] = (-dphi * ru[1:, 0].sum() + ddphi * (ru[1:, 2] * (x[:-1] - mu)).sum()
+              - 2.0 * dphi * (w1 / n[:-1]).sum())  # fmt: skip
+    g_v[1:] = sigma * ru[1:, 1]
+    g_n[:-1] += ru[1:, 2] * dphi * (-2.0 / n[:-1]) + w1 * 2.0 * phi / n[:-1] ** 2
+    g_n += w0 * (-2.0 / n**2)
+    # row 0
+    v0 = v[0]
+    g_u[1] += ru[0, 1] * sigma * v0 / s + ru[0, 2] * dphi * phi * sigma * v0 / s**3 + wdv[0] * sigma / s
+    g_u[2] += (ru[0, 1] * sigma * v0 * phi * dphi / s**3
+               + ru[0, 2] * sigma * v0 * (ddphi * phi / s**3 + dphi**2 / s**3
+                                          + 3.0 * phi**2 * dphi**2 / s**5)
+               + wdv[0] * sigma * phi * dphi / s**3)  # fmt: skip
+    g_v[0] = ru[0, 1] * sigma / s + ru[0, 2] * dphi * phi * sigma / s**3
+    return np.concatenate((g_u, g_v, g_n))
+
+
+def sv_log_det_sqrt_gram(q, y):  # systems.py:1233-1243 at q
+    jac, _ = sv_jacob_constr_split_blocks(*sv_split(q, y.shape[0]), y)
+    return log_det_sqrt_gram(*jac)
+
+
+def sv_leapfrog_step(q, p, dt, y, solver="newton", reverse_check_tol=2e-8, **kw):
+    """One step of Mici 0.2.1's ConstrainedLeapfrogIntegrator (restated) on
+    the stochastic-volatility system with the standard-normal extended prior
+    (systems.py:37-42): A(dt/2) = half kick with dh1_dpos (systems.py:368-379) + cotangent
+    projection, B(dt) = sv_constrained_position_step, A(dt/2).  Returns (pos, mom, status,
+    iters_fwd, iters_rev, h_init, h_final); a failed step leaves (q, p)."""
+    dim_y = y.shape[0]
+
+    def project_cotangent(q_, p_):
+        jac, _ = sv_jacob_constr_split_blocks(*sv_split(q_, dim_y), y)
+        gram = decompose_gram(*jac)
+        return p_ - rmult_by_jacob_constr(
+            *jac, lmult_by_inv_gram(*jac, *gram, lmult_by_jacob_constr(*jac, p_)))
+
+    def hamiltonian(q_, p_):
+        return 0.5 * q_ @ q_ + sv_log_det_sqrt_gram(q_, y) + 0.5 * p_ @ p_
+
+    h_init = hamiltonian(q, p)
+    p_half = project_cotangent(q, p - 0.5 * dt * (q + sv_grad_log_det_sqrt_gram(q, y)))
+    q1, p1, status, it_f, it_r = sv_constrained_position_step(
+        q, p_half, dt, y, solver=solver, reverse_check_tol=reverse_check_tol, **kw)
+    if status:
+        return q, p, status, it_f, it_r, h_init, h_init
+    p1 = project_cotangent(q1, p1 - 0.5 * dt * (q1 + sv_grad_log_det_sqrt_gram(q1, y)))
+    return q1, p1, status, it_f, it_r, h_init, hamiltonian(q1, p1)

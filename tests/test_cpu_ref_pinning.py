@@ -306,3 +306,7 @@ def test_state_space_restatement_matches_reference_source(tag):
         blocks_p, _ = ss.sv_jacob_constr_split_blocks(up, vp, np_, y)
         ijp = ss.lmult_by_inv_jacob_product(*blocks, *blocks_p, wy)
         assert rel_err(ijp, g[f"{tag}_ijp_w"][i]) < 1e-11
+        # closed-form gradient of log_det_sqrt_gram against the reference's reverse-mode
+        # autodiff of systems.py:1233-1243 (jax.value_and_grad, systems.py:332-334)
+        assert rel_err(ss.sv_grad_log_det_sqrt_gram(q, y), g[f"{tag}_grad_logdet"][i]) < 1e-10
+        assert rel_err(ss.sv_log_det_sqrt_gram(q, y), g[f"{tag}_logdet"][i]) < 1e-12

@@ -478,3 +478,113 @@ def test_state_space_kernels_stay_inside_their_arrays(dim_y, dim_u):
     same(gx, mlb.linalg.tridiagonal_solve(a, b, a, vy) if dim_y > 1
          else mlb.linalg.tridiagonal_solve(None, b, None, vy))
     assert bool(torch.isnan(big_x[:, :g]).all()) and bool(torch.isnan(big_x[:, g + dim_y :]).all())
+
+
+def _ref_sv():
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_sv.npz")
+    return np.load(path)
+
+
+@pytest.mark.parametrize("dim_y,dim_u", [(1, 1), (2, 3), (9, 2), (40, 3), (61, 5), (200, 8)])
+def test_band_of_inverse_gram_matches_dense_inverse(dim_y, dim_u):
+    """G^-1 dc_du, diag(G^-1) and the first off-diagonal of G^-1 from the two-sweep kernel
+    against the dense inverse of the assembled J J^T (random blocks)."""
+    import manifold_lifting_b200 as mlb
+
+    ss = mlb.state_space
+    rng = np.random.default_rng(dim_y * 31 + dim_u)
+    n = 37
+    blocks = [oss.random_blocks(rng, dim_y, dim_u) for _ in range(n)]
+    du = np.stack([b[0] for b in blocks])
+    dv = np.stack([b[1] for b in blocks])
+    dn0 = np.stack([b[2][0] for b in blocks])
+    dn1 = np.stack([b[2][1] for b in blocks]).reshape(n, max(dim_y - 1, 0))
+    dxdy = np.stack([b[3] for b in blocks])
+    J = ss.JacobBlocks(du, dv, (dn0, dn1), dxdy)
+    ru, gd, go = ss.band_of_inv_gram(J, ss.decompose_gram(J))
+    for i in range(n):
+        jac = oss.dense_jacobian(*blocks[i])
+        ginv = np.linalg.inv(jac @ jac.T)
+        scale = np.abs(ginv).max()
+        assert np.abs(ru[i].cpu().numpy().reshape(dim_y, dim_u) - ginv @ blocks[i][0]).max() < 1e-11 * max(
+            1.0, np.abs(ginv @ blocks[i][0]).max())
+        assert np.abs(gd[i].cpu().numpy() - np.diag(ginv)).max() < 1e-11 * scale
+        if dim_y > 1:
+            assert np.abs(go[i].cpu().numpy() - np.diag(ginv, 1)).max() < 1e-11 * scale
+
+
+def test_stochastic_volatility_log_det_gradient_matches_reference_source():
+    """d log_det_sqrt_gram / dq of the stochastic-volatility system: the CUDA path against
+    the outputs of the reference's own source (reverse-mode autodiff of systems.py:1233-1243
+    on the torch-backed jax stand-in; tests/golden/ref_sv.npz) to the north-star's 1e-10,
+    against the closed-form restatement on other sizes, and against central differences of
+    the CUDA value."""
+    import manifold_lifting_b200 as mlb
+
+    ss = mlb.state_space
+    g = _ref_sv()
+    model = ss.StochasticVolatilityModel(g["y_obs"])
+    for tag in ("closed", "auto"):
+        (val, _), grad = model.val_and_grad_log_det_sqrt_gram(g[f"{tag}_q"])
+        ref = g[f"{tag}_grad_logdet"]
+        err = np.abs(grad.cpu().numpy() - ref).max(1) / np.abs(ref).max(1)
+        assert err.max() < 1e-10, err
+        assert np.abs(val.cpu().numpy() - g[f"{tag}_logdet"]).max() < 1e-10 * np.abs(g[f"{tag}_logdet"]).max()
+    for dim_y in (1, 2, 7, 150):
+        rng, qs, y = _sv_setup(dim_y, 12, 100 + dim_y)
+        model = ss.StochasticVolatilityModel(y)
+        (val, aux), grad = model.val_and_grad_log_det_sqrt_gram(qs)
+        want = np.stack([oss.sv_grad_log_det_sqrt_gram(qs[i], y) for i in range(len(qs))])
+        err = np.abs(grad.cpu().numpy() - want).max(1) / np.maximum(np.abs(want).max(1), 1.0)
+        assert err.max() < 1e-9, (dim_y, err)
+        # central differences of the CUDA value along random directions
+        d = rng.normal(size=qs.shape)
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        eps = 1e-6
+        fd = (model.log_det_sqrt_gram(qs + eps * d)[0] - model.log_det_sqrt_gram(qs - eps * d)[0]) / (2 * eps)
+        an = (grad.cpu().numpy() * d).sum(1)
+        assert np.abs(fd.cpu().numpy() - an).max() < 1e-6 * max(1.0, np.abs(an).max())
+
+
+@pytest.mark.parametrize("solver", ["newton", "quasi_newton"])
+def test_stochastic_volatility_leapfrog_step_matches_restatement(solver):
+    """The whole constrained leapfrog step A(dt/2) B(dt) A(dt/2) for the state-space family
+    chain by chain against the restated integrator: positions, momenta, statuses, iteration
+    counts, Hamiltonians; the energy error is O(dt^2) and the step is time-reversible."""
+    import manifold_lifting_b200 as mlb
+    from manifold_lifting_b200 import _lib
+
+    ss = mlb.state_space
+    dim_y, n, dt = 50, 16, 0.02
+    rng, qs, y = _sv_setup(dim_y, n, 5)
+    model = ss.StochasticVolatilityModel(y)
+    J, _ = model.jacob_constr_blocks(qs)
+    p = ss.project_onto_cotangent_space(rng.normal(size=qs.shape), J, ss.decompose_gram(J))
+    p_np = p.cpu().numpy().copy()
+    out = model.leapfrog_step(qs, p_np, dt, solver=solver)
+    ref = [oss.sv_leapfrog_step(qs[i], p_np[i], dt, y, solver=solver) for i in range(n)]
+    st_ref = np.array([r[2] for r in ref])
+    assert (out["status"].cpu().numpy() == st_ref).all() and (st_ref == _lib.ST_OK).all()
+    qr, pr = np.stack([r[0] for r in ref]), np.stack([r[1] for r in ref])
+    same = (out["iters_fwd"].cpu().numpy() == np.array([r[3] for r in ref])) & (
+        out["iters_rev"].cpu().numpy() == np.array([r[4] for r in ref]))
+    assert same.sum() >= n - 2
+    assert np.abs(out["pos"].cpu().numpy()[same] - qr[same]).max() < 1e-10 * max(1.0, np.abs(qr).max())
+    assert np.abs(out["mom"].cpu().numpy()[same] - pr[same]).max() < 1e-8 * max(1.0, np.abs(pr).max())
+    h0 = np.array([r[5] for r in ref])
+    h1 = np.array([r[6] for r in ref])
+    assert np.abs(out["h_init"].cpu().numpy() - h0).max() < 1e-10 * np.abs(h0).max()
+    assert np.abs(out["h_final"].cpu().numpy()[same] - h1[same]).max() < 1e-9 * np.abs(h1).max()
+    # energy error O(dt^2): halving the step divides it by ~4 (loosely: by more than 2.5)
+    e_full = (out["h_final"] - out["h_init"]).abs().cpu().numpy()
+    half = model.leapfrog_step(qs, p_np, dt / 2, solver=solver)
+    e_half = (half["h_final"] - half["h_init"]).abs().cpu().numpy()
+    assert np.median(e_full / np.maximum(e_half, 1e-300)) > 2.5
+    # reversibility of the whole step: flip the momentum, step, flip again
+    back = model.leapfrog_step(out["pos"], -out["mom"], dt, solver=solver)
+    assert float((back["pos"] - torch.as_tensor(qs).cuda()).abs().max()) < 1e-7
+    assert float((-back["mom"] - torch.as_tensor(p_np).cuda()).abs().max()) < 1e-6
+    good = torch.ones(n, dtype=torch.bool, device="cuda")
+    assert float(model.constr(out["pos"])[good].abs().max()) < 1e-9
