@@ -786,23 +786,23 @@ def run_reference_sv(args, emit):
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
         for q, p in zip(qs, ps):
-            oss.sv_constrained_position_step(q, p, args.step_size, y, solver=solver)
+            oss.sv_leapfrog_step(q, p, args.step_size, y, solver=solver)
         if i >= args.warmup:
             secs.append(time.perf_counter() - t0)
     value = m / float(np.mean(secs))
     emit({
-        "impl": "reference", "metric": "constrained position half-steps/s (all chains)",
-        "value": value, "unit": "half-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": "constrained leapfrog steps/s (all chains)",
+        "value": value, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": f"stochastic-volatility state-space system (dim_y={SV_DIM_Y}), "
                                "extra workload outside the BASELINE configs",
                    "step_size": args.step_size, "solver": args.solver},
-        "cpu_baseline": {"value": value, "unit": "half-steps/s", "cores": 1, "kind": "port",
-                         "sample": f"{m} chains x 1 position half-step per bench step, NumPy "
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": 1, "kind": "port",
+                         "sample": f"{m} chains x 1 constrained leapfrog step per bench step, NumPy "
                                    "restatement, one core"},
-        "e2e": {"value": value, "unit": "half-steps/s", "h2d_bytes_per_step": 0,
+        "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     })  # fmt: skip
@@ -826,11 +826,11 @@ def sv_synthetic_observations(dim_y=SV_DIM_Y, seed=202101):
 
 
 def run_sv(args, emit):
-    """Extra workload outside the BASELINE configs: the position half of
-    the constrained leapfrog step (projection, momentum update + re-projection, reversibility
-    check) for the stochastic-volatility state-space system, dim_y = 1,000, every chain.
-    The Hamiltonian half of these systems is not built, so the unit is a
-    position half-step, not a leapfrog step."""
+    """Extra workload outside the BASELINE configs: one constrained
+    leapfrog step (half kick with dh1_dpos incl. the gradient of log_det_sqrt_gram +
+    cotangent projection, position step with projection onto the manifold, momentum
+    re-projection, reversibility check, second half kick) for the stochastic-volatility
+    state-space system, dim_y = 1,000, every chain."""
     import torch
     import torch.distributed as dist
 
@@ -878,7 +878,7 @@ def run_sv(args, emit):
     del J, gram
 
     def step():
-        return model.constrained_position_step(q, p, dt, solver=solver)
+        return model.leapfrog_step(q, p, dt, solver=solver)
 
     for _ in range(max(args.warmup, 3)):
         out = step()
@@ -914,8 +914,8 @@ def run_sv(args, emit):
     e2e_iters = max(3, args.steps // 3)
 
     def e2e_step():
-        o = model.constrained_position_step(qh.cuda(non_blocking=True),
-                                            ph.cuda(non_blocking=True), dt, solver=solver)
+        o = model.leapfrog_step(qh.cuda(non_blocking=True), ph.cuda(non_blocking=True), dt,
+                                solver=solver)
         qo.copy_(o["pos"], non_blocking=True), po.copy_(o["mom"], non_blocking=True)
         return o["status"].cpu()
 
@@ -967,22 +967,23 @@ def run_sv(args, emit):
         t0 = time.perf_counter()
         with np.errstate(all="ignore"):
             for i in range(m):
-                oss.sv_constrained_position_step(qs[i], ps[i], dt, y, solver=solver)
+                oss.sv_leapfrog_step(qs[i], ps[i], dt, y, solver=solver)
         sec = time.perf_counter() - t0
-        cpu = {"value": m / sec, "unit": "half-steps/s", "cores": 1, "kind": "port",
-               "sample": f"{m} chains x 1 position half-step, NumPy restatement "
+        cpu = {"value": m / sec, "unit": "steps/s", "cores": 1, "kind": "port",
+               "sample": f"{m} chains x 1 constrained leapfrog step, NumPy restatement "
                          "(oracle/mlift_oracle/state_space.py), one core", "seconds": sec}  # fmt: skip
     if rank == 0:
         emit({
-            "metric": "constrained position half-steps/s (all chains)", "value": value,
-            "unit": "half-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": "constrained leapfrog steps/s (all chains)", "value": value,
+            "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"stochastic-volatility state-space system (dim_u=3, dim_y={dim_y}, "
                                    f"dim_q={model.dim_q}), {n} chains per GPU, synthetic data; extra "
                                    "workload outside the BASELINE configs (SURVEY 8f rank 3)",
-                       "unit_of_work": "position half of the constrained leapfrog step: projection, "
-                                       "momentum update + cotangent re-projection, reversibility check",
+                       "unit_of_work": "one constrained leapfrog step: two half kicks with dh1_dpos "
+                                       "(gradient of log_det_sqrt_gram) + cotangent projections, "
+                                       "projection onto the manifold, reversibility check",
                        "step_size": dt, "solver": args.solver, "chains_total": n * world,
                        "ok_fraction": ok_frac,
                        "mean_projection_iters": [float(out["iters_fwd"].double().mean()),
@@ -992,10 +993,10 @@ def run_sv(args, emit):
                          "frac": ach / hbm_peak, "traffic": None, "kernel": kname,
                          "peak_source": src, "ms_per_launch": kms,
                          "algorithmic_bytes_per_chain": 8.0 * rows * dim_y},
-            "e2e": {"value": e2e_value, "unit": "half-steps/s",
+            "e2e": {"value": e2e_value, "unit": "steps/s",
                     "h2d_bytes_per_step": int(2 * qh.numel() * 8),
                     "d2h_bytes_per_step": int(2 * qh.numel() * 8 + 4 * n),
-                    "api": "StochasticVolatilityModel.constrained_position_step (pinned host arrays)"},
+                    "api": "StochasticVolatilityModel.leapfrog_step (pinned host arrays)"},
             "gpu_launches": launches, "clocks": clk, "cpu_baseline": cpu,
         })  # fmt: skip
     if world > 1:
