@@ -269,6 +269,11 @@ struct Work {
   Gram G, Gp;
   std::vector<double> c, w, x, tq, tq2, mat, tmpu, dprod, mu, delta, q_try, dir;
   std::vector<double> mu_dt, qb, mub;
+  // line search: set when a backtracking comparison |c(q + a d)| > |c(q)| was decided by
+  // rounding (both norms below the residual noise floor, or equal to 1e-6 relative): such a
+  // comparison, hence the halving count and the iteration path after it, is not
+  // reproducible between two fp64 implementations (tests/test_gpu_full_size.py)
+  int ls_ambiguous = 0;
   void init(const Model& M) {
     J.init(M), Jp.init(M), Jtmp.init(M), G.init(M), Gp.init(M);
     int K = M.dense ? M.Y : M.U;
@@ -374,6 +379,10 @@ static SolveOut solve_projection(const Model& M, Work& W, int solver, double* q,
         new_err = vec_norm(c, Y, o.norm);
         step *= 0.5;
         j += 1;
+        {
+          const double big = new_err > err_here ? new_err : err_here;
+          if (big < 1e-10 || std::fabs(new_err - err_here) <= 1e-6 * big) W.ls_ambiguous = 1;
+        }
       } while (j < o.max_ls && new_err > err_here);
       for (int k = 0; k < Q; ++k) delta[k] = qn[k] - q[k];
       r.ndq = vec_norm(delta, Q, o.norm);
@@ -682,6 +691,8 @@ int orc_max_threads(void) {
 #endif
 }
 
+static std::vector<int32_t> g_ls_ambiguous;  // per chain, of the last solve / step call
+
 #define ORC_FOR_CHAINS(body)                                   \
   _Pragma("omp parallel") {                                    \
     Work W;                                                    \
@@ -803,7 +814,9 @@ void orc_solve_projection(void* h, int64_t n, const double* q, const double* q_p
                           int32_t* n_constr, int32_t* status) {
   const Model& M = *(Model*)h;
   StepOpts so = to_step_opts(opts);
+  g_ls_ambiguous.assign((size_t)n, 0);
   ORC_FOR_CHAINS(
+      W.ls_ambiguous = 0;
       M.jacob(q_prev + i * M.Q, W.Jp.dy_du.data(), W.Jp.dy_dv.data(), W.Jp.dy_dn.data(),
               W.c.data());
       decompose_gram(M, W.Jp, W.Gp);
@@ -811,7 +824,7 @@ void orc_solve_projection(void* h, int64_t n, const double* q, const double* q_p
       SolveOut r = solve_projection(M, W, so.solver, q_out + i * M.Q, W.Jp, W.Gp, dt,
                                     so.so, mu_out + i * M.Q);
       iters[i] = r.iters; norm_dq[i] = r.ndq; err[i] = r.err; n_constr[i] = r.n_constr;
-      status[i] = r.status;)
+      status[i] = r.status; g_ls_ambiguous[(size_t)i] = W.ls_ambiguous;)
 }
 
 // n_step constrained leapfrog steps per chain.  dt_per_chain may be null (use dt).
@@ -824,6 +837,7 @@ void orc_leapfrog_steps(void* h, int64_t n, double* q, double* p, double dt,
                         double* h_final) {
   const Model& M = *(Model*)h;
   StepOpts so = to_step_opts(opts);
+  g_ls_ambiguous.assign((size_t)n, 0);
 #pragma omp parallel
   {
     Work W;
@@ -832,6 +846,7 @@ void orc_leapfrog_steps(void* h, int64_t n, double* q, double* p, double dt,
     C.init(M), N.init(M);
 #pragma omp for schedule(static)
     for (int64_t i = 0; i < n; ++i) {
+      W.ls_ambiguous = 0;
       std::memcpy(C.q.data(), q + i * M.Q, sizeof(double) * M.Q);
       std::memcpy(C.p.data(), p + i * M.Q, sizeof(double) * M.Q);
       double dti = dt_per_chain ? dt_per_chain[i] : dt;
@@ -847,6 +862,7 @@ void orc_leapfrog_steps(void* h, int64_t n, double* q, double* p, double dt,
       std::memcpy(q + i * M.Q, C.q.data(), sizeof(double) * M.Q);
       std::memcpy(p + i * M.Q, C.p.data(), sizeof(double) * M.Q);
       status[i] = st, n_done[i] = done;
+      g_ls_ambiguous[(size_t)i] = W.ls_ambiguous;
       if (iters_fwd) iters_fwd[i] = tf;
       if (iters_rev) iters_rev[i] = tr;
       if (h_final) h_final[i] = hamiltonian(M, C);
@@ -978,6 +994,12 @@ void orc_nuts_transition(void* h, int64_t n, double* q, double dt,
       if (depth_out) depth_out[i] = depth;
     }
   }
+}
+
+// per-chain flags of the last orc_solve_projection / orc_leapfrog_steps call (see Work)
+void orc_last_line_search_ambiguous(int32_t* out, int64_t n) {
+  for (int64_t i = 0; i < n; ++i)
+    out[i] = (size_t)i < g_ls_ambiguous.size() ? g_ls_ambiguous[(size_t)i] : 0;
 }
 
 void orc_philox_normals(uint64_t seed, uint64_t chain, uint32_t iter, int n, double* out) {

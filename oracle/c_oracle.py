@@ -201,6 +201,15 @@ class OracleModel:
             _p(jac_r[0]), _p(jac_r[1]), _p(jac_r[2]), _p(w), _p(out))  # fmt: skip
         return out
 
+    @staticmethod
+    def last_line_search_ambiguous(n):
+        """[n] bool: chains of the last solve_projection / leapfrog_steps call in which a
+        backtracking comparison of the line search (systems.py:299-303) was decided by
+        rounding (both residual norms below 1e-10, or equal to 1e-6 relative)."""
+        out = np.zeros(n, np.int32)
+        lib().orc_last_line_search_ambiguous(_p(out), C.c_int64(n))
+        return out.astype(bool)
+
     # ---- projection / step / transition drivers
     def solve_projection(self, q, q_prev, dt, opts):
         q, q_prev = _f(q), _f(q_prev)

@@ -31,14 +31,19 @@ def scaled_err(a, b):
     return float((np.abs(a - b).max(1) / np.maximum(np.abs(b).max(1), 1.0)).max())
 
 
-def compare(out, ref, tol_q, tol_p, tol_h, max_edge, err=rel_err, edge_tol=1e-7):
-    """Chain-by-chain comparison; returns the fraction of edge chains."""
+def compare(out, ref, tol_q, tol_p, tol_h, max_edge, err=rel_err, edge_tol=1e-7, explained=None):
+    """Chain-by-chain comparison; returns the fraction of edge chains.  `explained`: chains
+    whose iteration path is known not to be reproducible (line search decided by rounding);
+    `max_edge` then bounds the edge chains OUTSIDE that set."""
     st, n_done = cpu(out.status), cpu(out.n_done)
     itf, itr = cpu(out.iters_fwd), cpu(out.iters_rev)
     same_it = (itf == ref["iters_fwd"]) & (itr == ref["iters_rev"])
     same_st = (st == ref["status"]) & (n_done == ref["n_done"])
     edge = ~(same_it & same_st)
-    assert edge.mean() <= max_edge, f"{edge.sum()} of {edge.size} chains differ in counts / status"
+    unexplained = edge if explained is None else edge & ~explained
+    assert unexplained.mean() <= max_edge, (
+        f"{unexplained.sum()} of {edge.size} chains differ in counts / status"
+        + ("" if explained is None else f" outside the {explained.sum()} flagged chains"))
     # an edge chain differs by at most one iteration per solve and, when both completed,
     # sits at the same point to solver tolerance
     both = edge & (st == 0) & (ref["status"] == 0)
@@ -86,13 +91,17 @@ def test_eight_schools_65536_chains_match_oracle_per_chain(par, solver):
     p = tangent_momentum(cm, q)
     dt, n_step = 0.1, 3
     ref = cm.leapfrog_steps(q, p, dt, n_step, co.solver_opts(solver))
+    # line search: a backtracking comparison |c(q + a d)| > |c(q)| decided by rounding (both
+    # norms residual noise, or equal to 1e-6 relative: flagged by the oracle) changes the
+    # halving count and can change the iteration path; measured, that moves the path of
+    # < 0.1 % of the chains, so ALL solvers are held to the same 0.5 % bound on edge chains
+    amb = cm.last_line_search_ambiguous(n) if solver == co.SOLVER_NEWTON_LS else None
     out = integrator(mlb, gs, dt, solver).steps(mlb.states.ChainState(q, p), n_step)
-    # line search: the backtracking comparison |c(q + a d)| > |c(q)| between two residuals
-    # that are both rounding noise decides the halving count, hence the iteration path
-    max_edge = 0.03 if solver == co.SOLVER_NEWTON_LS else 0.005
-    edge = compare(out, ref, TOL, TOL, TOL, max_edge)
+    edge = compare(out, ref, TOL, TOL, TOL, 0.005)
     print(f"eight-schools {par} solver {solver}: edge chains {edge:.5f}, "
-          f"failed (both) {(ref['status'] != 0).mean():.4f}")
+          f"failed (both) {(ref['status'] != 0).mean():.4f}"
+          + ("" if amb is None else f", a line-search comparison decided by rounding in "
+             f"{amb.mean():.4f} of the chains"))
 
 
 @pytest.mark.parametrize("solver", [co.SOLVER_MICI_NEWTON, co.SOLVER_MICI_QUASI_NEWTON])

@@ -132,12 +132,21 @@ def test_projection_solvers_match_oracle(kind, par, solver):
     gram = gs._decompose_gram(jac)
     q_out, mu, it, ndq, err, n_c, status = gs._solve(
         solver, q_try, jac, gram, dt, 1e-9, 1e-8, 1e10, 50, "maximum")
-    # Backtracking line search decides on |c(q + a d)| > |c(q)|: on long, wandering
-    # Newton paths (non-convex toy constraint) those comparisons amplify rounding
-    # differences chaotically, so parity is asserted on regular solves (<= 8 iterations)
-    # for that solver and on every chain for the others.
-    reg = ref["iters"] <= 8 if solver == co.SOLVER_NEWTON_LS else np.ones(len(q), bool)
-    assert reg.mean() > 0.85
+    # Backtracking line search decides on |c(q + a d)| > |c(q)|: where such a comparison is
+    # decided by rounding (both norms residual noise, or equal to 1e-6 relative - the oracle
+    # flags those chains) the halving count and, on long wandering Newton paths (non-convex
+    # toy constraint), the iteration path are not reproducible between two fp64
+    # implementations.  Parity of status and iteration count is asserted on EVERY chain
+    # outside a stated fraction of 1 % (measured: none of 513 eight-schools chains, 2 of 513
+    # toy chains; the count carrying the oracle's flag is printed).
+    reg = np.ones(len(q), bool)
+    if solver == co.SOLVER_NEWTON_LS:
+        amb = cm.last_line_search_ambiguous(len(q))
+        mism = (cpu(status) != ref["status"]) | (np.abs(cpu(it) - ref["iters"]) > 1)
+        print(f"{kind} {par} line search: {mism.sum()} of {len(q)} chains take another path, "
+              f"{(mism & ~amb).sum()} of them unflagged; flagged overall {amb.mean():.3f}")
+        assert mism.mean() <= 0.01
+        reg = ~mism
     assert (cpu(status) == ref["status"])[reg].all()
     same = same_iters(cpu(it)[reg], ref["iters"][reg])
     assert np.abs(cpu(it)[reg] - ref["iters"][reg]).max() <= 1
@@ -173,8 +182,14 @@ def test_fused_leapfrog_steps_match_oracle(kind, par, solver):
     out = integ.steps(st, n_step)
     reg = np.ones(len(q), bool)
     if solver == co.SOLVER_NEWTON_LS:  # see test_projection_solvers_match_oracle
-        reg = (ref["iters_fwd"] <= 6 * n_step) & (ref["iters_rev"] <= 6 * n_step)
-    assert reg.mean() > 0.85
+        amb = cm.last_line_search_ambiguous(len(q))
+        mism = ((cpu(out.status) != ref["status"]) | (cpu(out.n_done) != ref["n_done"])
+                | (np.abs(cpu(out.iters_fwd) - ref["iters_fwd"]) > n_step)
+                | (np.abs(cpu(out.iters_rev) - ref["iters_rev"]) > n_step))  # fmt: skip
+        print(f"{kind} {par} line search: {mism.sum()} of {len(q)} chains take another path, "
+              f"{(mism & ~amb).sum()} of them unflagged")
+        assert mism.mean() <= 0.01
+        reg = ~mism
     assert (cpu(out.status) == ref["status"])[reg].all()
     assert (cpu(out.n_done) == ref["n_done"])[reg].all()
     same = (same_iters(cpu(out.iters_fwd)[reg], ref["iters_fwd"][reg])
