@@ -25,6 +25,7 @@
 #ifndef MLB_H_
 #define MLB_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -119,12 +120,24 @@ typedef struct mlb_solver_opts {
  * the fully asynchronous single-kernel path instead (one thread per chain).  The same holds
  * for mlb_hmc_sample on those models; mlb_nuts_sample on them is always host-driven. */
 #define MLB_FLAG_SINGLE_KERNEL 1
+/* mlb_nuts_sample follows Mici 0.2.1's DynamicMultinomialHMC defaults (the sampler built
+ * at example_models/utils.py:286-288): the no-U-turn criterion is also tested on the two
+ * overlapping sub-trajectories of every merge (`do_extra_subtree_checks=True`) and a
+ * trajectory is divergent when h - h_init > max_delta_h (one-sided).  These flags switch
+ * either off / to the two-sided |h - h_init| test. */
+#define MLB_FLAG_NUTS_NO_EXTRA_SUBTREE_CHECKS 2
+#define MLB_FLAG_NUTS_TWO_SIDED_DELTA_H 4
 
 /* ---- lifecycle */
 int mlb_version(void);
 const char* mlb_last_error(void);
 int mlb_model_create(const mlb_model_desc* desc, mlb_model** out);
 void mlb_model_destroy(mlb_model* m);
+/* Scratch of the drivers (tree storage of mlb_nuts_sample, sweep scratch of the ODE and
+ * state-space kernels) is stream-ordered memory from a pool owned by the library (one per
+ * device; the host application's default pool is not touched) that keeps freed blocks
+ * cached between calls.  Hands everything above `keep_bytes` back to the driver. */
+int mlb_scratch_trim(size_t keep_bytes);
 int mlb_model_dim_u(const mlb_model* m);
 int mlb_model_dim_y(const mlb_model* m);
 int mlb_model_dim_q(const mlb_model* m); /* dim_u + dim_y (additive) / dim_u + 2 dim_y (hier) */

@@ -18,6 +18,7 @@ PARAM_UNBOUNDED, PARAM_NORMAL = 0, 1
 (SOLVER_QUASI_NEWTON, SOLVER_NEWTON, SOLVER_NEWTON_LS, SOLVER_MICI_NEWTON,
  SOLVER_MICI_QUASI_NEWTON) = range(5)  # fmt: skip
 FLAG_SINGLE_KERNEL = 1
+FLAG_NUTS_NO_EXTRA_SUBTREE_CHECKS, FLAG_NUTS_TWO_SIDED_DELTA_H = 2, 4
 NORM_MAX, NORM_EUCLIDEAN = 0, 1
 ST_OK, ST_DIVERGED, ST_NOT_CONVERGED, ST_NON_REVERSIBLE, ST_H_DIVERGED, ST_LINALG = range(6)
 ADAPT_ROWS, STAT_ROWS = 5, 8
@@ -40,7 +41,7 @@ EXPORTS = (
     "mlb_ssm_lmult_by_jacob_constr", "mlb_ssm_rmult_by_jacob_constr",
     "mlb_ssm_sv_constr_blocks", "mlb_ssm_projection_update", "mlb_ssm_band_inv_gram",
     "mlb_ssm_sv_grad_log_det_sqrt_gram",
-    "mlb_ssm_project_onto_cotangent_space",
+    "mlb_ssm_project_onto_cotangent_space", "mlb_scratch_trim",
 )  # fmt: skip
 
 
@@ -86,6 +87,7 @@ def lib():
         L.mlb_launch_count.restype = C.c_int64
         L.mlb_measure_fp64_tflops.restype = C.c_double
         L.mlb_measure_fp64_tflops.argtypes = [C.c_int32]
+        L.mlb_scratch_trim.argtypes = [C.c_size_t]
         L.mlb_philox_uniform_host.restype = C.c_double
         L.mlb_philox_uniform_host.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
         L.mlb_philox_normals_host.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int32,
@@ -102,6 +104,13 @@ def lib():
 def check(rc):
     if rc != 0:
         raise MlbError(f"libmlb error {rc}: {lib().mlb_last_error().decode()}")
+
+
+def trim_scratch(keep_bytes=0):
+    """Hand the cached scratch of the library's own memory pools (tree storage of the
+    dynamic sampler, sweep scratch of the ODE / state-space kernels) back to the driver."""
+    torch.cuda.synchronize()
+    check(lib().mlb_scratch_trim(C.c_size_t(int(keep_bytes))))
 
 
 def require_cuda():

@@ -206,6 +206,7 @@ void mlb_model_destroy(mlb_model* m) {
       if (s) cudaStreamDestroy((cudaStream_t)s);
   delete m;
 }
+int mlb_scratch_trim(size_t keep_bytes) { return scratch_trim(keep_bytes); }
 int mlb_model_dim_u(const mlb_model* m) { return m->U; }
 int mlb_model_dim_y(const mlb_model* m) { return m->Y; }
 int mlb_model_dim_q(const mlb_model* m) { return m->Q; }

@@ -261,13 +261,18 @@ template <class M, int SOLVER, bool PROJECT_FIRST, bool CHECK_H, int kStride>
 MLB_DEV TrajOut run_trajectory_ev(const typename M::Params& P, double (&qw)[M::Q],
                                   double (&pw)[M::Q], double* cq, double* cp, int n_step,
                                   double dt, const Opts& o, double max_delta_h, Eval<M>& C,
-                                  bool have_eval, bool want_h = true) {
+                                  bool have_eval, bool want_h = true,
+                                  bool project_first = true) {
   using B = typename M::B;
   constexpr int Q = M::Q;
   TrajOut t;
   t.status = MLB_ST_OK, t.done = 0, t.it_fwd = 0, t.it_rev = 0;
   t.h_init = t.h_last = nan("");
-  int sub = PROJECT_FIRST ? -1 : 0;
+  // project_first = false at run time makes a PROJECT_FIRST instantiation behave like the
+  // plain one, so that a caller needing both (the dynamic sampler: momentum refresh, then
+  // single steps) has ONE copy of the step code instead of two (instruction cache)
+  const bool lead = PROJECT_FIRST && project_first;
+  int sub = lead ? -1 : 0;
   bool first = true;
   // Interior step boundaries (kFuseKicks): the closing half kick + projection of step s and
   // the opening half kick + projection of step s + 1 act at the same point, and the
@@ -288,13 +293,13 @@ MLB_DEV TrajOut run_trajectory_ev(const typename M::Params& P, double (&qw)[M::Q
       const bool want_val =
           want_h && (first || CHECK_H || !kFuseKicks || t.done + 1 >= n_step);
       const bool ok = (first && have_eval) ? C.G.ok : evaluate_at<M>(P, qw, C, want_val);
-      if (first && !PROJECT_FIRST) t.h_init = t.h_last = hamiltonian<M>(C, pw);
+      if (first && !lead) t.h_init = t.h_last = hamiltonian<M>(C, pw);
       first = false;
       if (!ok) {
         t.status = MLB_ST_LINALG;
         break;
       }
-      if (!PROJECT_FIRST && n_step <= 0) break;
+      if (!lead && n_step <= 0) break;
     }
     const bool fuse = kFuseKicks && sub == 2 && t.done + 1 < n_step;
     if (fuse) {

@@ -45,6 +45,16 @@ namespace mlb {
 std::string& last_error();           // thread-local, defined in mlb_api.cu
 std::atomic<int64_t>& launch_count();  // defined in mlb_api.cu
 #define g_err (::mlb::last_error())
+
+// Stream-ordered scratch (tree storage, sweep scratch of the ODE / state-space kernels)
+// comes from a memory pool OWNED BY THE LIBRARY, one per device, whose release threshold is
+// unlimited so that freed blocks stay cached between calls: with the default threshold a
+// host loop that synchronises once per round paid for a fresh physical allocation of
+// several hundred MB every round.  The process-wide default pool of the host application
+// (torch's allocator sits next to it) is left untouched; mlb_scratch_trim() hands the
+// cached memory back.  Defined in mlb_linalg.cu.
+cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t s);
+int scratch_trim(size_t keep_bytes);
 #define g_launches (::mlb::launch_count())
 
 #define MLB_CUDA_OK(expr)                                                       \
@@ -729,12 +739,20 @@ struct Launch {
     NutsArgs na = na0;
     na.lds = (n + 31) / 32 * 32;
     const size_t bytes = sizeof(double) * (size_t)NutsRows<M::Q>::total(na.max_depth) * (size_t)na.lds;
-    if (cudaMallocAsync((void**)&na.scratch, bytes, s) != cudaSuccess) {
+    if (scratch_alloc((void**)&na.scratch, bytes, s) != cudaSuccess) {
       g_err = "tree scratch allocation failed";
       return (int)MLB_ERR_CUDA;
     }
     const int rc = dispatch_solver(solver, [&]<int S>() {
-      k_nuts_sample<M, S><<<grid_for(n), kBlock, 0, s>>>(P(m), n, ld, q, o, a, na);
+      constexpr int smem = nuts_smem_bytes<M>();
+      static const bool configured =
+          cudaFuncSetAttribute(k_nuts_sample<M, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               smem) == cudaSuccess;
+      if (!configured) {
+        g_err = "shared-memory configuration of the dynamic sampler failed";
+        return (int)MLB_ERR_CUDA;
+      }
+      k_nuts_sample<M, S><<<grid_for(n), kBlock, smem, s>>>(P(m), n, ld, q, o, a, na);
       return finish_launch();
     });
     cudaFreeAsync(na.scratch, s);

@@ -23,23 +23,44 @@ namespace mlb {
 // per kPre steps instead of once per step.
 constexpr int kPre = 16;
 
-// Keep freed scratch cached in the device's default memory pool: with the default release
-// threshold (0) the pool returns its memory to the driver at the next synchronisation, and
-// a host loop that synchronises once per round (the projection loops of mlb_ssm.cu) pays
-// for a fresh physical allocation of several hundred MB every round.  Also used by
-// mlb_ssm.cu.
-void keep_default_pool_cached() {
-  static const bool done = [] {
-    int dev = 0;
-    cudaMemPool_t pool;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+// The library's own scratch pools (see mlb_launch.cuh), created on first use per device.
+namespace {
+constexpr int kMaxDevices = 64;
+std::mutex g_pool_mutex;
+cudaMemPool_t g_pools[kMaxDevices] = {};
+}  // namespace
+
+cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t s) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+  cudaMemPool_t pool;
+  {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (!g_pools[dev]) {
+      cudaMemPoolProps props = {};
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = dev;
+      if ((e = cudaMemPoolCreate(&g_pools[dev], &props)) != cudaSuccess) {
+        g_pools[dev] = nullptr;
+        return e;
+      }
       uint64_t thr = UINT64_MAX;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+      cudaMemPoolSetAttribute(g_pools[dev], cudaMemPoolAttrReleaseThreshold, &thr);
     }
-    return true;
-  }();
-  (void)done;
+    pool = g_pools[dev];
+  }
+  return cudaMallocFromPoolAsync(p, bytes, pool, s);
+}
+
+int scratch_trim(size_t keep_bytes) {
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  for (int d = 0; d < kMaxDevices; ++d)
+    if (g_pools[d] && cudaMemPoolTrimTo(g_pools[d], keep_bytes) != cudaSuccess) return MLB_ERR_CUDA;
+  return MLB_OK;
 }
 
 // forward elimination of mlift/linalg.py:67-75: w_i = a_{i-1} / b'_{i-1},
@@ -225,15 +246,14 @@ int mlb_tridiagonal_solve(int64_t n, int32_t dim, int32_t n_rhs, int64_t ld, con
   const int64_t ldf = (n + 31) / 32 * 32;
   double* fac = nullptr;
   const unsigned g = (unsigned)((n + 127) / 128);
-  keep_default_pool_cached();
   if (n_rhs == 1) {
-    MLB_CUDA_OK(cudaMallocAsync((void**)&fac, sizeof(double) * (size_t)dim * (size_t)ldf, s));
+    MLB_CUDA_OK(scratch_alloc((void**)&fac, sizeof(double) * (size_t)dim * (size_t)ldf, s));
     k_tridiag_solve_one<<<g, 128, 0, s>>>(n, dim, ld, a, b, c, d, x, fac, ldf);
     const int rc1 = finish_launch();
     cudaFreeAsync(fac, s);
     return rc1;
   }
-  MLB_CUDA_OK(cudaMallocAsync((void**)&fac, sizeof(double) * (size_t)(2 * dim) * (size_t)ldf, s));
+  MLB_CUDA_OK(scratch_alloc((void**)&fac, sizeof(double) * (size_t)(2 * dim) * (size_t)ldf, s));
   k_tridiag_factor<<<g, 128, 0, s>>>(n, dim, ld, a, b, c, fac, ldf);
   int rc = finish_launch();
   if (rc == MLB_OK) {

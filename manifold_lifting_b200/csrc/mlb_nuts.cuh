@@ -36,13 +36,25 @@ MLB_DEV double log_add_exp(double a, double b) {
   return m + log(exp(a - m) + exp(b - m));
 }
 
-// rows of the per-chain scratch column
+// log(exp(a) + exp(b)) and the share of b in it, exp(b) / (exp(a) + exp(b)): the weight of a
+// merged tree and the probability that its proposal comes from the part with log weight b
+MLB_DEV double log_add_exp_share(double a, double b, double& share_b) {
+  const double m = a > b ? a : b;
+  const double ea = exp(a - m), eb = exp(b - m), s = ea + eb;
+  share_b = eb / s;
+  return m + log(s);
+}
+
+// rows of the per-chain scratch column: tree edges (negative / positive time direction),
+// summed momentum, proposal, then per level the pending left sibling - first-built and
+// last-built momentum, summed momentum, proposal
 template <int Q>
 struct NutsRows {
   static constexpr int EN_Q = 0, EN_P = Q, EP_Q = 2 * Q, EP_P = 3 * Q, RHO = 4 * Q,
-                       NEXT = 5 * Q, CUR = 6 * Q, SLOT = 9 * Q;  // CUR / slot: PF, RH, PR
-  static __host__ __device__ constexpr int slot(int lvl) { return SLOT + 3 * Q * lvl; }
-  static __host__ __device__ constexpr int lw(int max_depth) { return SLOT + 3 * Q * max_depth; }
+                       NEXT = 5 * Q, SLOT = 6 * Q;
+  static constexpr int PF = 0, PL = Q, RH = 2 * Q, PR = 3 * Q, SLOT_ROWS = 4 * Q;
+  static __host__ __device__ constexpr int slot(int lvl) { return SLOT + SLOT_ROWS * lvl; }
+  static __host__ __device__ constexpr int lw(int max_depth) { return SLOT + SLOT_ROWS * max_depth; }
   static __host__ __device__ constexpr int total(int max_depth) { return lw(max_depth) + max_depth; }
 };
 
@@ -54,25 +66,53 @@ struct NutsArgs {
   int32_t* trace_depth;   // [n_iter][n] or NULL
 };
 
+// No-U-turn tests when the subtree built first (inner: first-built momentum pf_i, last-built
+// pl_i, summed rh_i) is joined by the one built after it (outer: pf_o, pl_o, rh_o), both in
+// build order, so the same expressions serve either time direction: the criterion on the
+// merged tree (its two edges against the total), and - Mici's `do_extra_subtree_checks`,
+// default on - on the two overlapping sub-trajectories "inner + first state of outer" and
+// "last state of inner + outer".
+struct UTurn {
+  double d1 = 0.0, d2 = 0.0, e1a = 0.0, e1b = 0.0, e2a = 0.0, e2b = 0.0;
+  MLB_DEV void add(double pf_i, double pl_i, double rh_i, double pf_o, double pl_o,
+                   double rh_o, double rho) {
+    d1 = fma(pf_i, rho, d1), d2 = fma(pl_o, rho, d2);
+    const double r1 = rh_i + pf_o, r2 = rh_o + pl_i;
+    e1a = fma(pf_i, r1, e1a), e1b = fma(pf_o, r1, e1b);
+    e2a = fma(pl_i, r2, e2a), e2b = fma(pl_o, r2, e2b);
+  }
+  MLB_DEV bool turned(bool extra) const {
+    return d1 < 0.0 || d2 < 0.0 ||
+           (extra && (e1a < 0.0 || e1b < 0.0 || e2a < 0.0 || e2b < 0.0));
+  }
+};
+
+// Shared memory (dynamic, 5 Q doubles per thread, element k of a column at [k * kBlock]):
+// the last committed (q, p) of the step code and the subtree under construction.  All tree
+// bookkeeping runs as ROLLED loops over these columns and the global scratch column - no
+// register arrays, a few hundred instructions of code.
+template <class M>
+constexpr int nuts_smem_bytes() {
+  return (int)sizeof(double) * 5 * M::Q * kBlock;
+}
+
 template <class M, int SOLVER>
 __global__ void __launch_bounds__(kBlock, MLB_LF_MIN_BLOCKS)
     k_nuts_sample(const __grid_constant__ typename M::Params P, int64_t n, int64_t ld, double* q,
                   Opts o, SampleArgs a, NutsArgs na) {
   constexpr int Q = M::Q;
   using R = NutsRows<Q>;
-  __shared__ double commit[2 * Q][kBlock];
+  extern __shared__ double nuts_smem[];
   MLB_CHAIN_INDEX();
+  double* const cq = nuts_smem + threadIdx.x;  // committed position
+  double* const cp = cq + Q * kBlock;          // committed momentum
+  double* const cur = cq + 2 * Q * kBlock;     // subtree under construction: PF, RH, PR
   double* const sc = na.scratch + i;
   const int64_t lds = na.lds;
+  const bool extra = !(o.flags & MLB_FLAG_NUTS_NO_EXTRA_SUBTREE_CHECKS);
+  const bool two_sided = (o.flags & MLB_FLAG_NUTS_TWO_SIDED_DELTA_H) != 0;
 #define SC(row) sc[(int64_t)(row) * lds]
-  double ad_iter = 0, ad_smooth = 0, ad_err = 0, ad_target = 0, dti = a.dt;
-  if (a.adapt) {
-    ad_iter = a.adapt[0 * ld + i], ad_smooth = a.adapt[1 * ld + i];
-    ad_err = a.adapt[2 * ld + i], ad_target = a.adapt[3 * ld + i];
-    dti = a.adapt[4 * ld + i];
-  }
-  double s_acc = 0, s_moved = 0, s_conv = 0, s_nonrev = 0, s_hdiv = 0, s_steps = 0, s_its = 0,
-         s_depth = 0;
+  double dti = a.adapt ? a.adapt[4 * ld + i] : a.dt;
   int last = MLB_ST_OK;
 #pragma unroll 1
   for (int it = 0; it < a.n_iter; ++it) {
@@ -80,98 +120,137 @@ __global__ void __launch_bounds__(kBlock, MLB_LF_MIN_BLOCKS)
     const uint64_t chain = a.chain0 + (uint64_t)i;
     uint32_t kdraw = 1;
     auto draw = [&]() { return philox_uniform_k(a.seed, chain, iter, kdraw++); };
-    double qw[Q], pw[Q];
-    load_vec<Q>(qw, q, ld, i);
+    // start of the transition in the committed columns: position, momentum noise
     if (a.mom_noise) {
-      load_vec<Q>(pw, a.mom_noise + (int64_t)it * Q * ld, ld, i);
+      const double* mn = a.mom_noise + (int64_t)it * Q * ld + i;
+#pragma unroll 1
+      for (int k = 0; k < Q; ++k) cp[k * kBlock] = mn[(int64_t)k * ld];
     } else {
-      double* col = &commit[Q][threadIdx.x];
 #pragma unroll 1
       for (int j = 0; 2 * j < Q; ++j) {
         double n0, n1;
         philox_normal_pair(a.seed, chain, iter, (uint32_t)j, n0, n1);
-        col[(2 * j) * kBlock] = n0;
-        if (2 * j + 1 < Q) col[(2 * j + 1) * kBlock] = n1;
+        cp[(2 * j) * kBlock] = n0;
+        if (2 * j + 1 < Q) cp[(2 * j + 1) * kBlock] = n1;
       }
-#pragma unroll
-      for (int k = 0; k < Q; ++k) pw[k] = col[k * kBlock];
     }
-    // momentum refresh: project onto the cotangent space, h_init (no step); C keeps the
-    // evaluation at the point the next step starts from (see run_trajectory_ev)
-    Eval<M> C;
-    const TrajOut t0 = run_trajectory_ev<M, SOLVER, true, false, kBlock>(
-        P, qw, pw, &commit[0][threadIdx.x], &commit[Q][threadIdx.x], 0, dti, o, 0.0, C, false);
-    bool have_eval = t0.status == MLB_ST_OK;  // both edges of the one-state tree are here
-    int last_dir = 0;
-    int st = t0.status;
-    const double h0 = t0.h_init;
 #pragma unroll 1
-    for (int k = 0; k < Q; ++k) {
-      SC(R::EN_Q + k) = qw[k], SC(R::EP_Q + k) = qw[k], SC(R::NEXT + k) = qw[k];
-      SC(R::EN_P + k) = pw[k], SC(R::EP_P + k) = pw[k], SC(R::RHO + k) = pw[k];
-    }
-    double lw_tree = 0.0, sum_acc = 0.0;
+    for (int k = 0; k < Q; ++k) cq[k * kBlock] = q[(int64_t)k * ld + i];
+    // ONE call site of the step code serves the momentum refresh (leading pass: projection
+    // onto the cotangent space and h_init, no step) and every tree leaf: with two inlined
+    // copies the kernel was 135 KB of SASS and ncu showed 4.3 stall cycles per issue waiting
+    // for instructions (profiles/r6a_full_k_nuts_sample_hier.md).  C keeps the evaluation
+    // at the point the next step starts from (see run_trajectory_ev).
+    Eval<M> C;
+    bool refresh = true, have_eval = false, moved = false, active = true;
+    int last_dir = 0, st = MLB_ST_OK;
+    double h0 = 0.0, lw_tree = 0.0, sum_acc = 0.0, lw0 = 0.0;
     int depth = 0, leaf = 0, dir = 1, n_leaf = 0, its = 0;
-    bool moved = false;
-    bool active = st == MLB_ST_OK && na.max_depth > 0;
 #pragma unroll 1
     while (active) {
-      if (leaf == 0) {  // new doubling: direction, start from that edge of the tree
+      double qw[Q], pw[Q];
+      if (!refresh && leaf == 0) {  // new doubling: direction, start from that edge of the tree
         dir = draw() < 0.5 ? 1 : -1;
         if (last_dir != 0 && dir != last_dir) have_eval = false;  // C sits at the other edge
-        const int eq = dir > 0 ? R::EP_Q : R::EN_Q, ep = dir > 0 ? R::EP_P : R::EN_P;
-#pragma unroll 1
-        for (int k = 0; k < Q; ++k) qw[k] = SC(eq + k), pw[k] = SC(ep + k);
+        const double* eq = &SC(dir > 0 ? R::EP_Q : R::EN_Q);
+        const double* ep = &SC(dir > 0 ? R::EP_P : R::EN_P);
+#pragma unroll
+        for (int k = 0; k < Q; ++k) qw[k] = eq[(int64_t)k * lds], pw[k] = ep[(int64_t)k * lds];
+      } else {  // continue from the last committed state
+#pragma unroll
+        for (int k = 0; k < Q; ++k) qw[k] = cq[k * kBlock], pw[k] = cp[k * kBlock];
       }
-      const TrajOut t = run_trajectory_ev<M, SOLVER, false, false, kBlock>(
-          P, qw, pw, &commit[0][threadIdx.x], &commit[Q][threadIdx.x], 1, dir * dti, o, 0.0, C,
-          have_eval);
-      have_eval = t.status == MLB_ST_OK, last_dir = dir;
+      const TrajOut t = run_trajectory_ev<M, SOLVER, true, false, kBlock>(
+          P, qw, pw, cq, cp, refresh ? 0 : 1, refresh ? dti : dir * dti, o, 0.0, C,
+          !refresh && have_eval, true, refresh);
+      have_eval = t.status == MLB_ST_OK;
+      if (refresh) {  // the tree is the single state (q, projected p)
+        refresh = false;
+        st = t.status, h0 = t.h_init;
+#pragma unroll 1
+        for (int k = 0; k < Q; ++k) {
+          const double qk = cq[k * kBlock], pk = cp[k * kBlock];
+          SC(R::EN_Q + k) = qk, SC(R::EP_Q + k) = qk, SC(R::NEXT + k) = qk;
+          SC(R::EN_P + k) = pk, SC(R::EP_P + k) = pk, SC(R::RHO + k) = pk;
+        }
+        active = st == MLB_ST_OK && na.max_depth > 0;
+        continue;
+      }
+      last_dir = dir;
       n_leaf += 1;
       its += t.it_fwd + t.it_rev;
       bool terminate = false;
       const double h = t.h_last;
+      double lw_cur = h0 - h;  // log weight of the subtree under construction
       if (t.status != MLB_ST_OK) {
         st = t.status, terminate = true;
-      } else if (h != h || fabs(h - h0) > a.max_delta_h) {
+      } else if (h != h || h - h0 > a.max_delta_h || (two_sided && h0 - h > a.max_delta_h)) {
         st = MLB_ST_H_DIVERGED, terminate = true;
       }
       if (!terminate) {
-        double lw_cur = h0 - h;
         sum_acc += exp(lw_cur < 0.0 ? lw_cur : 0.0);
-        // the leaf as a one-state subtree, in registers: it is born after the step and
-        // parked before the next one, so it never competes with the step for registers
-        // (the first version kept it in global scratch: 160 GB of DRAM writes per launch
-        // and 5.3 long-scoreboard stall cycles per issue)
-        double c_pf[Q], c_rh[Q], c_pr[Q];
-#pragma unroll
-        for (int k = 0; k < Q; ++k) c_pf[k] = pw[k], c_rh[k] = pw[k], c_pr[k] = qw[k];
+        // The leaf is the committed state (cq, cp).  Level 0 never leaves shared memory: an
+        // even leaf waits in `cur` as the pending sibling of the odd leaf that follows it
+        // (one state: first = last = summed momentum, proposal = its position), and their
+        // merge reads both from shared memory.  Only the pending siblings of levels >= 1
+        // live in the global scratch column, and a subtree that is complete is joined to
+        // the tree straight from `cur`.
         int lvl = 0;
-#pragma unroll 1
-        while ((leaf >> lvl) & 1) {  // a left sibling waits at this level: merge
-          const int sl = R::slot(lvl);
-          const double lw_left = SC(R::lw(na.max_depth) + lvl);
-          const double lw_new = log_add_exp(lw_left, lw_cur);
-          const bool take_outer = draw() < exp(lw_cur - lw_new);
-          double d_first = 0.0, d_last = 0.0;
-#pragma unroll
+        if (leaf & 1) {
+          double share;
+          lw_cur = log_add_exp_share(lw0, lw_cur, share);
+          const bool take_outer = draw() < share;
+          UTurn ut;
+#pragma unroll 2
           for (int k = 0; k < Q; ++k) {
-            c_rh[k] += SC(sl + Q + k), c_pf[k] = SC(sl + k);
-            if (!take_outer) c_pr[k] = SC(sl + 2 * Q + k);
-            d_first = fma(c_pf[k], c_rh[k], d_first), d_last = fma(pw[k], c_rh[k], d_last);
+            const double p_i = cur[k * kBlock], p_o = cp[k * kBlock], rho = p_i + p_o;
+            ut.add(p_i, p_i, p_i, p_o, p_o, p_o, rho);
+            cur[(Q + k) * kBlock] = rho;
+            if (take_outer) cur[(2 * Q + k) * kBlock] = cq[k * kBlock];
           }
-          lw_cur = lw_new;
-          if (d_first < 0.0 || d_last < 0.0) {
-            terminate = true;
-            break;
+          terminate = ut.turned(extra);
+          lvl = 1;
+        } else {
+          lw0 = lw_cur;
+#pragma unroll 2
+          for (int k = 0; k < Q; ++k) {
+            const double pk = cp[k * kBlock];
+            cur[k * kBlock] = pk, cur[(Q + k) * kBlock] = pk;
+            cur[(2 * Q + k) * kBlock] = cq[k * kBlock];
           }
+        }
+#pragma unroll 1
+        while (!terminate && ((leaf >> lvl) & 1)) {  // a left sibling waits at this level: merge
+          const double* sl = &SC(R::slot(lvl));
+          double share;
+          lw_cur = log_add_exp_share(SC(R::lw(na.max_depth) + lvl), lw_cur, share);
+          const bool take_outer = draw() < share;
+          UTurn ut;
+          // (unrolled by 6: the loads of six components are in flight together - rolled, every
+          // component paid its own L2 / DRAM round trip, 40 % of the kernel's memory stalls)
+#pragma unroll 6
+          for (int k = 0; k < Q; ++k) {
+            const double pf_i = sl[(int64_t)(R::PF + k) * lds], pl_i = sl[(int64_t)(R::PL + k) * lds];
+            const double rh_i = sl[(int64_t)(R::RH + k) * lds];
+            const double pr_i = sl[(int64_t)(R::PR + k) * lds];
+            const double pf_o = cur[k * kBlock], rh_o = cur[(Q + k) * kBlock];
+            const double rho = rh_i + rh_o;
+            ut.add(pf_i, pl_i, rh_i, pf_o, cp[k * kBlock], rh_o, rho);
+            cur[k * kBlock] = pf_i, cur[(Q + k) * kBlock] = rho;
+            if (!take_outer) cur[(2 * Q + k) * kBlock] = pr_i;
+          }
+          terminate = ut.turned(extra);
           ++lvl;
         }
-        if (!terminate) {  // park as the pending sibling of level lvl (= depth: complete)
-          const int sl = R::slot(lvl);
-#pragma unroll
-          for (int k = 0; k < Q; ++k)
-            SC(sl + k) = c_pf[k], SC(sl + Q + k) = c_rh[k], SC(sl + 2 * Q + k) = c_pr[k];
+        if (!terminate && lvl >= 1 && lvl < depth) {  // park as the pending sibling of level lvl
+          double* sl = &SC(R::slot(lvl));
+#pragma unroll 2
+          for (int k = 0; k < Q; ++k) {
+            sl[(int64_t)(R::PF + k) * lds] = cur[k * kBlock];
+            sl[(int64_t)(R::PL + k) * lds] = cp[k * kBlock];
+            sl[(int64_t)(R::RH + k) * lds] = cur[(Q + k) * kBlock];
+            sl[(int64_t)(R::PR + k) * lds] = cur[(2 * Q + k) * kBlock];
+          }
           SC(R::lw(na.max_depth) + lvl) = lw_cur;
         }
       }
@@ -179,65 +258,68 @@ __global__ void __launch_bounds__(kBlock, MLB_LF_MIN_BLOCKS)
       if (terminate) {
         active = false;
       } else if (leaf == (1 << depth)) {  // new subtree complete: join it to the tree
-        const int sl = R::slot(depth);
-        const double lw_sub = SC(R::lw(na.max_depth) + depth);
-        const bool take = draw() < exp(lw_sub - lw_tree);
-        lw_tree = log_add_exp(lw_tree, lw_sub);
-        const int eq = dir > 0 ? R::EP_Q : R::EN_Q, ep = dir > 0 ? R::EP_P : R::EN_P;
+        // (inner = the tree so far: first-built = its far edge, last-built = the edge the
+        // subtree grew from; outer = the subtree, whose last state is the committed one)
+        // (biased progressive sampling: the new subtree's proposal with min(1, w_sub / w_tree))
+        const bool take = draw() < exp(lw_cur - lw_tree);
+        double share;
+        lw_tree = log_add_exp_share(lw_tree, lw_cur, share);
         moved |= take;
-#pragma unroll 1
+        double* eq = &SC(dir > 0 ? R::EP_Q : R::EN_Q);
+        double* ep = &SC(dir > 0 ? R::EP_P : R::EN_P);
+        const double* fp = &SC(dir > 0 ? R::EN_P : R::EP_P);
+        UTurn ut;
+#pragma unroll 6
         for (int k = 0; k < Q; ++k) {
-          if (take) SC(R::NEXT + k) = SC(sl + 2 * Q + k);
-          SC(R::RHO + k) += SC(sl + Q + k);
-          SC(eq + k) = qw[k], SC(ep + k) = pw[k];
-        }
-        double d_neg = 0.0, d_pos = 0.0;
-#pragma unroll 1
-        for (int k = 0; k < Q; ++k) {
-          const double rho = SC(R::RHO + k);
-          d_neg = fma(SC(R::EN_P + k), rho, d_neg), d_pos = fma(SC(R::EP_P + k), rho, d_pos);
+          const double rh_i = SC(R::RHO + k), rh_o = cur[(Q + k) * kBlock];
+          const double pl_o = cp[k * kBlock], rho = rh_i + rh_o;
+          ut.add(fp[(int64_t)k * lds], ep[(int64_t)k * lds], rh_i, cur[k * kBlock], pl_o, rh_o, rho);
+          if (take) SC(R::NEXT + k) = cur[(2 * Q + k) * kBlock];
+          SC(R::RHO + k) = rho;
+          eq[(int64_t)k * lds] = cq[k * kBlock], ep[(int64_t)k * lds] = pl_o;
         }
         ++depth, leaf = 0;
-        if (d_neg < 0.0 || d_pos < 0.0 || depth >= na.max_depth) active = false;
+        if (ut.turned(extra) || depth >= na.max_depth) active = false;
       }
     }
     const double a_stat = n_leaf > 0 ? sum_acc / n_leaf : 0.0;
-#pragma unroll 1
-    for (int k = 0; k < Q; ++k) q[(int64_t)k * ld + i] = SC(R::NEXT + k);
-    s_acc += a_stat, s_moved += moved, s_steps += n_leaf, s_its += its, s_depth += depth;
-    s_conv += (st == MLB_ST_DIVERGED || st == MLB_ST_NOT_CONVERGED || st == MLB_ST_LINALG);
-    s_nonrev += (st == MLB_ST_NON_REVERSIBLE);
-    s_hdiv += (st == MLB_ST_H_DIVERGED);
+    const bool tr = a.trace_q && (it + 1) % a.trace_every == 0;
+    double* tq = tr ? a.trace_q + (int64_t)((it + 1) / a.trace_every - 1) * a.trace_dim * ld + i
+                    : nullptr;
+#pragma unroll 6
+    for (int k = 0; k < Q; ++k) {
+      const double v = SC(R::NEXT + k);
+      q[(int64_t)k * ld + i] = v;
+      if (tr && k < a.trace_dim) tq[(int64_t)k * ld] = v;
+    }
     last = st;
+    if (a.stats) {  // accumulated in global memory: eight fewer live doubles in the tree loop
+      a.stats[0 * ld + i] += a_stat, a.stats[1 * ld + i] += moved;
+      a.stats[2 * ld + i] +=
+          (st == MLB_ST_DIVERGED || st == MLB_ST_NOT_CONVERGED || st == MLB_ST_LINALG);
+      a.stats[3 * ld + i] += (st == MLB_ST_NON_REVERSIBLE);
+      a.stats[4 * ld + i] += (st == MLB_ST_H_DIVERGED);
+      a.stats[5 * ld + i] += n_leaf, a.stats[6 * ld + i] += its, a.stats[7 * ld + i] += depth;
+    }
     if (a.trace_accept) a.trace_accept[(int64_t)it * ld + i] = a_stat;
     if (na.trace_n_step) na.trace_n_step[(int64_t)it * ld + i] = n_leaf;
     if (na.trace_depth) na.trace_depth[(int64_t)it * ld + i] = depth;
-    if (a.trace_q && (it + 1) % a.trace_every == 0) {
-      double* tq = a.trace_q + (int64_t)((it + 1) / a.trace_every - 1) * a.trace_dim * ld + i;
-#pragma unroll 1
-      for (int k = 0; k < a.trace_dim; ++k) tq[(int64_t)k * ld] = SC(R::NEXT + k);
-    }
     if (a.adapt) {  // Mici DualAveragingStepSizeAdapter.update
+      double ad_iter = a.adapt[0 * ld + i], ad_smooth = a.adapt[1 * ld + i];
+      double ad_err = a.adapt[2 * ld + i];
+      const double ad_target = a.adapt[3 * ld + i];
       ad_iter += 1;
       const double w = 1.0 / (a.a_offset + ad_iter);
       ad_err = (1.0 - w) * ad_err + w * (a.a_target - a_stat);
-      const double sw = pow(1.0 / ad_iter, a.a_decay);
+      const double sw = exp(-a.a_decay * log(ad_iter));  // (1 / iter)^decay
       const double log_eps = ad_target - ad_err * sqrt(ad_iter) / a.a_reg;
       ad_smooth = (1.0 - sw) * ad_smooth + sw * log_eps;
       dti = exp(log_eps);
+      a.adapt[0 * ld + i] = ad_iter, a.adapt[1 * ld + i] = ad_smooth;
+      a.adapt[2 * ld + i] = ad_err, a.adapt[4 * ld + i] = dti;
     }
   }
 #undef SC
-  if (a.adapt) {
-    a.adapt[0 * ld + i] = ad_iter, a.adapt[1 * ld + i] = ad_smooth;
-    a.adapt[2 * ld + i] = ad_err, a.adapt[4 * ld + i] = dti;
-  }
-  if (a.stats) {
-    a.stats[0 * ld + i] += s_acc, a.stats[1 * ld + i] += s_moved;
-    a.stats[2 * ld + i] += s_conv, a.stats[3 * ld + i] += s_nonrev;
-    a.stats[4 * ld + i] += s_hdiv, a.stats[5 * ld + i] += s_steps;
-    a.stats[6 * ld + i] += s_its, a.stats[7 * ld + i] += s_depth;
-  }
   if (a.last_status) a.last_status[i] = last;
 }
 

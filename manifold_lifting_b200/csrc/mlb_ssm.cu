@@ -30,7 +30,6 @@
 
 namespace mlb {
 
-void keep_default_pool_cached();  // mlb_linalg.cu
 
 struct SsmBlocks {
   const double *du, *dv, *n0, *n1, *dxdy;
@@ -352,8 +351,13 @@ __global__ void __launch_bounds__(128)
     for (int j = 0; j < P; j += 2) {
       // a non-positive pivot (matrix not positive definite) must give NaN, also in a pair
       const bool bad = piv[j] <= 0.0 || piv[j + 1] <= 0.0;
-      st += log(bad ? -1.0 : piv[j] * piv[j + 1]);
-      sx += log(xv[j] * xv[j + 1]);
+      // one logarithm per pair; a product that leaves the normal range (pivots or |dx_dy|
+      // around 1e+-160) falls back to the sum of the two logarithms, which stays finite as
+      // the reference's per-term recursion does (linalg.py:104-114)
+      const double pp = piv[j] * piv[j + 1], xx = xv[j] * xv[j + 1];
+      const bool pn = pp >= 2.3e-308 && pp <= 1.7e308, xn = xx >= 2.3e-308 && xx <= 1.7e308;
+      st += bad ? log(-1.0) : (pn ? log(pp) : log(piv[j]) + log(piv[j + 1]));
+      sx += xn ? log(xx) : log(xv[j]) + log(xv[j + 1]);
     }
   }
   double sc = 0.0;
@@ -714,8 +718,7 @@ struct Scratch {
   cudaStream_t s;
   int alloc(size_t rows, int64_t ld, cudaStream_t st) {
     s = st;
-    keep_default_pool_cached();
-    MLB_CUDA_OK(cudaMallocAsync((void**)&p, sizeof(double) * rows * (size_t)ld, st));
+    MLB_CUDA_OK(scratch_alloc((void**)&p, sizeof(double) * rows * (size_t)ld, st));
     return MLB_OK;
   }
   ~Scratch() {
@@ -886,8 +889,7 @@ int mlb_ssm_projection_update(int64_t n, int32_t dim_q, int32_t dim_y, int64_t l
   if (n == 0) return MLB_OK;
   cudaStream_t s = (cudaStream_t)stream;
   unsigned long long* mx = nullptr;  // [2][n] partial maxima
-  keep_default_pool_cached();
-  MLB_CUDA_OK(cudaMallocAsync((void**)&mx, sizeof(unsigned long long) * 2 * (size_t)n, s));
+  MLB_CUDA_OK(scratch_alloc((void**)&mx, sizeof(unsigned long long) * 2 * (size_t)n, s));
   MLB_CUDA_OK(cudaMemsetAsync(mx, 0, sizeof(unsigned long long) * 2 * (size_t)n, s));
   const unsigned g = (unsigned)((n + 127) / 128);
   k_ssm_projection_apply<<<dim3(g, (unsigned)((dim_q + kUpdRows - 1) / kUpdRows)), 128, 0, s>>>(

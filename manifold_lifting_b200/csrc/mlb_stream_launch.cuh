@@ -320,22 +320,8 @@ struct ScratchBuf {  // stream-ordered scratch allocation
   cudaStream_t s;
   int alloc(int64_t rows, int64_t lds, cudaStream_t stream) {
     s = stream;
-    // keep freed scratch cached in the device's default pool: with the default release
-    // threshold (0) the pool hands its memory back to the driver at the next
-    // synchronisation and every call pays for a fresh physical allocation of several
-    // hundred MB (measured: 22 ms -> seconds-scale jitter on the host entry point)
-    static const bool keep = [] {
-      int dev = 0;
-      cudaMemPool_t pool;
-      if (cudaGetDevice(&dev) == cudaSuccess &&
-          cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        uint64_t thr = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-      }
-      return true;
-    }();
-    (void)keep;
-    cudaError_t e = cudaMallocAsync((void**)&p, sizeof(double) * (size_t)rows * (size_t)lds, s);
+    // (library-owned pool whose freed blocks stay cached: mlb_launch.cuh)
+    cudaError_t e = scratch_alloc((void**)&p, sizeof(double) * (size_t)rows * (size_t)lds, s);
     if (e != cudaSuccess) {
       g_err = std::string("scratch allocation: ") + cudaGetErrorString(e);
       p = nullptr;

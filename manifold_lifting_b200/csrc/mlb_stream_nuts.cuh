@@ -8,7 +8,8 @@
 // bookkeeping of a round is one small kernel per chain batch and the host reads one
 // integer per round (chains still growing).  Per-chain tree storage is a column of global
 // scratch: edges, summed momentum, proposal, working state and one pending sibling per
-// level - (8 + 3 D) Q doubles.
+// level (first-built and last-built momentum, summed momentum, proposal) - (8 + 4 D) Q
+// doubles.
 #pragma once
 #include "mlb_stream_phased.cuh"  // (brings in mlb_launch.cuh and, through it, mlb_nuts.cuh)
 
@@ -22,12 +23,12 @@ struct SNutsLayout {
   enum { EN_Q, EN_P, EP_Q, EP_P, RHO, NEXT, WQ, WP, N_FIXED };
   __host__ __device__ double* blk(int b) const { return base + (int64_t)b * Q * lds; }
   __host__ __device__ double* slot(int lvl, int part) const {
-    return base + ((int64_t)(N_FIXED + 3 * lvl + part) * Q) * lds;
+    return base + ((int64_t)(N_FIXED + 4 * lvl + part) * Q) * lds;  // part: PF, PL, RH, PR
   }
   // per-chain doubles: h0, lw_tree, sum_acc, dt (signed, this round), dt0, h_init, h_final, lw[D]
   enum { H0, LW_TREE, SUM_ACC, DT, DT0, H_INIT, H_FINAL, N_DBL };
   __host__ __device__ double* dbl(int r) const {
-    return base + ((int64_t)(N_FIXED + 3 * D) * Q + r) * lds;
+    return base + ((int64_t)(N_FIXED + 4 * D) * Q + r) * lds;
   }
   __host__ __device__ double* lw(int lvl) const { return dbl(N_DBL + lvl); }
   // per-chain int32: depth, leaf, dir, n_leaf, its, st, active, moved, kdraw, + step outputs
@@ -36,7 +37,7 @@ struct SNutsLayout {
   __host__ __device__ int32_t* i32(int r) const {
     return reinterpret_cast<int32_t*>(dbl(N_DBL + D)) + (int64_t)r * lds;
   }
-  int64_t rows() const { return (int64_t)(N_FIXED + 3 * D) * Q + N_DBL + D + (N_INT + 1) / 2 + 1; }
+  int64_t rows() const { return (int64_t)(N_FIXED + 4 * D) * Q + N_DBL + D + (N_INT + 1) / 2 + 1; }
 };
 
 // new transition: working state = (q, fresh momentum noise), tree state reset
@@ -121,7 +122,8 @@ static __global__ void __launch_bounds__(32)
 // uniform draws in the recursion's post-order), a completed subtree joins the tree
 // (mlb_nuts.cuh has the same bookkeeping with the chain state in registers)
 static __global__ void __launch_bounds__(32)
-    kn_post(SNutsLayout T, int64_t n, SampleArgs a, int it, int max_depth, int* counter) {
+    kn_post(SNutsLayout T, int64_t n, SampleArgs a, int it, int max_depth, int flags,
+            int* counter) {
   const int64_t i = (int64_t)blockIdx.x * 32 + threadIdx.x;
   if (i >= n || !T.i32(T.ACTIVE)[i]) return;
   const int Q = T.Q;
@@ -141,42 +143,45 @@ static __global__ void __launch_bounds__(32)
   bool terminate = false;
   if (sst != MLB_ST_OK) {
     T.i32(T.ST)[i] = sst, terminate = true;
-  } else if (h != h || fabs(h - h0) > a.max_delta_h) {
+  } else if (h != h || h - h0 > a.max_delta_h ||
+             ((flags & MLB_FLAG_NUTS_TWO_SIDED_DELTA_H) && h0 - h > a.max_delta_h)) {
     T.i32(T.ST)[i] = MLB_ST_H_DIVERGED, terminate = true;
   }
+  const bool extra = !(flags & MLB_FLAG_NUTS_NO_EXTRA_SUBTREE_CHECKS);
+  double lw_cur = h0 - h;
   if (!terminate) {
-    double lw_cur = h0 - h;
     T.dbl(T.SUM_ACC)[i] += exp(lw_cur < 0.0 ? lw_cur : 0.0);
     // the subtree under construction is assembled in slot `lvl` (the level it will be
     // parked at): start from the leaf, fold in the pending siblings below
     int top = 0;
     while ((leaf >> top) & 1) ++top;  // park level = number of trailing ones of leaf
     double* pf = T.slot(top, 0) + i;
-    double* rh = T.slot(top, 1) + i;
-    double* pr = T.slot(top, 2) + i;
+    double* pl = T.slot(top, 1) + i;
+    double* rh = T.slot(top, 2) + i;
+    double* pr = T.slot(top, 3) + i;
 #pragma unroll 4
     for (int r = 0; r < Q; ++r) {
       const int64_t at = (int64_t)r * lds;
-      pf[at] = wp[at], rh[at] = wp[at], pr[at] = wq[at];
+      pf[at] = wp[at], pl[at] = wp[at], rh[at] = wp[at], pr[at] = wq[at];
     }
     for (int lvl = 0; lvl < top; ++lvl) {  // merge with the left sibling of level lvl
-      const double lw_left = T.lw(lvl)[i];
-      const double lw_new = log_add_exp(lw_left, lw_cur);
-      const bool take_outer = draw() < exp(lw_cur - lw_new);
+      double share;
+      lw_cur = log_add_exp_share(T.lw(lvl)[i], lw_cur, share);
+      const bool take_outer = draw() < share;
       const double* spf = T.slot(lvl, 0) + i;
-      const double* srh = T.slot(lvl, 1) + i;
-      const double* spr = T.slot(lvl, 2) + i;
-      double d_first = 0.0, d_last = 0.0;
-#pragma unroll 4
+      const double* spl = T.slot(lvl, 1) + i;
+      const double* srh = T.slot(lvl, 2) + i;
+      const double* spr = T.slot(lvl, 3) + i;
+      UTurn ut;
+#pragma unroll 2
       for (int r = 0; r < Q; ++r) {
         const int64_t at = (int64_t)r * lds;
-        const double rho = srh[at] + rh[at], p1 = spf[at];
+        const double rh_i = srh[at], rh_o = rh[at], p1 = spf[at], rho = rh_i + rh_o;
+        ut.add(p1, spl[at], rh_i, pf[at], wp[at], rh_o, rho);
         rh[at] = rho, pf[at] = p1;
         if (!take_outer) pr[at] = spr[at];
-        d_first = fma(p1, rho, d_first), d_last = fma(wp[at], rho, d_last);
       }
-      lw_cur = lw_new;
-      if (d_first < 0.0 || d_last < 0.0) {
+      if (ut.turned(extra)) {
         terminate = true;
         break;
       }
@@ -186,33 +191,33 @@ static __global__ void __launch_bounds__(32)
   ++leaf;
   bool done = terminate;
   if (!terminate && leaf == (1 << depth)) {  // new subtree complete: join it to the tree
+    // (inner = the tree so far: first-built = its far edge, last-built = the edge the
+    // subtree grew from; outer = the subtree, whose last state is the working one)
     const double lw_sub = T.lw(depth)[i], lw_tree = T.dbl(T.LW_TREE)[i];
     const bool take = draw() < exp(lw_sub - lw_tree);
-    T.dbl(T.LW_TREE)[i] = log_add_exp(lw_tree, lw_sub);
+    double share;
+    T.dbl(T.LW_TREE)[i] = log_add_exp_share(lw_tree, lw_sub, share);
     if (take) T.i32(T.MOVED)[i] = 1;
-    const double* srh = T.slot(depth, 1) + i;
-    const double* spr = T.slot(depth, 2) + i;
+    const double* spf = T.slot(depth, 0) + i;
+    const double* srh = T.slot(depth, 2) + i;
+    const double* spr = T.slot(depth, 3) + i;
     double* eq = T.blk(dir > 0 ? T.EP_Q : T.EN_Q) + i;
     double* ep = T.blk(dir > 0 ? T.EP_P : T.EN_P) + i;
+    const double* fp = T.blk(dir > 0 ? T.EN_P : T.EP_P) + i;
     double* rho = T.blk(T.RHO) + i;
     double* nx = T.blk(T.NEXT) + i;
-#pragma unroll 4
+    UTurn ut;
+#pragma unroll 2
     for (int r = 0; r < Q; ++r) {
       const int64_t at = (int64_t)r * lds;
+      const double rh_i = rho[at], rh_o = srh[at], pl_o = wp[at], rr = rh_i + rh_o;
+      ut.add(fp[at], ep[at], rh_i, spf[at], pl_o, rh_o, rr);
       if (take) nx[at] = spr[at];
-      rho[at] += srh[at];
-      eq[at] = wq[at], ep[at] = wp[at];
-    }
-    const double* enp = T.blk(T.EN_P) + i;
-    const double* epp = T.blk(T.EP_P) + i;
-    double d_neg = 0.0, d_pos = 0.0;
-#pragma unroll 4
-    for (int r = 0; r < Q; ++r) {
-      const int64_t at = (int64_t)r * lds;
-      d_neg = fma(enp[at], rho[at], d_neg), d_pos = fma(epp[at], rho[at], d_pos);
+      rho[at] = rr;
+      eq[at] = wq[at], ep[at] = pl_o;
     }
     ++depth, leaf = 0;
-    done = d_neg < 0.0 || d_pos < 0.0 || depth >= max_depth;
+    done = ut.turned(extra) || depth >= max_depth;
   }
   T.i32(T.DEPTH)[i] = depth, T.i32(T.LEAF)[i] = leaf, T.i32(T.KDRAW)[i] = (int)kdraw;
   T.i32(T.ACTIVE)[i] = !done;
@@ -322,7 +327,7 @@ int phased_nuts_sample(const mlb_model* m, const OdeData& D, int64_t n, int64_t 
       if ((rc = phased_leapfrog_steps<M, SOLVER>(m, D, n, T.lds, o,
                                                  step_io(1, false, T.i32(T.ACTIVE)), s)) != MLB_OK)
         goto fail;
-      MLB_KN((kn_post<<<g1, 32, 0, s>>>(T, n, a, it, na.max_depth, counter)));
+      MLB_KN((kn_post<<<g1, 32, 0, s>>>(T, n, a, it, na.max_depth, o.flags, counter)));
       active = read_counter();
     }
     if (active < 0) {

@@ -137,10 +137,14 @@ class DynamicMultinomialHMC(StaticMetropolisHMC):
     reports the mean tree depth, and `n_step` the integrator steps taken."""
 
     def __init__(self, system, integrator, rng=None, max_tree_depth=10, max_delta_h=1000.0,
-                 seed=None):  # fmt: skip
+                 do_extra_subtree_checks=True, seed=None, two_sided_max_delta_h=False):  # fmt: skip
         super().__init__(system, integrator, rng=rng, n_step=0, seed=seed,
                          max_delta_h=max_delta_h)  # fmt: skip
         self.max_tree_depth = int(max_tree_depth)
+        # Mici 0.2.1 defaults: no-U-turn criterion also on the overlapping sub-trajectories
+        # of every merge, divergence when h - h_init > max_delta_h (one-sided)
+        self.do_extra_subtree_checks = bool(do_extra_subtree_checks)
+        self.two_sided_max_delta_h = bool(two_sided_max_delta_h)
         self.trace_n_step = self.trace_depth = None  # set to int32 [n_iter, n] tensors to record
 
     def _launch(self, q, n_iter, adapt=None, adapt_opts=None, trace_q=None, trace_every=1,
@@ -151,6 +155,10 @@ class DynamicMultinomialHMC(StaticMetropolisHMC):
         sysm, integ = self.system, self.integrator
         n = q.shape[0]
         opts = integ.solver_opts()
+        if not self.do_extra_subtree_checks:
+            opts.flags |= _lib.FLAG_NUTS_NO_EXTRA_SUBTREE_CHECKS
+        if self.two_sided_max_delta_h:
+            opts.flags |= _lib.FLAG_NUTS_TWO_SIDED_DELTA_H
         pq, ld = p_soa(q, sysm.dim_q)
         check(lib().mlb_nuts_sample(
             sysm._h, C.c_int64(n), C.c_int64(ld), pq, C.c_double(integ.step_size_scalar()),

@@ -561,10 +561,13 @@ static double philox_uniform_k(uint64_t seed, uint64_t chain, uint32_t iter, uin
 // proposal with weights exp(h_init - h) (uniform sampling inside a new subtree, biased
 // progressive sampling between the old tree and the new subtree), no-U-turn termination
 // on the summed momentum (identity metric: dh/dmom = p) checked for every subtree and for
-// the whole tree, termination on an integrator error or |h - h_init| > max_delta_h.
-// accept_stat = mean over the tree's integrator steps of min(1, exp(h_init - h)) (a
-// failed step counts as 0).  The extra sub-tree checks of later Mici versions
-// (`do_extra_subtree_checks`) are not applied.
+// the whole tree and - `do_extra_subtree_checks`, Mici's default - for the two overlapping
+// sub-trajectories of every merge (the subtree built first plus the first state of the one
+// built after it; the last state of the first plus the second), termination on an
+// integrator error or h - h_init > max_delta_h (one-sided, as Mici's dynamic transitions
+// test it).  accept_stat = mean over the tree's integrator steps of min(1, exp(h_init - h))
+// (a failed step counts as 0).  NUTS_NO_EXTRA_CHECKS / NUTS_TWO_SIDED (flags of
+// orc_solver_opts, same values as include/mlb.h) switch the two refinements off.
 struct Tree {
   Chain neg, pos;            // edge states (time order), evaluated
   std::vector<double> rho;   // sum of momenta over the tree's states
@@ -578,6 +581,7 @@ struct NutsCtx {
   Work& W;
   const StepOpts& so;
   double dt, h0, max_delta_h;
+  bool extra_checks, two_sided;
   uint64_t seed, chain;
   uint32_t iter, k;  // next uniform index
   const double* unif;  // optional supplied draws (index k - 1)
@@ -603,6 +607,20 @@ static bool no_u_turn_violated(const Model& M, const Chain& a, const Chain& b,
   return da < 0.0 || db < 0.0;
 }
 
+// The criterion on the two overlapping sub-trajectories when `outer` (built in direction
+// dir after `inner`) joins `inner`: inner + first state of outer, last state of inner + outer.
+static bool extra_checks_violated(const Model& M, const Tree& inner, const Tree& outer, int dir) {
+  const Chain& in_first = dir > 0 ? inner.neg : inner.pos;
+  const Chain& in_last = dir > 0 ? inner.pos : inner.neg;
+  const Chain& out_first = dir > 0 ? outer.neg : outer.pos;
+  const Chain& out_last = dir > 0 ? outer.pos : outer.neg;
+  std::vector<double> rho(M.Q);
+  for (int k = 0; k < M.Q; ++k) rho[k] = inner.rho[k] + out_first.p[k];
+  if (no_u_turn_violated(M, in_first, out_first, rho)) return true;
+  for (int k = 0; k < M.Q; ++k) rho[k] = outer.rho[k] + in_last.p[k];
+  return no_u_turn_violated(M, in_last, out_last, rho);
+}
+
 // Builds a subtree of 2^depth states beyond `edge` in direction dir; returns true if the
 // transition must terminate (the subtree is then discarded).
 static bool build_tree(NutsCtx& X, int depth, const Chain& edge, int dir, Tree& out) {
@@ -618,7 +636,8 @@ static bool build_tree(NutsCtx& X, int depth, const Chain& edge, int dir, Tree& 
       return true;
     }
     double h = hamiltonian(M, N);
-    if (std::isnan(h) || std::fabs(h - X.h0) > X.max_delta_h) {
+    if (std::isnan(h) || h - X.h0 > X.max_delta_h ||
+        (X.two_sided && X.h0 - h > X.max_delta_h)) {
       if (X.status == ST_OK) X.status = ST_H_DIVERGED;
       return true;
     }
@@ -639,7 +658,8 @@ static bool build_tree(NutsCtx& X, int depth, const Chain& edge, int dir, Tree& 
   for (int k = 0; k < M.Q; ++k) out.rho[k] += outer.rho[k];
   if (dir > 0) out.neg = inner.neg, out.pos = outer.pos;
   else out.neg = outer.neg, out.pos = inner.pos;
-  return no_u_turn_violated(M, out.neg, out.pos, out.rho);
+  if (no_u_turn_violated(M, out.neg, out.pos, out.rho)) return true;
+  return X.extra_checks && extra_checks_violated(M, inner, outer, dir);
 }
 
 }  // namespace orc
@@ -653,8 +673,9 @@ typedef struct orc_solver_opts {
   int solver, max_iters, max_ls, norm;
   double ctol, ptol, dtol;
   double rev_tol;
-  int rev_norm, _pad;
+  int rev_norm, flags;  // flags: NUTS_* below (values of include/mlb.h MLB_FLAG_NUTS_*)
 } orc_solver_opts;
+enum { NUTS_NO_EXTRA_CHECKS = 2, NUTS_TWO_SIDED = 4 };
 
 static StepOpts to_step_opts(const orc_solver_opts* o) {
   StepOpts s;
@@ -971,7 +992,7 @@ void orc_nuts_transition(void* h, int64_t n, double* q, double dt,
       int st0 = evaluate_at(M, W, C) ? ST_OK : ST_LINALG;
       project_cotangent(M, W, C.J, C.G, C.p.data());
       NutsCtx X{M, W, so, dt_per_chain ? dt_per_chain[i] : dt, hamiltonian(M, C), max_delta_h,
-                seed, (uint64_t)(chain0 + i), iter, 1u, unif ? unif + i * n_unif : nullptr,
+                !(opts->flags & NUTS_NO_EXTRA_CHECKS), (opts->flags & NUTS_TWO_SIDED) != 0, seed, (uint64_t)(chain0 + i), iter, 1u, unif ? unif + i * n_unif : nullptr,
                 n_unif, 0, st0, 0.0};
       T.neg = C, T.pos = C, T.rho = C.p, T.prop = C.q, T.lw = 0.0;
       int depth = 0;
@@ -980,9 +1001,10 @@ void orc_nuts_transition(void* h, int64_t n, double* q, double dt,
         if (build_tree(X, depth, dir > 0 ? T.pos : T.neg, dir, S)) break;
         if (X.draw() < std::exp(S.lw - T.lw)) T.prop = S.prop;
         T.lw = log_add_exp(T.lw, S.lw);
+        const bool extra_turn = X.extra_checks && extra_checks_violated(M, T, S, dir);
         for (int k = 0; k < Q; ++k) T.rho[k] += S.rho[k];
         if (dir > 0) T.pos = S.pos; else T.neg = S.neg;
-        if (no_u_turn_violated(M, T.neg, T.pos, T.rho)) {
+        if (extra_turn || no_u_turn_violated(M, T.neg, T.pos, T.rho)) {
           ++depth;
           break;
         }

@@ -32,18 +32,24 @@ class SolverOpts(C.Structure):
         ("solver", C.c_int), ("max_iters", C.c_int), ("max_ls", C.c_int),
         ("norm", C.c_int), ("ctol", C.c_double), ("ptol", C.c_double),
         ("dtol", C.c_double), ("rev_tol", C.c_double), ("rev_norm", C.c_int),
-        ("_pad", C.c_int),
+        ("flags", C.c_int),  # NUTS_* (dynamic sampler only)
     ]  # fmt: skip
 
 
 def solver_opts(solver=SOLVER_NEWTON, constraint_tol=1e-9, position_tol=1e-8,
                 divergence_tol=1e10, max_iters=50, max_line_search_iters=10,
-                norm=NORM_MAX, reverse_check_tol=None, reverse_check_norm=NORM_MAX):  # fmt: skip
+                norm=NORM_MAX, reverse_check_tol=None, reverse_check_norm=NORM_MAX,
+                flags=0):  # fmt: skip
     if reverse_check_tol is None:
         reverse_check_tol = 2 * position_tol
     return SolverOpts(solver, max_iters, max_line_search_iters, norm, constraint_tol,
                       position_tol, divergence_tol, reverse_check_tol,
-                      reverse_check_norm, 0)  # fmt: skip
+                      reverse_check_norm, flags)  # fmt: skip
+
+
+# orc_solver_opts.flags (same values as include/mlb.h MLB_FLAG_NUTS_*): the dynamic sampler
+# follows Mici's defaults (extra subtree checks, one-sided h - h_init > max_delta_h)
+NUTS_NO_EXTRA_SUBTREE_CHECKS, NUTS_TWO_SIDED_DELTA_H = 2, 4
 
 
 _lib = None

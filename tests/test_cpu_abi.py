@@ -54,6 +54,10 @@ def test_python_enums_match_header():
         assert getattr(_lib, py) == enum(c), (py, c)
     assert _lib.ADAPT_ROWS == int(re.search(r"#define MLB_ADAPT_ROWS (\d+)", HEADER).group(1))
     assert _lib.STAT_ROWS == int(re.search(r"#define MLB_STAT_ROWS (\d+)", HEADER).group(1))
+    for py, c in [("FLAG_SINGLE_KERNEL", "MLB_FLAG_SINGLE_KERNEL"),
+                  ("FLAG_NUTS_NO_EXTRA_SUBTREE_CHECKS", "MLB_FLAG_NUTS_NO_EXTRA_SUBTREE_CHECKS"),
+                  ("FLAG_NUTS_TWO_SIDED_DELTA_H", "MLB_FLAG_NUTS_TWO_SIDED_DELTA_H")]:
+        assert getattr(_lib, py) == int(re.search(rf"#define {c} (\d+)", HEADER).group(1))
     assert C.sizeof(_lib.SolverOpts) == 56 and C.sizeof(_lib.ModelDesc) == 24
 
 

@@ -239,6 +239,42 @@ def test_oracle_dynamic_sampler_reproduces_toy_posterior_and_notebook_accept_rat
         assert se < 3e-3 and abs(x.mean() - want[k]) < 5 * se, (k, x.mean(), want[k], se)
 
 
+def test_oracle_dynamic_sampler_extra_subtree_checks_and_one_sided_divergence():
+    """Mici's defaults for DynamicMultinomialHMC (utils.py:286-288 passes none of them):
+    `do_extra_subtree_checks=True` only ADDS termination tests, so from the same state with
+    the same draws a tree built with them is never larger than without, is identical when
+    no extra test fires, and on the funnel-shaped eight-schools posterior some trees do
+    stop earlier; the one-sided divergence test accepts any energy decrease."""
+    y = np.array([28.0, 8.0, -3.0, 7.0, -1.0, 1.0, 18.0, 12.0])
+    s = np.array([15.0, 10.0, 16.0, 11.0, 9.0, 11.0, 10.0, 18.0])
+    cm = co.OracleModel.hier(y, s)
+    rng = np.random.default_rng(11)
+    n = 1024
+    u = np.stack([rng.normal(4.0, 3.0, n), rng.normal(1.0, 0.7, n)], 1)
+    v = rng.standard_normal((n, 8))
+    q = np.concatenate([u, v, (y[None] - u[:, :1] - np.exp(u[:, 1:2]) * v) / s[None]], 1)
+    on = co.solver_opts(co.SOLVER_NEWTON)
+    off = co.solver_opts(co.SOLVER_NEWTON, flags=co.NUTS_NO_EXTRA_SUBTREE_CHECKS)
+    fewer = 0
+    for it in range(6):
+        a = cm.nuts_transition(q, 0.5, on, max_depth=8, seed=3, iteration=it)
+        b = cm.nuts_transition(q, 0.5, off, max_depth=8, seed=3, iteration=it)
+        assert (a["n_step"] <= b["n_step"]).all()
+        # (equal steps with a smaller depth: the last subtree's final merge was refused)
+        same = (a["n_step"] == b["n_step"]) & (a["depth"] == b["depth"])
+        assert np.array_equal(a["q"][same], b["q"][same])
+        assert np.array_equal(a["accept_stat"][same], b["accept_stat"][same])
+        fewer += int((~same).sum())
+        q = a["q"]
+    assert 0 < fewer < 0.2 * 6 * n, fewer
+    # a (huge) energy DECREASE is divergent only under the two-sided test
+    two = co.solver_opts(co.SOLVER_NEWTON, flags=co.NUTS_TWO_SIDED_DELTA_H)
+    a = cm.nuts_transition(q, 0.5, on, max_depth=6, seed=5, max_delta_h=0.05)
+    b = cm.nuts_transition(q, 0.5, two, max_depth=6, seed=5, max_delta_h=0.05)
+    H_DIV = 4
+    assert (b["status"] == H_DIV).sum() > (a["status"] == H_DIV).sum() > 0
+
+
 def test_tridiagonal_restatement_matches_dense_linear_algebra():
     """oracle/mlift_oracle/linalg.py (the scans of mlift/linalg.py:46-114 as loops) against
     dense NumPy: np.linalg.solve and slogdet of the assembled matrix, including dim 1 and 2

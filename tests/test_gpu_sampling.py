@@ -103,19 +103,23 @@ def test_eight_schools_chain_statistics_match_cpu_oracle_chains():
 
 
 # ------------------------------------------------------- dynamic multinomial HMC (NUTS)
+@pytest.mark.parametrize("extra", [True, False])
 @pytest.mark.parametrize("kind", ["toy", "hier"])
-def test_nuts_transitions_match_oracle_trees(kind):
+def test_nuts_transitions_match_oracle_trees(kind, extra):
     """Tree by tree: the kernel builds its trees iteratively (pending sibling per level),
     the oracle recursively as Mici does; with the same Philox streams they must take the
     same number of steps to the same depth, report the same accept statistic and pick
-    the same proposal."""
+    the same proposal.  `extra`: Mici's defaults (no-U-turn tests on the overlapping
+    sub-trajectories of every merge, one-sided divergence test) or both switched off."""
     import manifold_lifting_b200 as mlb
     from test_gpu_parity import make_case
 
     _, _, cm, gm, gs, q = make_case(kind, "unbounded" if kind == "hier" else None, 640, seed=5)
     dt = 0.1 if kind == "toy" else 0.25
     sampler, integ = _sampler(mlb, gs, dt, 0, seed=31)
-    nuts = mlb.samplers.DynamicMultinomialHMC(gs, integ, max_tree_depth=7, seed=31)
+    nuts = mlb.samplers.DynamicMultinomialHMC(gs, integ, max_tree_depth=7, seed=31,
+                                              do_extra_subtree_checks=extra,
+                                              two_sided_max_delta_h=not extra)
     n, n_iter = q.shape[0], 3
     nuts.trace_n_step = torch.zeros(n_iter, n, dtype=torch.int32, device="cuda")
     nuts.trace_depth = torch.zeros(n_iter, n, dtype=torch.int32, device="cuda")
@@ -123,7 +127,8 @@ def test_nuts_transitions_match_oracle_trees(kind):
     qg = mlb._lib.soa_clone(mlb._lib.to_soa(q))
     nuts._launch(qg, n_iter, trace_accept=acc, chain_offset=1000)
     qo = q.copy()
-    opts = co.solver_opts(co.SOLVER_NEWTON)
+    opts = co.solver_opts(co.SOLVER_NEWTON, flags=0 if extra else (
+        co.NUTS_NO_EXTRA_SUBTREE_CHECKS | co.NUTS_TWO_SIDED_DELTA_H))
     same_all = np.ones(n, bool)
     for it in range(n_iter):
         r = cm.nuts_transition(qo, dt, opts, max_depth=7, seed=31, chain0=1000, iteration=it)

@@ -69,6 +69,32 @@ def test_state_space_gram_ops_match_restatement(dim_y, dim_u):
     _close(ss.log_det_sqrt_gram(J), ss.log_det_sqrt_gram(J, gram=(a, b, chol)).cpu().numpy(), 0.0)
 
 
+@pytest.mark.parametrize("scale", [1e-85, 1e85])
+def test_state_space_log_det_with_badly_scaled_pivots(scale):
+    """The kernel takes one logarithm per PAIR of pivots (and of |dx_dy| entries); with
+    pivots around 1e-170 / 1e+170 the pair products leave the double range, where the
+    reference's per-term recursion (linalg.py:104-114) stays finite.  The log-determinant
+    must follow: log det sqrt Gram(s J) = log det sqrt Gram(J) + dim_y log s."""
+    import manifold_lifting_b200 as mlb
+
+    ss = mlb.state_space
+    rng = np.random.default_rng(8)
+    n, dim_y, dim_u = 33, 37, 3
+    chains, (du, dv, dn, dx) = _batch(rng, n, dim_y, dim_u)
+    base = ss.log_det_sqrt_gram(ss.JacobBlocks(du, dv, dn, dx)).cpu().numpy()
+    scaled = ss.log_det_sqrt_gram(
+        ss.JacobBlocks(du * scale, dv * scale, (dn[0] * scale, dn[1] * scale), dx)).cpu().numpy()
+    assert np.isfinite(scaled).all()
+    assert np.abs(scaled - (base + dim_y * np.log(scale))).max() < 1e-9 * dim_y * abs(np.log(scale))
+    ref = np.array([oss.log_det_sqrt_gram(c[0] * scale, c[1] * scale,
+                                          (c[2][0] * scale, c[2][1] * scale), c[3])
+                    for c in chains])
+    assert np.abs(scaled - ref).max() < 1e-9 * np.abs(ref).max()
+    # |dx_dy| around 1e+-170: pair products of the second sum leave the range as well
+    dxs = ss.log_det_sqrt_gram(ss.JacobBlocks(du, dv, dn, dx * scale**2)).cpu().numpy()
+    assert np.abs(dxs - (base - dim_y * np.log(scale**2))).max() < 1e-9 * dim_y * abs(np.log(scale**2))
+
+
 def test_state_space_gram_ops_match_dense_linear_algebra():
     """Independent of the restated scans: J assembled densely, G = J J^T."""
     import manifold_lifting_b200 as mlb
