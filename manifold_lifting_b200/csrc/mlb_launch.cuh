@@ -10,6 +10,7 @@
 #pragma once
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -738,6 +739,14 @@ struct Launch {
     // per-chain tree storage (edges, summed momentum, proposal, pending siblings per level)
     NutsArgs na = na0;
     na.lds = (n + 31) / 32 * 32;
+    // start batching of the per-lane transitions (mlb_nuts.cuh); MLB_NUTS_BATCH in the
+    // environment overrides the default for experiments (1 = start at once, 32 = lock step)
+    static const int batch = [] {
+      const char* e = std::getenv("MLB_NUTS_BATCH");
+      const int b = e ? std::atoi(e) : 0;
+      return b >= 1 && b <= 32 ? b : 8;
+    }();
+    na.batch = batch;
     const size_t bytes = sizeof(double) * (size_t)NutsRows<M::Q>::total(na.max_depth) * (size_t)na.lds;
     if (scratch_alloc((void**)&na.scratch, bytes, s) != cudaSuccess) {
       g_err = "tree scratch allocation failed";

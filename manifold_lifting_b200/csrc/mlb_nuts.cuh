@@ -64,6 +64,7 @@ struct NutsArgs {
   int64_t lds;
   int32_t* trace_n_step;  // [n_iter][n] or NULL
   int32_t* trace_depth;   // [n_iter][n] or NULL
+  int batch;  // lanes of a warp that start their next transition together (see the kernel)
 };
 
 // No-U-turn tests when the subtree built first (inner: first-built momentum pf_i, last-built
@@ -103,7 +104,8 @@ __global__ void __launch_bounds__(kBlock, MLB_LF_MIN_BLOCKS)
   constexpr int Q = M::Q;
   using R = NutsRows<Q>;
   extern __shared__ double nuts_smem[];
-  MLB_CHAIN_INDEX();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < n;  // no early return: the warp votes below need every lane
   double* const cq = nuts_smem + threadIdx.x;  // committed position
   double* const cp = cq + Q * kBlock;          // committed momentum
   double* const cur = cq + 2 * Q * kBlock;     // subtree under construction: PF, RH, PR
@@ -112,42 +114,62 @@ __global__ void __launch_bounds__(kBlock, MLB_LF_MIN_BLOCKS)
   const bool extra = !(o.flags & MLB_FLAG_NUTS_NO_EXTRA_SUBTREE_CHECKS);
   const bool two_sided = (o.flags & MLB_FLAG_NUTS_TWO_SIDED_DELTA_H) != 0;
 #define SC(row) sc[(int64_t)(row) * lds]
-  double dti = a.adapt ? a.adapt[4 * ld + i] : a.dt;
+  double dti = (valid && a.adapt) ? a.adapt[4 * ld + i] : a.dt;
   int last = MLB_ST_OK;
+  const uint64_t chain = a.chain0 + (uint64_t)i;
+  // Every lane runs its OWN sequence of transitions: a lane whose tree is complete does not
+  // wait for the largest tree of its warp (72 % of the eight-schools trees have 7 leaves,
+  // 21 % have 15: in lock step a warp ran ~16 passes per transition for a mean of 8.75
+  // leaves).  Starting a transition (momentum draw, evaluation at the start point) runs
+  // with only the starting lanes active, so starts are batched: a lane waits until
+  // `batch` lanes of its warp are ready, or until no lane is stepping.  The refresh
+  // itself shares the one call site of the step code with the other lanes' leaves.
+  int it = 0;
+  bool in_tr = false, finished = !valid || a.n_iter <= 0;
+  // ONE call site of the step code serves the momentum refresh (leading pass: projection
+  // onto the cotangent space and h_init, no step) and every tree leaf: with two inlined
+  // copies the kernel was 135 KB of SASS and ncu showed 4.3 stall cycles per issue waiting
+  // for instructions (profiles/r6a_full_k_nuts_sample_hier.md).  C keeps the evaluation
+  // at the point the next step starts from (see run_trajectory_ev).
+  Eval<M> C;
+  bool refresh = false, have_eval = false, moved = false;
+  int last_dir = 0, st = MLB_ST_OK;
+  double h0 = 0.0, lw_tree = 0.0, sum_acc = 0.0, lw0 = 0.0;
+  int depth = 0, leaf = 0, dir = 1, n_leaf = 0, its = 0;
+  uint32_t kdraw = 1;
 #pragma unroll 1
-  for (int it = 0; it < a.n_iter; ++it) {
+  for (;;) {
+    const unsigned m_step = __ballot_sync(0xffffffffu, in_tr);
+    const unsigned m_wait = __ballot_sync(0xffffffffu, !in_tr && !finished);
+    if ((m_step | m_wait) == 0u) break;
     const uint32_t iter = a.iter0 + (uint32_t)it;
-    const uint64_t chain = a.chain0 + (uint64_t)i;
-    uint32_t kdraw = 1;
     auto draw = [&]() { return philox_uniform_k(a.seed, chain, iter, kdraw++); };
-    // start of the transition in the committed columns: position, momentum noise
-    if (a.mom_noise) {
-      const double* mn = a.mom_noise + (int64_t)it * Q * ld + i;
+    if (!in_tr && !finished && (m_step == 0u || __popc(m_wait) >= na.batch)) {
+      // start of a transition in the committed columns: position, momentum noise
+      if (a.mom_noise) {
+        const double* mn = a.mom_noise + (int64_t)it * Q * ld + i;
 #pragma unroll 1
-      for (int k = 0; k < Q; ++k) cp[k * kBlock] = mn[(int64_t)k * ld];
-    } else {
+        for (int k = 0; k < Q; ++k) cp[k * kBlock] = mn[(int64_t)k * ld];
+      } else {
 #pragma unroll 1
-      for (int j = 0; 2 * j < Q; ++j) {
-        double n0, n1;
-        philox_normal_pair(a.seed, chain, iter, (uint32_t)j, n0, n1);
-        cp[(2 * j) * kBlock] = n0;
-        if (2 * j + 1 < Q) cp[(2 * j + 1) * kBlock] = n1;
+        for (int j = 0; 2 * j < Q; ++j) {
+          double n0, n1;
+          philox_normal_pair(a.seed, chain, iter, (uint32_t)j, n0, n1);
+          cp[(2 * j) * kBlock] = n0;
+          if (2 * j + 1 < Q) cp[(2 * j + 1) * kBlock] = n1;
+        }
       }
+      if (it == 0) {  // (later transitions: the previous one left its result in cq)
+#pragma unroll 6
+        for (int k = 0; k < Q; ++k) cq[k * kBlock] = q[(int64_t)k * ld + i];
+      }
+      in_tr = true, refresh = true, have_eval = false, moved = false;
+      last_dir = 0, st = MLB_ST_OK, kdraw = 1;
+      lw_tree = 0.0, sum_acc = 0.0;
+      depth = 0, leaf = 0, dir = 1, n_leaf = 0, its = 0;
     }
-#pragma unroll 1
-    for (int k = 0; k < Q; ++k) cq[k * kBlock] = q[(int64_t)k * ld + i];
-    // ONE call site of the step code serves the momentum refresh (leading pass: projection
-    // onto the cotangent space and h_init, no step) and every tree leaf: with two inlined
-    // copies the kernel was 135 KB of SASS and ncu showed 4.3 stall cycles per issue waiting
-    // for instructions (profiles/r6a_full_k_nuts_sample_hier.md).  C keeps the evaluation
-    // at the point the next step starts from (see run_trajectory_ev).
-    Eval<M> C;
-    bool refresh = true, have_eval = false, moved = false, active = true;
-    int last_dir = 0, st = MLB_ST_OK;
-    double h0 = 0.0, lw_tree = 0.0, sum_acc = 0.0, lw0 = 0.0;
-    int depth = 0, leaf = 0, dir = 1, n_leaf = 0, its = 0;
-#pragma unroll 1
-    while (active) {
+    if (in_tr) {
+      bool active = true;
       double qw[Q], pw[Q];
       if (!refresh && leaf == 0) {  // new doubling: direction, start from that edge of the tree
         dir = draw() < 0.5 ? 1 : -1;
@@ -174,153 +196,178 @@ __global__ void __launch_bounds__(kBlock, MLB_LF_MIN_BLOCKS)
           SC(R::EN_P + k) = pk, SC(R::EP_P + k) = pk, SC(R::RHO + k) = pk;
         }
         active = st == MLB_ST_OK && na.max_depth > 0;
-        continue;
-      }
-      last_dir = dir;
-      n_leaf += 1;
-      its += t.it_fwd + t.it_rev;
-      bool terminate = false;
-      const double h = t.h_last;
-      double lw_cur = h0 - h;  // log weight of the subtree under construction
-      if (t.status != MLB_ST_OK) {
-        st = t.status, terminate = true;
-      } else if (h != h || h - h0 > a.max_delta_h || (two_sided && h0 - h > a.max_delta_h)) {
-        st = MLB_ST_H_DIVERGED, terminate = true;
-      }
-      if (!terminate) {
-        sum_acc += exp(lw_cur < 0.0 ? lw_cur : 0.0);
-        // The leaf is the committed state (cq, cp).  Level 0 never leaves shared memory: an
-        // even leaf waits in `cur` as the pending sibling of the odd leaf that follows it
-        // (one state: first = last = summed momentum, proposal = its position), and their
-        // merge reads both from shared memory.  Only the pending siblings of levels >= 1
-        // live in the global scratch column, and a subtree that is complete is joined to
-        // the tree straight from `cur`.
-        int lvl = 0;
-        if (leaf & 1) {
-          double share;
-          lw_cur = log_add_exp_share(lw0, lw_cur, share);
-          const bool take_outer = draw() < share;
-          UTurn ut;
-#pragma unroll 2
-          for (int k = 0; k < Q; ++k) {
-            const double p_i = cur[k * kBlock], p_o = cp[k * kBlock], rho = p_i + p_o;
-            ut.add(p_i, p_i, p_i, p_o, p_o, p_o, rho);
-            cur[(Q + k) * kBlock] = rho;
-            if (take_outer) cur[(2 * Q + k) * kBlock] = cq[k * kBlock];
-          }
-          terminate = ut.turned(extra);
-          lvl = 1;
-        } else {
-          lw0 = lw_cur;
-#pragma unroll 2
-          for (int k = 0; k < Q; ++k) {
-            const double pk = cp[k * kBlock];
-            cur[k * kBlock] = pk, cur[(Q + k) * kBlock] = pk;
-            cur[(2 * Q + k) * kBlock] = cq[k * kBlock];
-          }
+      } else {
+        last_dir = dir;
+        n_leaf += 1;
+        its += t.it_fwd + t.it_rev;
+        bool terminate = false;
+        const double h = t.h_last;
+        double lw_cur = h0 - h;  // log weight of the subtree under construction
+        if (t.status != MLB_ST_OK) {
+          st = t.status, terminate = true;
+        } else if (h != h || h - h0 > a.max_delta_h || (two_sided && h0 - h > a.max_delta_h)) {
+          st = MLB_ST_H_DIVERGED, terminate = true;
         }
+        bool joined = false;
+        if (!terminate) {
+          sum_acc += exp(lw_cur < 0.0 ? lw_cur : 0.0);
+          // The leaf is the committed state (cq, cp).  Level 0 never leaves shared memory: an
+          // even leaf waits in `cur` as the pending sibling of the odd leaf that follows it
+          // (one state: first = last = summed momentum, proposal = its position), and their
+          // merge reads both from shared memory.  Only the pending siblings of levels >= 1
+          // live in the global scratch column, and a subtree that is complete is joined to
+          // the tree straight from `cur`.
+          if (!(leaf & 1)) {
+            lw0 = lw_cur;
+#pragma unroll 2
+            for (int k = 0; k < Q; ++k) {
+              const double pk = cp[k * kBlock];
+              cur[k * kBlock] = pk, cur[(Q + k) * kBlock] = pk;
+              cur[(2 * Q + k) * kBlock] = cq[k * kBlock];
+            }
+          }
+          // "Combine" events of this leaf, bottom-up: merges with the pending left siblings of
+          // the levels whose bit in `leaf` is set, then - if that completes the subtree of
+          // this doubling - its join with the tree.  ONE code site evaluates the weights and
+          // draws the uniform for all of them (instruction-cache footprint).
+          int lvl = 0;
 #pragma unroll 1
-        while (!terminate && ((leaf >> lvl) & 1)) {  // a left sibling waits at this level: merge
-          const double* sl = &SC(R::slot(lvl));
-          double share;
-          lw_cur = log_add_exp_share(SC(R::lw(na.max_depth) + lvl), lw_cur, share);
-          const bool take_outer = draw() < share;
-          UTurn ut;
-          // (unrolled by 6: the loads of six components are in flight together - rolled, every
-          // component paid its own L2 / DRAM round trip, 40 % of the kernel's memory stalls)
+          for (;;) {
+            const bool merge = (leaf >> lvl) & 1;
+            if (!merge && lvl != depth) break;  // park below (levels >= 1)
+            const double lw_in = !merge ? lw_tree : lvl == 0 ? lw0 : SC(R::lw(na.max_depth) + lvl);
+            double share;  // of the part built last (the subtree under construction) in the sum
+            const double lw_new = log_add_exp_share(lw_in, lw_cur, share);
+            const double u = draw();
+            UTurn ut;
+            if (!merge) {
+              // join: inner = the tree so far (first-built = its far edge, last-built = the edge
+              // the subtree grew from), outer = the subtree, whose last state is the committed
+              // one; biased progressive sampling takes the subtree's proposal with probability
+              // min(1, w_sub / w_tree) = share / (1 - share)
+              const bool take = u * (1.0 - share) < share;
+              moved |= take;
+              double* eq = &SC(dir > 0 ? R::EP_Q : R::EN_Q);
+              double* ep = &SC(dir > 0 ? R::EP_P : R::EN_P);
+              const double* fp = &SC(dir > 0 ? R::EN_P : R::EP_P);
 #pragma unroll 6
-          for (int k = 0; k < Q; ++k) {
-            const double pf_i = sl[(int64_t)(R::PF + k) * lds], pl_i = sl[(int64_t)(R::PL + k) * lds];
-            const double rh_i = sl[(int64_t)(R::RH + k) * lds];
-            const double pr_i = sl[(int64_t)(R::PR + k) * lds];
-            const double pf_o = cur[k * kBlock], rh_o = cur[(Q + k) * kBlock];
-            const double rho = rh_i + rh_o;
-            ut.add(pf_i, pl_i, rh_i, pf_o, cp[k * kBlock], rh_o, rho);
-            cur[k * kBlock] = pf_i, cur[(Q + k) * kBlock] = rho;
-            if (!take_outer) cur[(2 * Q + k) * kBlock] = pr_i;
-          }
-          terminate = ut.turned(extra);
-          ++lvl;
-        }
-        if (!terminate && lvl >= 1 && lvl < depth) {  // park as the pending sibling of level lvl
-          double* sl = &SC(R::slot(lvl));
+              for (int k = 0; k < Q; ++k) {
+                const double rh_i = SC(R::RHO + k), rh_o = cur[(Q + k) * kBlock];
+                const double pl_o = cp[k * kBlock], rho = rh_i + rh_o;
+                ut.add(fp[(int64_t)k * lds], ep[(int64_t)k * lds], rh_i, cur[k * kBlock], pl_o, rh_o,
+                       rho);
+                if (take) SC(R::NEXT + k) = cur[(2 * Q + k) * kBlock];
+                SC(R::RHO + k) = rho;
+                eq[(int64_t)k * lds] = cq[k * kBlock], ep[(int64_t)k * lds] = pl_o;
+              }
+              lw_tree = lw_new;
+              joined = true;
+              if (ut.turned(extra)) active = false;
+              break;
+            }
+            const bool take_outer = u < share;
+            if (lvl == 0) {  // the previous leaf, still in `cur`
 #pragma unroll 2
-          for (int k = 0; k < Q; ++k) {
-            sl[(int64_t)(R::PF + k) * lds] = cur[k * kBlock];
-            sl[(int64_t)(R::PL + k) * lds] = cp[k * kBlock];
-            sl[(int64_t)(R::RH + k) * lds] = cur[(Q + k) * kBlock];
-            sl[(int64_t)(R::PR + k) * lds] = cur[(2 * Q + k) * kBlock];
+              for (int k = 0; k < Q; ++k) {
+                const double p_i = cur[k * kBlock], p_o = cp[k * kBlock], rho = p_i + p_o;
+                ut.add(p_i, p_i, p_i, p_o, p_o, p_o, rho);
+                cur[(Q + k) * kBlock] = rho;
+                if (take_outer) cur[(2 * Q + k) * kBlock] = cq[k * kBlock];
+              }
+            } else {
+              // (unrolled by 6: the loads of six components are in flight together - rolled,
+              // every component paid its own L2 / DRAM round trip, 40 % of the memory stalls)
+              const double* sl = &SC(R::slot(lvl));
+#pragma unroll 6
+              for (int k = 0; k < Q; ++k) {
+                const double pf_i = sl[(int64_t)(R::PF + k) * lds];
+                const double pl_i = sl[(int64_t)(R::PL + k) * lds];
+                const double rh_i = sl[(int64_t)(R::RH + k) * lds];
+                const double pr_i = sl[(int64_t)(R::PR + k) * lds];
+                const double pf_o = cur[k * kBlock], rh_o = cur[(Q + k) * kBlock];
+                const double rho = rh_i + rh_o;
+                ut.add(pf_i, pl_i, rh_i, pf_o, cp[k * kBlock], rh_o, rho);
+                cur[k * kBlock] = pf_i, cur[(Q + k) * kBlock] = rho;
+                if (!take_outer) cur[(2 * Q + k) * kBlock] = pr_i;
+              }
+            }
+            lw_cur = lw_new;
+            if (ut.turned(extra)) {
+              terminate = true;
+              break;
+            }
+            ++lvl;
           }
-          SC(R::lw(na.max_depth) + lvl) = lw_cur;
+          if (!terminate && !joined && lvl >= 1) {  // park as the pending sibling of level lvl
+            double* sl = &SC(R::slot(lvl));
+#pragma unroll 2
+            for (int k = 0; k < Q; ++k) {
+              sl[(int64_t)(R::PF + k) * lds] = cur[k * kBlock];
+              sl[(int64_t)(R::PL + k) * lds] = cp[k * kBlock];
+              sl[(int64_t)(R::RH + k) * lds] = cur[(Q + k) * kBlock];
+              sl[(int64_t)(R::PR + k) * lds] = cur[(2 * Q + k) * kBlock];
+            }
+            SC(R::lw(na.max_depth) + lvl) = lw_cur;
+          }
+        }
+        ++leaf;
+        if (terminate) {
+          active = false;
+        } else if (joined) {
+          ++depth, leaf = 0;
+          if (depth >= na.max_depth) active = false;
         }
       }
-      ++leaf;
-      if (terminate) {
-        active = false;
-      } else if (leaf == (1 << depth)) {  // new subtree complete: join it to the tree
-        // (inner = the tree so far: first-built = its far edge, last-built = the edge the
-        // subtree grew from; outer = the subtree, whose last state is the committed one)
-        // (biased progressive sampling: the new subtree's proposal with min(1, w_sub / w_tree))
-        const bool take = draw() < exp(lw_cur - lw_tree);
-        double share;
-        lw_tree = log_add_exp_share(lw_tree, lw_cur, share);
-        moved |= take;
-        double* eq = &SC(dir > 0 ? R::EP_Q : R::EN_Q);
-        double* ep = &SC(dir > 0 ? R::EP_P : R::EN_P);
-        const double* fp = &SC(dir > 0 ? R::EN_P : R::EP_P);
-        UTurn ut;
+      if (!active) {  // end of this lane's transition: new state, statistics, adaptation
+        const double a_stat = n_leaf > 0 ? sum_acc / n_leaf : 0.0;
+        const bool tr = a.trace_q && (it + 1) % a.trace_every == 0;
+        double* tq =
+            tr ? a.trace_q + (int64_t)((it + 1) / a.trace_every - 1) * a.trace_dim * ld + i
+               : nullptr;
 #pragma unroll 6
         for (int k = 0; k < Q; ++k) {
-          const double rh_i = SC(R::RHO + k), rh_o = cur[(Q + k) * kBlock];
-          const double pl_o = cp[k * kBlock], rho = rh_i + rh_o;
-          ut.add(fp[(int64_t)k * lds], ep[(int64_t)k * lds], rh_i, cur[k * kBlock], pl_o, rh_o, rho);
-          if (take) SC(R::NEXT + k) = cur[(2 * Q + k) * kBlock];
-          SC(R::RHO + k) = rho;
-          eq[(int64_t)k * lds] = cq[k * kBlock], ep[(int64_t)k * lds] = pl_o;
+          const double v = SC(R::NEXT + k);
+          q[(int64_t)k * ld + i] = v, cq[k * kBlock] = v;
+          if (tr && k < a.trace_dim) tq[(int64_t)k * ld] = v;
         }
-        ++depth, leaf = 0;
-        if (ut.turned(extra) || depth >= na.max_depth) active = false;
+        last = st;
+        if (a.stats) {
+          // accumulated in global memory (eight fewer live doubles in the loop) by
+          // reductions without a return value: nothing waits for them
+          atomicAdd(&a.stats[0 * ld + i], a_stat), atomicAdd(&a.stats[1 * ld + i], (double)moved);
+          const bool conv =
+              st == MLB_ST_DIVERGED || st == MLB_ST_NOT_CONVERGED || st == MLB_ST_LINALG;
+          if (conv) atomicAdd(&a.stats[2 * ld + i], 1.0);
+          if (st == MLB_ST_NON_REVERSIBLE) atomicAdd(&a.stats[3 * ld + i], 1.0);
+          if (st == MLB_ST_H_DIVERGED) atomicAdd(&a.stats[4 * ld + i], 1.0);
+          atomicAdd(&a.stats[5 * ld + i], (double)n_leaf);
+          atomicAdd(&a.stats[6 * ld + i], (double)its);
+          atomicAdd(&a.stats[7 * ld + i], (double)depth);
+        }
+        if (a.trace_accept) a.trace_accept[(int64_t)it * ld + i] = a_stat;
+        if (na.trace_n_step) na.trace_n_step[(int64_t)it * ld + i] = n_leaf;
+        if (na.trace_depth) na.trace_depth[(int64_t)it * ld + i] = depth;
+        if (a.adapt) {  // Mici DualAveragingStepSizeAdapter.update
+          double ad_iter = a.adapt[0 * ld + i], ad_smooth = a.adapt[1 * ld + i];
+          double ad_err = a.adapt[2 * ld + i];
+          const double ad_target = a.adapt[3 * ld + i];
+          ad_iter += 1;
+          const double w = 1.0 / (a.a_offset + ad_iter);
+          ad_err = (1.0 - w) * ad_err + w * (a.a_target - a_stat);
+          const double sw = exp(-a.a_decay * log(ad_iter));  // (1 / iter)^decay
+          const double log_eps = ad_target - ad_err * sqrt(ad_iter) / a.a_reg;
+          ad_smooth = (1.0 - sw) * ad_smooth + sw * log_eps;
+          dti = exp(log_eps);
+          a.adapt[0 * ld + i] = ad_iter, a.adapt[1 * ld + i] = ad_smooth;
+          a.adapt[2 * ld + i] = ad_err, a.adapt[4 * ld + i] = dti;
+        }
+        ++it;
+        in_tr = false, finished = it >= a.n_iter;
       }
-    }
-    const double a_stat = n_leaf > 0 ? sum_acc / n_leaf : 0.0;
-    const bool tr = a.trace_q && (it + 1) % a.trace_every == 0;
-    double* tq = tr ? a.trace_q + (int64_t)((it + 1) / a.trace_every - 1) * a.trace_dim * ld + i
-                    : nullptr;
-#pragma unroll 6
-    for (int k = 0; k < Q; ++k) {
-      const double v = SC(R::NEXT + k);
-      q[(int64_t)k * ld + i] = v;
-      if (tr && k < a.trace_dim) tq[(int64_t)k * ld] = v;
-    }
-    last = st;
-    if (a.stats) {  // accumulated in global memory: eight fewer live doubles in the tree loop
-      a.stats[0 * ld + i] += a_stat, a.stats[1 * ld + i] += moved;
-      a.stats[2 * ld + i] +=
-          (st == MLB_ST_DIVERGED || st == MLB_ST_NOT_CONVERGED || st == MLB_ST_LINALG);
-      a.stats[3 * ld + i] += (st == MLB_ST_NON_REVERSIBLE);
-      a.stats[4 * ld + i] += (st == MLB_ST_H_DIVERGED);
-      a.stats[5 * ld + i] += n_leaf, a.stats[6 * ld + i] += its, a.stats[7 * ld + i] += depth;
-    }
-    if (a.trace_accept) a.trace_accept[(int64_t)it * ld + i] = a_stat;
-    if (na.trace_n_step) na.trace_n_step[(int64_t)it * ld + i] = n_leaf;
-    if (na.trace_depth) na.trace_depth[(int64_t)it * ld + i] = depth;
-    if (a.adapt) {  // Mici DualAveragingStepSizeAdapter.update
-      double ad_iter = a.adapt[0 * ld + i], ad_smooth = a.adapt[1 * ld + i];
-      double ad_err = a.adapt[2 * ld + i];
-      const double ad_target = a.adapt[3 * ld + i];
-      ad_iter += 1;
-      const double w = 1.0 / (a.a_offset + ad_iter);
-      ad_err = (1.0 - w) * ad_err + w * (a.a_target - a_stat);
-      const double sw = exp(-a.a_decay * log(ad_iter));  // (1 / iter)^decay
-      const double log_eps = ad_target - ad_err * sqrt(ad_iter) / a.a_reg;
-      ad_smooth = (1.0 - sw) * ad_smooth + sw * log_eps;
-      dti = exp(log_eps);
-      a.adapt[0 * ld + i] = ad_iter, a.adapt[1 * ld + i] = ad_smooth;
-      a.adapt[2 * ld + i] = ad_err, a.adapt[4 * ld + i] = dti;
     }
   }
 #undef SC
-  if (a.last_status) a.last_status[i] = last;
+  if (valid && a.last_status) a.last_status[i] = last;
 }
 
 }  // namespace mlb
