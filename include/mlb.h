@@ -302,6 +302,22 @@ int mlb_tridiagonal_solve(int64_t n, int32_t dim, int32_t n_rhs, int64_t ld, con
 int mlb_tridiagonal_pos_def_log_det(int64_t n, int32_t dim, int64_t ld, const double* a,
                                     const double* b, double* out, void* stream);
 
+/* ---- dense helpers of mlift.linalg (reference mlift/linalg.py:6-43; used by the
+ * Gaussian-process systems, systems.py:871-899), batched over chains.  Arrays are the
+ * reference's with a leading chain axis, chain-major and row-major: l, u, chol_mtx
+ * [n][dim][dim] (l / chol_mtx lower-, u upper-triangular; the other triangle is not read),
+ * b, x [n][dim][n_rhs], vct [n][dim], tangents [n][n_dir][dim][dim] (symmetric; the
+ * reference vmaps over directions, systems.py:868-873), out [n][n_dir][dim]. */
+#define MLB_DENSE_MAX_DIM 2048
+/* solve l u x = b (linalg.py:6-9) */
+int mlb_lu_triangular_solve(int64_t n, int32_t dim, int32_t n_rhs, const double* l,
+                            const double* u, const double* b, double* x, void* stream);
+/* Jacobian-vector product of mtx -> cholesky(mtx) vct in the direction `tangents`
+ * (linalg.py:12-43): chol Phi(chol^-1 t chol^-T) vct, Phi = lower triangle, diagonal halved */
+int mlb_jvp_cholesky_mtx_mult_by_vct(int64_t n, int32_t n_dir, int32_t dim,
+                                     const double* tangents, const double* chol_mtx,
+                                     const double* vct, double* out, void* stream);
+
 /* ---- "tridiagonal + low rank" Gram algebra of the state-space systems (reference
  * mlift/systems.py:1161-1243, the closures of PartiallyInvertibleStateSpaceModelSystem),
  * batched over chains, on top of the Thomas recurrence above.  The Jacobian blocks are the

@@ -42,6 +42,7 @@ EXPORTS = (
     "mlb_ssm_sv_constr_blocks", "mlb_ssm_projection_update", "mlb_ssm_band_inv_gram",
     "mlb_ssm_sv_grad_log_det_sqrt_gram",
     "mlb_ssm_project_onto_cotangent_space", "mlb_scratch_trim",
+    "mlb_lu_triangular_solve", "mlb_jvp_cholesky_mtx_mult_by_vct",
 )  # fmt: skip
 
 

@@ -53,7 +53,15 @@ struct HhOde {
   static constexpr int ROLE_DIRS = MLB_HH_ROLE_DIRS, N_ROLE = ND / ROLE_DIRS;  // Jacobian sweep split
   // launches of more than WIDE_MIN_CHAINS chains take ROLE_DIRS_WIDE directions per role
   static constexpr int ROLE_DIRS_WIDE = MLB_HH_ROLE_DIRS_WIDE, WIDE_MIN_CHAINS = 3072;
-  static constexpr int NG_WIDE = 1;  // second-order sweep of a full GPU: all 21 pairs per thread
+  // second-order sweep of a full GPU: all 21 pairs per thread.  At 8,192 chains that is 256
+  // warps on 592 schedulers (11.1 ms, 1.7 warps active per SM,
+  // profiles/r6j_full_kp_second_order_hh.md); three groups of 7 pairs (768 warps, each
+  // repeating the state + first-order part) measured the same per step: 302.8 against
+  // 297.9 ms per 4 steps (MLB_HH_NG_WIDE=3)
+#ifndef MLB_HH_NG_WIDE
+#define MLB_HH_NG_WIDE 1
+#endif
+  static constexpr int NG_WIDE = MLB_HH_NG_WIDE;
   static constexpr int GATE_WARPS = MLB_HH_GATE_WARPS;  // warps sharing one chain batch in a cooperative sweep
   static_assert(NPAIR % NG == 0, "pair groups must be equal-sized");
   static MLB_DEV int dir_u(int d) { return d; }

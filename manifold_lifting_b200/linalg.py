@@ -1,9 +1,9 @@
-"""`mlift.linalg` tridiagonal primitives (reference mlift/linalg.py:46-114), batched over a
-leading chain axis and run on the GPU (csrc/mlb_linalg.cu): the linear algebra under the
-state-space systems' "tridiagonal + low rank" Gram matrices (mlift/systems.py:1189-1238).
-Same names and argument order as the reference; every array carries a leading chain axis.
-`lu_triangular_solve` and `jvp_cholesky_mtx_mult_by_vct` (dense, used by the Gaussian-process
-systems only) are not built.
+"""`mlift.linalg` (reference mlift/linalg.py), batched over a leading chain axis and run on
+the GPU: the tridiagonal primitives (linalg.py:46-114, csrc/mlb_linalg.cu) under the
+state-space systems' "tridiagonal + low rank" Gram matrices (mlift/systems.py:1189-1238) and
+the dense helpers (linalg.py:6-43, csrc/mlb_dense.cu) under the Gaussian-process systems
+(systems.py:871-899).  Same names and argument order as the reference; every array carries
+a leading chain axis.
 """
 import ctypes as C
 
@@ -68,3 +68,54 @@ def tridiagonal_pos_def_log_det(a, b):
     check(lib().mlb_tridiagonal_pos_def_log_det(C.c_int64(n), C.c_int32(dim), C.c_int64(ld), pa,
                                                 pb, C.c_void_p(out.data_ptr()), stream_ptr()))
     return out
+
+
+def _dense(x, shape_tail):
+    t = torch.as_tensor(x, dtype=torch.float64)
+    if t.shape[1:] != tuple(shape_tail):
+        raise _lib.MlbError(f"expected trailing shape {tuple(shape_tail)}, got {tuple(t.shape[1:])}")
+    return t.to("cuda").contiguous()
+
+
+def lu_triangular_solve(l, u, b):
+    """Solve `l @ u @ x = b` per chain, `l` lower- and `u` upper-triangular [n, dim, dim];
+    b [n, dim] or [n, dim, n_rhs].  linalg.py:6-9."""
+    _lib.require_cuda()
+    l_t = torch.as_tensor(l, dtype=torch.float64)
+    n, dim = l_t.shape[0], l_t.shape[1]
+    b_t = torch.as_tensor(b, dtype=torch.float64)
+    vec = b_t.ndim == 2
+    n_rhs = 1 if vec else b_t.shape[2]
+    ld, ud = _dense(l_t, (dim, dim)), _dense(u, (dim, dim))
+    bd = _dense(b_t.reshape(n, dim, n_rhs), (dim, n_rhs))
+    if ud.shape[0] != n or bd.shape[0] != n:
+        raise _lib.MlbError("lu_triangular_solve: arrays must share the chain axis")
+    x = torch.empty_like(bd)
+    check(lib().mlb_lu_triangular_solve(
+        C.c_int64(n), C.c_int32(dim), C.c_int32(n_rhs), C.c_void_p(ld.data_ptr()),
+        C.c_void_p(ud.data_ptr()), C.c_void_p(bd.data_ptr()), C.c_void_p(x.data_ptr()),
+        stream_ptr()))  # fmt: skip
+    return x[:, :, 0] if vec else x
+
+
+def jvp_cholesky_mtx_mult_by_vct(tangents, chol_mtx, vct):
+    """Forward-mode derivative of `mtx -> cholesky(mtx) @ vct` in the symmetric direction
+    `tangents` [n, dim, dim] - or [n, n_dir, dim, dim] for several directions at once, the
+    reference's `vmap(..., (1, None, None), 1)` of systems.py:871-873 - given
+    `chol_mtx = cholesky(mtx)` [n, dim, dim] and vct [n, dim].  linalg.py:12-43."""
+    _lib.require_cuda()
+    c_t = torch.as_tensor(chol_mtx, dtype=torch.float64)
+    n, dim = c_t.shape[0], c_t.shape[1]
+    t_t = torch.as_tensor(tangents, dtype=torch.float64)
+    single = t_t.ndim == 3
+    n_dir = 1 if single else t_t.shape[1]
+    td = _dense(t_t.reshape(n, n_dir, dim, dim), (n_dir, dim, dim))
+    cd, vd = _dense(c_t, (dim, dim)), _dense(vct, (dim,))
+    if td.shape[0] != n or vd.shape[0] != n:
+        raise _lib.MlbError("jvp_cholesky_mtx_mult_by_vct: arrays must share the chain axis")
+    out = torch.empty(n, n_dir, dim, dtype=torch.float64, device="cuda")
+    check(lib().mlb_jvp_cholesky_mtx_mult_by_vct(
+        C.c_int64(n), C.c_int32(n_dir), C.c_int32(dim), C.c_void_p(td.data_ptr()),
+        C.c_void_p(cd.data_ptr()), C.c_void_p(vd.data_ptr()), C.c_void_p(out.data_ptr()),
+        stream_ptr()))  # fmt: skip
+    return out[:, 0] if single else out

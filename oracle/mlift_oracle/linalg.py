@@ -36,3 +36,23 @@ def tridiagonal_pos_def_log_det(a, b):
         l_ip1 = log_diff_exp(np.log(b[i + 1]) + l_i, 2 * np.log(abs(a[i])) + l_im1)
         l_i, l_im1 = l_ip1, l_i
     return l_i
+
+
+def lu_triangular_solve(l, u, b):
+    """linalg.py:6-9: solve l u x = b, l lower- and u upper-triangular (two substitutions)."""
+    from scipy.linalg import solve_triangular
+
+    x = solve_triangular(np.asarray(l, dtype=np.float64), np.asarray(b, dtype=np.float64), lower=True)
+    return solve_triangular(np.asarray(u, dtype=np.float64), x, lower=False)
+
+
+def jvp_cholesky_mtx_mult_by_vct(tangents, chol_mtx, vct):
+    """linalg.py:12-43: chol Phi(chol^-1 t chol^-T) vct with Phi = lower triangle, diagonal
+    halved (forward-mode rule of the Cholesky factorisation)."""
+    from scipy.linalg import solve_triangular
+
+    L = np.asarray(chol_mtx, dtype=np.float64)
+    tmp = solve_triangular(L, np.asarray(tangents, dtype=np.float64).T, lower=True).T  # t L^-T
+    tmp = solve_triangular(L, tmp, lower=True)
+    phi = np.tril(tmp) / (np.ones_like(L) + np.identity(L.shape[-1]))
+    return L @ (phi @ np.asarray(vct, dtype=np.float64))

@@ -149,10 +149,18 @@ def vmap(fun, in_axes=0, out_axes=0):
             return tree_map(lambda l: Array(as_t(l).select(ax, i)), wrap(a))
 
         outs = [fun(*[take(a, ax, i) for a, ax in zip(args, axes)]) for i in range(n)]
-        return tree_map(
-            lambda first, *rest: Array(torch.stack([as_t(first)] + [as_t(r) for r in rest],
-                                                   out_axes)),
-            outs[0], *outs[1:])  # fmt: skip
+
+        def stack(ax, first, *rest):
+            if ax is None:  # unbatched output: every instance returns the same value
+                return first
+            return tree_map(
+                lambda f, *r: Array(torch.stack([as_t(f)] + [as_t(x) for x in r], ax)),
+                first, *rest)  # fmt: skip
+
+        if isinstance(out_axes, (tuple, list)):  # one axis (or None) per element of the output
+            return tuple(stack(ax, outs[0][k], *[o[k] for o in outs[1:]])
+                         for k, ax in enumerate(out_axes))
+        return stack(out_axes, outs[0], *outs[1:])
 
     return vf
 

@@ -21,7 +21,7 @@ The system objects are built exactly as `example_models/utils.py:292-327, 572-58
 them.  This script needs /root/reference, so it runs in the build container only; the
 fixtures it writes are committed and travel to the GPU box.
 
-    python tests/golden/make_ref_golden.py [hier] [fn] [hh] [sv] [linalg]
+    python tests/golden/make_ref_golden.py [hier] [fn] [hh] [sv] [linalg] [dense]
 """
 import os
 import sys
@@ -367,7 +367,80 @@ def sv():
     np.savez(os.path.join(HERE, "ref_sv.npz"), **out)
 
 
+def dense():
+    """mlift/linalg.py:6-43 (`lu_triangular_solve`, `jvp_cholesky_mtx_mult_by_vct`) on random
+    factors, and the Gaussian-process system built on them (systems.py:810-931) with the
+    squared-exponential covariance of gp_regression.py:33-44 on random inputs: blocks,
+    Gram factor, both solves, log-determinant and its gradient at a few states."""
+    import jax
+    from mlift.linalg import jvp_cholesky_mtx_mult_by_vct, lu_triangular_solve
+
+    rng = np.random.default_rng(21)
+    out = dict(source=SOURCE)
+    dims = (1, 2, 5, 33, 70, 150)
+    for k, n in enumerate(dims):
+        a, b2 = rng.standard_normal((n, n)), rng.standard_normal((n, n))
+        mtx = a @ a.T / n + np.eye(n)
+        chol = np.linalg.cholesky(mtx)
+        upper = np.linalg.cholesky(b2 @ b2.T / n + np.eye(n)).T
+        rhs = rng.standard_normal((n, 4))
+        out[f"l_{k}"], out[f"u_{k}"], out[f"b_{k}"] = chol, upper, rhs
+        out[f"x_{k}"] = np.asarray(lu_triangular_solve(chol, upper, rhs))
+        out[f"xv_{k}"] = np.asarray(lu_triangular_solve(chol, upper, rhs[:, 0]))
+        t = rng.standard_normal((n, 3, n))
+        t = t + t.transpose(2, 1, 0)  # symmetric in (0, 2) for every direction
+        v = rng.standard_normal(n)
+        out[f"t_{k}"], out[f"v_{k}"] = t, v
+        out[f"jvp_{k}"] = np.asarray(
+            jax.vmap(jvp_cholesky_mtx_mult_by_vct, (1, None, None), 1)(t, chol, v))
+    out["n_case"] = len(dims)
+    # Gaussian-process system on the reference's regression model, synthetic inputs
+    m = ref_loader.example_model("gp_regression")
+    dim_y, dim_x = 12, 2
+    data = {"x": rng.standard_normal((dim_y, dim_x)), "y_obs": np.zeros(dim_y)}
+    dim_u = m.compute_dim_u(data)
+    u_true = np.array([0.3, -0.2, 0.1, -1.0])[:dim_u]
+    covar = np.asarray(m.covar_func(u_true, data))
+    data["y_obs"] = np.linalg.cholesky(covar) @ rng.standard_normal(dim_y)
+    system = build_system(mlift.GaussianProcessModelSystem, m, data, covar_func=m.covar_func)
+    rec = {}
+
+    def put(key, val):
+        rec.setdefault(key, []).append(np.asarray(val, dtype=np.float64))
+
+    for _ in range(4):
+        u = u_true + 0.3 * rng.standard_normal(dim_u)
+        chol_u = np.linalg.cholesky(np.asarray(m.covar_func(u, data)))
+        q = np.concatenate([u, np.linalg.solve(chol_u, data["y_obs"])])
+        up = u + 0.05 * rng.standard_normal(dim_u)
+        chol_p = np.linalg.cholesky(np.asarray(m.covar_func(up, data)))
+        qp = np.concatenate([up, np.linalg.solve(chol_p, data["y_obs"])
+                             + 0.05 * rng.standard_normal(dim_y)])
+        st, stp = state_of(q), state_of(qp)
+        (dy_du, dy_dn), (dy_du_p, dy_dn_p) = system.jacob_constr_blocks(st), system.jacob_constr_blocks(stp)
+        covar_u, dcovar_du = jax.vmap(
+            partial(jax.jvp, lambda uu: m.covar_func(uu, data), (u,)), out_axes=(None, 1)
+        )((np.identity(dim_u),))
+        vq, wy = rng.standard_normal(q.size), rng.standard_normal(dim_y)
+        put("q", q), put("q_prev", qp), put("vec_q", vq), put("vec_y", wy)
+        put("covar", covar_u), put("dcovar_du", dcovar_du)
+        put("c", system.constr(st)), put("dy_du", dy_du), put("dy_dn", dy_dn)
+        put("dy_du_prev", dy_du_p), put("dy_dn_prev", dy_dn_p)
+        put("chol_cap", system.gram_components(st)[0])
+        put("logdet", system.log_det_sqrt_gram(state_of(q)))
+        put("grad_logdet", system.grad_log_det_sqrt_gram(st))
+        put("jv", system.lmult_by_jacob_constr(st, vq))
+        put("jtw", system.rmult_by_jacob_constr(st, wy))
+        put("pinv_w", system.lmult_by_pinv_jacob_constr(st, wy))
+        put("ijp_w", system.lmult_by_inv_jacob_product(st, stp, wy))
+        put("proj_v", system.project_onto_cotangent_space(vq.copy(), st))
+    out.update({f"gp_{k}": np.array(v) for k, v in rec.items()})
+    out["gp_x"], out["gp_y_obs"] = data["x"], data["y_obs"]
+    np.savez(os.path.join(HERE, "ref_dense.npz"), **out)
+    print("dense done")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:2] or ["linalg", "hier", "sv", "fn", "hh"]
+    which = sys.argv[1:2] or ["linalg", "dense", "hier", "sv", "fn", "hh"]
     for w in which:
-        {"hier": hier, "fn": fn, "hh": hh, "sv": sv, "linalg": linalg}[w]()
+        {"hier": hier, "fn": fn, "hh": hh, "sv": sv, "linalg": linalg, "dense": dense}[w]()
