@@ -318,6 +318,38 @@ int mlb_jvp_cholesky_mtx_mult_by_vct(int64_t n, int32_t n_dir, int32_t dim,
                                      const double* tangents, const double* chol_mtx,
                                      const double* vct, double* out, void* stream);
 
+/* ---- block algebra of GaussianProcessModelSystem (reference mlift/systems.py:859-918:
+ * y = cholesky(covar(u)) n), batched over chains, given the Jacobian blocks dy_du
+ * [n][dim_y][dim_u] and dy_dn = cholesky(covar) [n][dim_y][dim_y] (lower; row-major, as the
+ * reference's arrays with a leading chain axis).  Gram = dy_du dy_du^T + dy_dn dy_dn^T =
+ * "Cholesky-factored covariance + low rank": solves go through the dim_u x dim_u
+ * capacitance matrix (Cholesky factor chol_cap_mtx [n][dim_u][dim_u] for the symmetric
+ * Gram, pivoted LU for the non-symmetric product of the Newton iteration). */
+#define MLB_GP_MAX_DIM_U 16
+/* cholesky(covar) per chain (systems.py:869); a matrix that is not positive definite gives
+ * a NaN factor for its chain */
+int mlb_dense_cholesky(int64_t n, int32_t dim, const double* a, double* l, void* stream);
+/* systems.py:885-888 */
+int mlb_gp_decompose_gram(int64_t n, int32_t dim_y, int32_t dim_u, const double* dy_du,
+                          const double* dy_dn, double* chol_cap_mtx, void* stream);
+/* systems.py:890-897: Gram^-1 vct, vct / out [n][dim_y] */
+int mlb_gp_lmult_by_inv_gram(int64_t n, int32_t dim_y, int32_t dim_u, const double* dy_du,
+                             const double* dy_dn, const double* chol_cap_mtx, const double* vct,
+                             double* out, void* stream);
+/* systems.py:899-911: (J_l J_r^T)^-1 vct */
+int mlb_gp_lmult_by_inv_jacob_product(int64_t n, int32_t dim_y, int32_t dim_u,
+                                      const double* dy_du_l, const double* dy_dn_l,
+                                      const double* dy_du_r, const double* dy_dn_r,
+                                      const double* vct, double* out, void* stream);
+/* systems.py:878-883: transpose = 0: J vct (vct [n][dim_u + dim_y] -> out [n][dim_y]);
+ * transpose = 1: J^T vct (vct [n][dim_y] -> out [n][dim_u + dim_y]) */
+int mlb_gp_jacob_constr_mult(int64_t n, int32_t dim_y, int32_t dim_u, int32_t transpose,
+                             const double* dy_du, const double* dy_dn, const double* vct,
+                             double* out, void* stream);
+/* systems.py:913-918 from the factors: sum log diag chol_cap_mtx + sum log diag dy_dn */
+int mlb_gp_log_det_sqrt_gram(int64_t n, int32_t dim_y, int32_t dim_u, const double* dy_dn,
+                             const double* chol_cap_mtx, double* out, void* stream);
+
 /* ---- "tridiagonal + low rank" Gram algebra of the state-space systems (reference
  * mlift/systems.py:1161-1243, the closures of PartiallyInvertibleStateSpaceModelSystem),
  * batched over chains, on top of the Thomas recurrence above.  The Jacobian blocks are the

@@ -6,8 +6,8 @@ imports (`import mlift`, `from mlift.systems import ...`) resolve to the CUDA pa
 """
 import sys
 
-from . import (_lib, adapters, errors, integrators, linalg, models, outputs, parallel, samplers,
-               solvers, state_space, states, systems, transitions)  # fmt: skip
+from . import (_lib, adapters, errors, gaussian_process, integrators, linalg, models, outputs,
+               parallel, samplers, solvers, state_space, states, systems, transitions)  # fmt: skip
 from .adapters import *  # noqa: F401,F403
 from .solvers import *  # noqa: F401,F403
 from .systems import *  # noqa: F401,F403

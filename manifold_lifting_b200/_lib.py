@@ -42,7 +42,9 @@ EXPORTS = (
     "mlb_ssm_sv_constr_blocks", "mlb_ssm_projection_update", "mlb_ssm_band_inv_gram",
     "mlb_ssm_sv_grad_log_det_sqrt_gram",
     "mlb_ssm_project_onto_cotangent_space", "mlb_scratch_trim",
-    "mlb_lu_triangular_solve", "mlb_jvp_cholesky_mtx_mult_by_vct",
+    "mlb_lu_triangular_solve", "mlb_jvp_cholesky_mtx_mult_by_vct", "mlb_dense_cholesky",
+    "mlb_gp_decompose_gram", "mlb_gp_lmult_by_inv_gram", "mlb_gp_lmult_by_inv_jacob_product",
+    "mlb_gp_jacob_constr_mult", "mlb_gp_log_det_sqrt_gram",
 )  # fmt: skip
 
 

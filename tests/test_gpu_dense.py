@@ -92,3 +92,76 @@ def test_dense_helpers_argument_checks():
     l[1, 2, 2] = 0.0
     x = mlb.linalg.lu_triangular_solve(l, np.stack([np.eye(4)] * 2), np.ones((2, 4)))
     assert torch.isfinite(x[0]).all() and not torch.isfinite(x[1]).all()
+
+
+# --------------------------------------------- Gaussian-process block algebra (mlb_gp_*)
+def test_gaussian_process_closures_match_reference_source():
+    """`manifold_lifting_b200.gaussian_process` (the closures of GaussianProcessModelSystem,
+    systems.py:859-918, on the GPU) against the outputs of the reference's own source for
+    the squared-exponential regression model (ref_dense.npz gp_*), all recorded states as
+    one batch."""
+    import manifold_lifting_b200 as mlb
+
+    gp = mlb.gaussian_process
+    dim_u = G["gp_dy_du"].shape[2]
+    q, vq, wy = G["gp_q"], G["gp_vec_q"], G["gp_vec_y"]
+    dcov = G["gp_dcovar_du"].transpose(0, 2, 1, 3)  # [n, U, Y, Y]
+    (dy_du, dy_dn), c = gp.jacob_constr_blocks(G["gp_covar"], dcov, q[:, dim_u:], G["gp_y_obs"])
+    assert _rel(dy_dn, G["gp_dy_dn"]) < 1e-12 and _rel(dy_du, G["gp_dy_du"]) < 1e-11
+    assert _rel(c, G["gp_c"]) < 1e-12
+    (chol_cap,) = gp.decompose_gram(dy_du, dy_dn)
+    assert _rel(chol_cap, G["gp_chol_cap"]) < 1e-11
+    assert float(torch.triu(chol_cap, 1).abs().max()) == 0.0
+    assert _rel(gp.log_det_sqrt_gram(dy_du, dy_dn, chol_cap), G["gp_logdet"]) < 1e-11
+    assert _rel(gp.log_det_sqrt_gram(dy_du, dy_dn), G["gp_logdet"]) < 1e-11
+    assert _rel(gp.lmult_by_jacob_constr(dy_du, dy_dn, vq), G["gp_jv"]) < 1e-12
+    assert _rel(gp.rmult_by_jacob_constr(dy_du, dy_dn, wy), G["gp_jtw"]) < 1e-12
+    pinv = gp.rmult_by_jacob_constr(dy_du, dy_dn, gp.lmult_by_inv_gram(dy_du, dy_dn, chol_cap, wy))
+    assert _rel(pinv, G["gp_pinv_w"]) < 1e-10
+    ijp = gp.lmult_by_inv_jacob_product(dy_du, dy_dn, G["gp_dy_du_prev"], G["gp_dy_dn_prev"], wy)
+    assert _rel(ijp, G["gp_ijp_w"]) < 1e-10
+    nsc = gp.rmult_by_jacob_constr(dy_du, dy_dn, gp.lmult_by_inv_gram(
+        dy_du, dy_dn, chol_cap, gp.lmult_by_jacob_constr(dy_du, dy_dn, vq)))
+    assert _rel(torch.as_tensor(vq, device="cuda") - nsc, G["gp_proj_v"]) < 1e-10
+
+
+@pytest.mark.parametrize("dim_y,dim_u", [(1, 1), (5, 2), (40, 16), (129, 3), (260, 7)])
+def test_gaussian_process_block_algebra_matches_restatement(dim_y, dim_u):
+    import manifold_lifting_b200 as mlb
+    from mlift_oracle import gp as ogp
+
+    gp = mlb.gaussian_process
+    rng = np.random.default_rng(7 * dim_y + dim_u)
+    n = 5
+    a, b = rng.standard_normal((2, n, dim_y, dim_y))
+    covar = a @ a.transpose(0, 2, 1) / dim_y + np.eye(dim_y)
+    L = gp.cholesky(covar)
+    assert _rel(L, np.linalg.cholesky(covar)) < 1e-12
+    Lr = np.linalg.cholesky(b @ b.transpose(0, 2, 1) / dim_y + np.eye(dim_y))
+    Ln = L.cpu().numpy()
+    du, dur = rng.standard_normal((2, n, dim_y, dim_u))
+    vq, wy = rng.standard_normal((n, dim_u + dim_y)), rng.standard_normal((n, dim_y))
+    (cc,) = gp.decompose_gram(du, Ln)
+    ref = [ogp.decompose_gram(du[i], Ln[i])[0] for i in range(n)]
+    assert _rel(cc, np.stack(ref)) < 1e-11
+    assert _rel(gp.lmult_by_inv_gram(du, Ln, cc, wy),
+                np.stack([ogp.lmult_by_inv_gram(du[i], Ln[i], ref[i], wy[i]) for i in range(n)])) < 1e-10
+    assert _rel(gp.lmult_by_inv_jacob_product(du, Ln, dur, Lr, wy),
+                np.stack([ogp.lmult_by_inv_jacob_product(du[i], Ln[i], dur[i], Lr[i], wy[i])
+                          for i in range(n)])) < 1e-9
+    assert _rel(gp.lmult_by_jacob_constr(du, Ln, vq),
+                np.stack([ogp.lmult_by_jacob_constr(du[i], Ln[i], vq[i]) for i in range(n)])) < 1e-12
+    assert _rel(gp.rmult_by_jacob_constr(du, Ln, wy),
+                np.stack([ogp.rmult_by_jacob_constr(du[i], Ln[i], wy[i]) for i in range(n)])) < 1e-12
+    assert _rel(gp.log_det_sqrt_gram(du, Ln),
+                np.array([ogp.log_det_sqrt_gram(du[i], Ln[i]) for i in range(n)])) < 1e-11
+    # Gram (Gram^-1 w) = w through the Jacobian products: J J^T x
+    x = gp.lmult_by_inv_gram(du, Ln, cc, wy)
+    back = gp.lmult_by_jacob_constr(du, Ln, gp.rmult_by_jacob_constr(du, Ln, x))
+    assert _rel(back, wy) < 1e-9
+    # a covariance that is not positive definite poisons its chain only
+    bad = covar.copy()
+    bad[2] = -np.eye(dim_y)
+    Lb = gp.cholesky(bad)
+    isn = torch.isnan(Lb).flatten(1).any(1).cpu().numpy()
+    assert isn[2] and not isn[[0, 1, 3, 4]].any()
