@@ -443,15 +443,27 @@ int mlb_leapfrog_steps_host(const mlb_model* m, int64_t n, double* q, double* p,
   // streaming (ODE) family keeps one chunk and transposes on the device: its batches are
   // small and its kernels long.
   const bool small_state = m->model == MLB_MODEL_TOY || m->model == MLB_MODEL_HIER;
-  // chunk size: four chunks in flight (one per stream), between 2,048 and 16,384 chains -
-  // 16,384 measured best for 65,536 chains; below that the fused kernel's
-  // duration no longer depends on the chunk size (one warp per scheduler: the latency of a
-  // single chain's trajectory), so smaller chunks only shorten the exposed first H2D / last
-  // D2H copy
+  // chunk size: eight chunks in flight (one per stream), between 2,048 and 16,384 chains.
+  // Below ~16,384 chains the fused kernel's duration no longer depends on the chunk size
+  // (one warp per scheduler: the latency of a single chain's trajectory, 0.25 ms for 32
+  // eight-schools steps), so the call costs about H2D of everything + one kernel + the last
+  // chunk's D2H; with eight streams 8,192-chain chunks measured best for 65,536 chains
+  // (2.23e9 steps/s against 2.11e9 with four 16,384-chain chunks, profiles/r6n_e2e_sweep.txt;
+  // with four streams a fifth chunk waited for the first one's D2H and smaller chunks lost)
   int64_t chunk = n;
   if (small_state) {
-    chunk = ((n + 3) / 4 + 63) / 64 * 64;
+    static const int64_t forced = [] {  // MLB_HOST_CHUNK: chunk size for experiments
+      const char* e = std::getenv("MLB_HOST_CHUNK");
+      return e ? (int64_t)std::atoll(e) : (int64_t)0;
+    }();
+    static const int64_t parts = [] {  // MLB_HOST_PARTS: chunks a batch is cut into
+      const char* e = std::getenv("MLB_HOST_PARTS");
+      const int64_t v = e ? (int64_t)std::atoll(e) : 0;
+      return v >= 1 ? v : (int64_t)8;
+    }();
+    chunk = ((n + parts - 1) / parts + 63) / 64 * 64;
     chunk = chunk < 2048 ? 2048 : chunk > 16384 ? 16384 : chunk;
+    if (forced >= 64) chunk = forced / 64 * 64;
   }
   const int n_chunk = (int)((n + chunk - 1) / chunk);
   // per chunk: row-major state (2 vec), component-major state (2 vec, ODE family only),

@@ -35,8 +35,8 @@ struct mlb_model {
   mutable std::mutex host_mutex;  // serialises mlb_leapfrog_steps_host calls on the handle
   mutable void* host_ws = nullptr;
   mutable size_t host_ws_bytes = 0;
-  static constexpr int kHostStreams = 4;  // chunk pipeline of the host entry point
-  mutable void* host_streams[kHostStreams] = {nullptr, nullptr, nullptr, nullptr};
+  static constexpr int kHostStreams = 8;  // chunk pipeline of the host entry point
+  mutable void* host_streams[kHostStreams] = {};
   mutable std::mutex pin_mutex;
   mutable int* pinned_word = nullptr;  // polled by the host-driven streaming path
 };
