@@ -583,6 +583,20 @@ struct ModelOps {
 
 inline unsigned grid_for(int64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
 
+// Runs `configure` once per device of this process (kernel function attributes such as the
+// dynamic shared-memory limit belong to a device's context) and remembers a success in one
+// bit per device; a failure is retried at the next call.
+template <class F>
+inline bool once_per_device(std::atomic<uint64_t>& ready, F configure) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+  const uint64_t bit = 1ull << dev;
+  if (ready.load(std::memory_order_acquire) & bit) return true;
+  if (!configure()) return false;
+  ready.fetch_or(bit, std::memory_order_release);
+  return true;
+}
+
 inline int finish_launch() {
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
@@ -706,13 +720,15 @@ struct Launch {
         const int64_t sms = sm_count();
         if (n > sms * 4 * kBlock && n <= sms * 7 * kBlock && S <= MLB_SOLVER_NEWTON_LS) {
           constexpr int smem = (int)sizeof(double) * LeanCol<M, kBlock>::ROWS * kBlock;
-          static const bool configured = [] {
+          // (function attributes are per device: one bit per device of this process)
+          static std::atomic<uint64_t> ready{0};
+          const bool configured = once_per_device(ready, [] {
             cudaFuncSetAttribute(k_leapfrog_steps_lean<M, S>,
                                  cudaFuncAttributePreferredSharedMemoryCarveout, 100);
             return cudaFuncSetAttribute(k_leapfrog_steps_lean<M, S>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         smem) == cudaSuccess;
-          }();
+          });
           if (configured) {
             k_leapfrog_steps_lean<M, S><<<grid_for(n), kBlock, smem, s>>>(
                 P(m), n, es, cs, io.q, io.p, io.dt, io.dt_pc, io.n_step, o, io.status, io.n_done,
@@ -754,9 +770,12 @@ struct Launch {
     }
     const int rc = dispatch_solver(solver, [&]<int S>() {
       constexpr int smem = nuts_smem_bytes<M>();
-      static const bool configured =
-          cudaFuncSetAttribute(k_nuts_sample<M, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               smem) == cudaSuccess;
+      static std::atomic<uint64_t> ready{0};
+      const bool configured = once_per_device(ready, [] {
+        return cudaFuncSetAttribute(k_nuts_sample<M, S>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    smem) == cudaSuccess;
+      });
       if (!configured) {
         g_err = "shared-memory configuration of the dynamic sampler failed";
         return (int)MLB_ERR_CUDA;
