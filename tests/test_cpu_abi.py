@@ -167,6 +167,29 @@ def test_reference_api_surface():
     assert mlift is me and mlift.solvers is mlb.solvers
     # out-of-scope baselines stay importable by name (transitions.py:9,66,129)
     import mlift.transitions  # noqa: F401
+    # mlift.linalg: all four functions with the reference's parameter names (linalg.py:6,12,46,88)
+    import mlift.linalg as la
+
+    for fn, params in [("lu_triangular_solve", ["l", "u", "b"]),
+                       ("jvp_cholesky_mtx_mult_by_vct", ["tangents", "chol_mtx", "vct"]),
+                       ("tridiagonal_solve", ["a", "b", "c", "d"]),
+                       ("tridiagonal_pos_def_log_det", ["a", "b"])]:
+        assert list(inspect.signature(getattr(la, fn)).parameters) == params, fn
+    # closures of GaussianProcessModelSystem by the reference's names (systems.py:878-913)
+    for fn, params in [("lmult_by_jacob_constr", ["dy_du", "dy_dn", "vct"]),
+                       ("rmult_by_jacob_constr", ["dy_du", "dy_dn", "vct"]),
+                       ("decompose_gram", ["dy_du", "dy_dn"]),
+                       ("lmult_by_inv_gram", ["dy_du", "dy_dn", "chol_cap_mtx", "vct"]),
+                       ("lmult_by_inv_jacob_product",
+                        ["dy_du_l", "dy_dn_l", "dy_du_r", "dy_dn_r", "vct"])]:
+        assert list(inspect.signature(getattr(mlb.gaussian_process, fn)).parameters) == params, fn
+    # the dynamic sampler is built as the reference builds Mici's (utils.py:286-288) and
+    # carries Mici's defaults
+    sig = inspect.signature(mlb.samplers.DynamicMultinomialHMC.__init__)
+    assert list(sig.parameters)[1:4] == ["system", "integrator", "rng"]
+    assert sig.parameters["max_tree_depth"].default == 10
+    assert sig.parameters["max_delta_h"].default == 1000.0
+    assert sig.parameters["do_extra_subtree_checks"].default is True
 
 
 def test_header_is_plain_c():
