@@ -511,6 +511,7 @@ int mlb_leapfrog_steps_host(const mlb_model* m, int64_t n, double* q, double* p,
       StepsIO io{d_q, d_p, dt, nullptr, n_step, d_status, d_done, d_itf, d_itr,
                  h_init ? d_h0 : nullptr, h_final ? d_h1 : nullptr};
       io.row_major = small_state;
+      io.batch_total = n;
       if ((rc = m->ops->steps(m, opts->solver, nc, nc, o, io, s)) != MLB_OK) break;
       if (!small_state) {
         if ((rc = mlb_soa_to_aos(nc, Q, d_q, nc, d_aos_q, s)) != MLB_OK) break;

@@ -302,6 +302,10 @@ __global__ void __launch_bounds__(kBlock)
 #define MLB_TMA_STATE 1
 #endif
 
+}  // namespace mlb
+#include "mlb_duo.cuh"
+namespace mlb {
+
 template <class M, int SOLVER>
 __global__ void __launch_bounds__(kBlock, MLB_LF_MIN_BLOCKS)
     k_leapfrog_steps(const __grid_constant__ typename M::Params P, int64_t n, int64_t es,
@@ -545,6 +549,9 @@ struct StepsIO {
   // q, p given as chain-major rows [n][Q] (the reference's layout) instead of [Q][ld];
   // only the register-resident family reads it (it touches q, p once per launch)
   bool row_major = false;
+  // chains of the whole batch this launch is a chunk of (host entry point: its chunks run
+  // concurrently, so the small-launch form is chosen by the batch, not by the chunk); 0 = n
+  int64_t batch_total = 0;
   // sampler use of the ODE family's host-driven path: project p onto the cotangent space
   // first (h_init is taken after that), and stop a chain with MLB_ST_H_DIVERGED when
   // |h - h_init| > max_delta_h after a step (<= 0: no check)
@@ -712,6 +719,33 @@ struct Launch {
                    const StepsIO& io, cudaStream_t s) {
     return dispatch_solver(solver, [&]<int S>() {
       const int64_t es = io.row_major ? 1 : ld, cs = io.row_major ? (int64_t)M::Q : 1;
+      {
+        // small launches (at most one warp per scheduler): two warps per 32 chains, the
+        // reversibility check one step behind the trajectory (mlb_duo.cuh);
+        // MLB_DUO_MAX_CHAINS overrides the threshold (0 switches the form off)
+        static const int64_t duo_max = [] {
+          const char* e = std::getenv("MLB_DUO_MAX_CHAINS");
+          return e ? (int64_t)std::atoll(e) : (int64_t)-1;
+        }();
+        // (8,192 chains x 32 eight-schools steps: 0.254 -> 0.161 ms; 16,384: 0.256 -> 0.227;
+        // 32,768: 0.327 -> 0.429: profiles/r6r_duo_sweep.txt)
+        const int64_t lim = duo_max >= 0 ? duo_max : sm_count() * 112;
+        if ((io.batch_total > n ? io.batch_total : n) <= lim) {
+          constexpr int smem = duo_smem_bytes<M>();
+          static std::atomic<uint64_t> ready{0};
+          const bool configured = once_per_device(ready, [] {
+            return cudaFuncSetAttribute(k_leapfrog_steps_duo<M, S>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        smem) == cudaSuccess;
+          });
+          if (configured) {
+            k_leapfrog_steps_duo<M, S><<<(unsigned)((n + 31) / 32), 64, smem, s>>>(
+                P(m), n, es, cs, io.q, io.p, io.dt, io.dt_pc, io.n_step, o, io.status, io.n_done,
+                io.iters_fwd, io.iters_rev, io.h_init, io.h_final);
+            return finish_launch();
+          }
+        }
+      }
       if constexpr (kHasLean) {
         // the parked form holds 7 CTAs per SM against 4: taken when the batch is more than
         // one wave of the register-resident kernel but fits one wave of the parked one

@@ -397,6 +397,50 @@ def test_host_buffer_entry_point_chunk_pipeline():
         assert np.allclose(f64[1], cpu(dev.h_final), rtol=1e-14, atol=0, equal_nan=True)
 
 
+@pytest.mark.parametrize("kind,solver,dt,max_iters,rev_tol", [
+    ("hier", "newton", 1.0, 8, 2e-8), ("hier", "quasi_newton", 0.4, 9, 2e-8),
+    ("hier", "newton_line_search", 1.0, 8, 2e-8), ("toy", "newton", 0.15, 50, 2e-8),
+    ("toy", "quasi_newton", 0.15, 50, 2e-8)])
+def test_small_launch_form_matches_large_batch(kind, solver, dt, max_iters, rev_tol):
+    """Launches below ~16,000 chains take the two-warp form of the fused trajectory kernel
+    (csrc/mlb_duo.cuh: reversibility check on a second warp, one step behind, speculative
+    steps discarded on a failed verdict); larger ones the one-warp forms.  The same chains
+    run alone (small launch) and as the head of a 40,000-chain batch must give the same
+    statuses, completed steps, iteration counts and states (not bitwise: the small-launch
+    form does not fuse the interior half kicks), failures included: step sizes and iteration
+    caps make eight-schools chains fail at different steps in the forward and in the reverse
+    solve, and the toy model's chains also fail the reversibility check itself (for 3,000
+    chains x 6 steps at dt = 0.15 the oracle counts 104 not converged, 57 non-reversible)."""
+    mlb = _mlb()
+    _, _, cm, gm, gs, q = make_case(kind, "unbounded" if kind == "hier" else None, 40000)
+    p = tangent_momentum(cm, q)
+    fn = {"newton": mlb.jitted_solve_projection_onto_manifold_newton,
+          "quasi_newton": mlb.jitted_solve_projection_onto_manifold_quasi_newton,
+          "newton_line_search":
+              mlb.jitted_solve_projection_onto_manifold_newton_with_line_search}[solver]
+    integ = mlb.integrators.ConstrainedLeapfrogIntegrator(
+        gs, dt, projection_solver=fn, reverse_check_tol=rev_tol,
+        projection_solver_kwargs=dict(constraint_tol=1e-9, position_tol=1e-8,
+                                      max_iters=max_iters))
+    big = integ.steps(mlb.states.ChainState(q, p), 6, raise_on_failure=False)
+    m = 3000
+    small = integ.steps(mlb.states.ChainState(q[:m], p[:m]), 6, raise_on_failure=False)
+    st_b, st_s = cpu(big.status)[:m], cpu(small.status)
+    nd_b, nd_s = cpu(big.n_done)[:m], cpu(small.n_done)
+    assert (st_s != 0).any() and (st_s == 0).any()  # both outcomes are exercised
+    if kind == "toy" and solver == "newton":
+        assert (st_s == 3).sum() > 10 and (st_s == 2).sum() > 10  # failed checks, failed solves
+    # a solve decided by rounding (iteration count tie at a tolerance) may differ: rare
+    same = (st_b == st_s) & (nd_b == nd_s) & (cpu(big.iters_fwd)[:m] == cpu(small.iters_fwd)) \
+        & (cpu(big.iters_rev)[:m] == cpu(small.iters_rev))
+    assert same.mean() > 0.995, same.mean()
+    assert rel_err(cpu(small.pos)[same], cpu(big.pos)[:m][same]) < 1e-10
+    assert rel_err(cpu(small.mom)[same], cpu(big.mom)[:m][same]) < 1e-10
+    ok = same & (st_s == 0)
+    assert np.allclose(cpu(small.h_final)[ok], cpu(big.h_final)[:m][ok], rtol=1e-11, atol=0)
+    assert np.allclose(cpu(small.h_init), cpu(big.h_init)[:m], rtol=1e-13, atol=0)
+
+
 def test_full_size_properties_65536_chains():
     """BASELINE config 3 at full size: size-independent properties (the oracle is not run
     at this size): on-manifold, tangent momentum, energy error O(dt^2), reversibility."""
