@@ -42,6 +42,9 @@ struct PhasedLayout {
   double* base;
   int64_t lds;
   int U, Y, NGND;
+  // first column of this VIEW of the allocation (chain i of the view lives in column
+  // col0 + i; the list of still-iterating chains and the counter belong to the allocation)
+  int64_t col0 = 0;
   __host__ __device__ int64_t rows_main() const { return StreamScratch::rows(U, Y); }
   // + one row for the list of still-iterating chains (lds int32 used) + one for the counter
   __host__ __device__ int64_t rows_total() const {
@@ -54,11 +57,12 @@ struct PhasedLayout {
     Phased p;
     p.lds = lds;
     double* after = base + StreamScratch::rows(U, Y) * lds;
-    p.hpart = Col{after + i, lds};
-    p.cd = after + (int64_t)NGND * lds;
-    p.ct = reinterpret_cast<int32_t*>(p.cd + (int64_t)CD_DBL_ROWS * lds);
+    p.hpart = Col{after + col0 + i, lds};
+    double* cd0 = after + (int64_t)NGND * lds;
+    p.cd = cd0 + col0;
+    p.ct = reinterpret_cast<int32_t*>(cd0 + (int64_t)CD_DBL_ROWS * lds) + col0;
 #ifdef __CUDA_ARCH__
-    p.S = StreamScratch::make(base, lds, i, U, Y);
+    p.S = StreamScratch::make(base, lds, col0 + i, U, Y);
 #endif
     return p;
   }
@@ -754,8 +758,18 @@ __global__ void __launch_bounds__(kStreamBlock)
 
 // ------------------------------------------------------------------------ host driver
 template <class M, int SOLVER>
+int phased_leapfrog_steps_overlapped(const mlb_model* m, const OdeData& D, int64_t n,
+                                     int64_t ld, const Opts& o, const StepsIO& io,
+                                     cudaStream_t s);
+inline bool ode_overlap_enabled();
+
+template <class M, int SOLVER>
 int phased_leapfrog_steps(const mlb_model* m, const OdeData& D, int64_t n, int64_t ld,
                           const Opts& o, const StepsIO& io, cudaStream_t s) {
+  // plain trajectories of two steps or more: reversibility checks one step behind (below)
+  if (io.n_step >= 2 && !io.project_first && !io.alive_mask && io.max_delta_h <= 0.0 &&
+      ode_overlap_enabled())
+    return phased_leapfrog_steps_overlapped<M, SOLVER>(m, D, n, ld, o, io, s);
   constexpr int U = M::U;
   PhasedLayout L;
   L.lds = pad32(n), L.U = U, L.Y = D.Y, L.NGND = M::NG * M::ND;
@@ -846,6 +860,201 @@ int phased_leapfrog_steps(const mlb_model* m, const OdeData& D, int64_t n, int64
     if (io.n_step <= 0) break;
   }
   MLB_KP((kp_finish<M><<<g1, blk, 0, s>>>(L, n, io.status, io.n_done, io.iters_fwd,
+                                          io.iters_rev, io.h_init, io.h_final)));
+#undef MLB_KP
+  return MLB_OK;
+}
+
+// ---------------------------------------------- reversibility check one step behind
+// The reverse solve of step s only yields a verdict; nothing of step s + 1 needs its
+// result (mlb_duo.cuh does the same inside one kernel for the register-resident family).
+// Here every chain gets a TWIN column (columns [n, 2 n) of a scratch allocation twice as
+// wide): at the end of step s the twin receives a copy of what the check needs - working
+// (q, p) projected at the new point, Jacobian blocks / Gram factor there, the committed
+// state of the start of the step - and its reverse solve then runs in the SAME solver
+// rounds as the chain's forward solve of step s + 1: one compaction, one Jacobian sweep, one
+// update kernel over the virtual chains of both.  The sweeps of small batches cost the same
+// whatever they carry (1.75 ms for 64 ... 3,232 Hodgkin-Huxley chains), so a step costs
+// max(forward, reverse) rounds instead of their sum.  The chain commits step s
+// optimistically; a failed verdict rolls it back to the state its twin saved (and stops its
+// speculative forward solve before its iterations are counted), so states, statuses,
+// completed steps and iteration counts are those of the sequential integrator.  All
+// kernels are the ones above, launched on three views of the same layout (chains, twins,
+// both); two small kernels copy a chain to its twin and apply a verdict.
+template <int NCH>
+__global__ void __launch_bounds__(32 * NCH)
+    kp_twin_copy(PhasedLayout Lm, PhasedLayout Lt, int64_t n, int64_t ld, const double* q,
+                 const double* p, double* tq, double* tp, int64_t tld, int gram_rows,
+                 int jac_rows) {
+  const int64_t i = (int64_t)blockIdx.x * 32 + threadIdx.x;
+  if (i >= n) return;
+  const Phased P = Lm.at(i), T = Lt.at(i);
+  const int alive = P.I(CT_ALIVE, i);
+  if (threadIdx.y == 0) {
+    T.I(CT_ALIVE, i) = alive, T.I(CT_STATUS, i) = MLB_ST_OK;
+    T.I(CT_DONE, i) = P.I(CT_DONE, i), T.Dv(CD_HLAST, i) = P.Dv(CD_HLAST, i);
+  }
+  if (!alive) return;
+  const int Q = Lm.U + Lm.Y;
+  const Col qw = col(q, ld, i), pw = col(p, ld, i), tqw = col(tq, tld, i), tpw = col(tp, tld, i);
+  for (int k = threadIdx.y; k < Q; k += NCH) {
+    tqw[k] = qw[k], tpw[k] = pw[k];
+    T.S.cq[k] = P.S.cq[k], T.S.cp[k] = P.S.cp[k];
+  }
+  for (int k = threadIdx.y; k < jac_rows; k += NCH) T.S.Jc[k] = P.S.Jc[k];
+  for (int k = threadIdx.y; k < gram_rows; k += NCH) T.S.Gc[k] = P.S.Gc[k];
+}
+
+// verdict of the twin's reverse solve + check (kp_solve_end on the twin view has run):
+// failure -> the chain dies at the state the twin saved; the twin is retired either way
+template <int NCH>
+__global__ void __launch_bounds__(32 * NCH)
+    kp_apply_verdict(PhasedLayout Lm, PhasedLayout Lt, int64_t n, int64_t ld, double* q,
+                     double* p) {
+  const int64_t i = (int64_t)blockIdx.x * 32 + threadIdx.x;
+  if (i >= n) return;
+  const Phased P = Lm.at(i), T = Lt.at(i);
+  const int tst = T.I(CT_STATUS, i);
+  const bool failed = P.I(CT_ALIVE, i) && tst != MLB_ST_OK;
+  if (failed) {
+    const int Q = Lm.U + Lm.Y;
+    const Col qw = col(q, ld, i), pw = col(p, ld, i);
+    for (int k = threadIdx.y; k < Q; k += NCH) {
+      const double a = T.S.cq[k], b = T.S.cp[k];
+      qw[k] = a, pw[k] = b, P.S.cq[k] = a, P.S.cp[k] = b;
+    }
+  }
+  __syncthreads();  // every warp has read the chain's flags
+  if (threadIdx.y != 0) return;
+  if (failed) {
+    P.I(CT_STATUS, i) = tst, P.I(CT_ALIVE, i) = 0, P.I(CT_ACTIVE, i) = 0;
+    P.I(CT_DONE, i) = T.I(CT_DONE, i), P.Dv(CD_HLAST, i) = T.Dv(CD_HLAST, i);
+  }
+  T.I(CT_ALIVE, i) = 0, T.I(CT_ACTIVE, i) = 0;
+}
+
+template <class M>
+__global__ void __launch_bounds__(kStreamBlock)
+    kp_merge_twin_counts(PhasedLayout Lm, PhasedLayout Lt, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Lm.at(i).I(CT_TR, i) += Lt.at(i).I(CT_TR, i);
+}
+
+inline bool ode_overlap_enabled() {
+  static const bool v = [] {
+    const char* e = std::getenv("MLB_ODE_OVERLAP");
+    return !e || std::atoi(e) != 0;
+  }();
+  return v;
+}
+
+template <class M, int SOLVER>
+int phased_leapfrog_steps_overlapped(const mlb_model* m, const OdeData& D, int64_t n,
+                                     int64_t ld, const Opts& o, const StepsIO& io,
+                                     cudaStream_t s) {
+  constexpr int U = M::U;
+  constexpr int NCH = kChunkWarps;
+  const int Q = U + D.Y;
+  PhasedLayout Lf;  // both: chains in columns [0, n), twins in [n, 2 n)
+  Lf.lds = pad32(2 * n), Lf.U = U, Lf.Y = D.Y, Lf.NGND = M::NG * M::ND;
+  ScratchBuf sb;
+  int rc = sb.alloc(Lf.rows_total() + 2 * (int64_t)Q, Lf.lds, s);
+  if (rc != MLB_OK) return rc;
+  Lf.base = sb.p;
+  PhasedLayout Lm = Lf, Lt = Lf;
+  Lt.col0 = n;
+  double* const tq = sb.p + Lf.rows_total() * Lf.lds + n;  // twins' working (q, p)
+  double* const tp = tq + (int64_t)Q * Lf.lds;
+  int* counter = reinterpret_cast<int*>(sb.p + (Lf.rows_total() - 1) * Lf.lds);
+  std::lock_guard<std::mutex> lock(m->pin_mutex);
+  if (!m->pinned_word && cudaMallocHost((void**)&m->pinned_word, sizeof(int)) != cudaSuccess) {
+    g_err = "pinned counter allocation failed";
+    return MLB_ERR_CUDA;
+  }
+  int* host_count = m->pinned_word;
+  const dim3 blk(kStreamBlock), g1(sgrid(n));
+  const dim3 cblk(32, NCH);
+  constexpr size_t sh_eval = sizeof(double) * 32 * (U * U + 1);
+  constexpr size_t sh_proj = sizeof(double) * 32 * (U + 1 > NCH ? U + 1 : NCH);
+  constexpr size_t sh_upd = sizeof(double) * 32 * (U * U + U > NCH ? U * U + U : NCH);
+#define MLB_KP(call)                                  \
+  do {                                                \
+    call;                                             \
+    if ((rc = finish_launch()) != MLB_OK) return rc;  \
+  } while (0)
+  auto read_counter = [&]() -> int {
+    cudaMemcpyAsync(host_count, counter, sizeof(int), cudaMemcpyDeviceToHost, s);
+    cudaMemsetAsync(counter, 0, sizeof(int), s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) return -1;
+    return *host_count;
+  };
+  // solver rounds over the still-iterating virtual chains of BOTH views
+  auto rounds = [&]() -> int {
+    MLB_KP((kp_compact<M><<<1, 1024, 0, s>>>(Lf, 2 * n, counter)));
+    int active = read_counter();
+    while (active > 0) {
+      const dim3 ga(sgrid(active));
+      if (SOLVER == MLB_SOLVER_QUASI_NEWTON)
+        MLB_KP((kp_constr<M><<<ga, blk, 0, s>>>(D, Lf, active)));
+      else if ((rc = launch_jacob<M, false>(D, Lf, active, ld, io.q, s)) != MLB_OK)
+        return rc;
+      MLB_KP((kp_update<M, SOLVER, NCH><<<ga, cblk, sh_upd, s>>>(Lf, active, o)));
+      MLB_KP((kp_compact<M><<<1, 1024, 0, s>>>(Lf, 2 * n, counter)));
+      active = read_counter();
+    }
+    if (active < 0) {
+      g_err = "stream synchronisation failed in the solver loop";
+      return MLB_ERR_CUDA;
+    }
+    return MLB_OK;
+  };
+  auto verdict = [&]() -> int {  // close the twins' reverse solve and apply it
+    MLB_KP((kp_solve_end<M, NCH><<<g1, cblk, 0, s>>>(Lt, n, Lf.lds, tq, tp, io.dt, io.dt_pc, -1.0,
+                                                     o, 0)));
+    MLB_KP((kp_apply_verdict<NCH><<<g1, cblk, 0, s>>>(Lm, Lt, n, ld, io.q, io.p)));
+    return MLB_OK;
+  };
+  cudaMemsetAsync(counter, 0, sizeof(int), s);
+  MLB_KP((kp_begin<M, NCH><<<g1, cblk, 0, s>>>(Lm, n, ld, io.q, io.p, nullptr)));
+  // twins start retired (control block zero: not alive, not active, status OK, counts 0)
+  {
+    const Phased T0 = Lt.at(0);
+    cudaMemset2DAsync(T0.ct, sizeof(int32_t) * Lf.lds, 0, sizeof(int32_t) * n, CT_INT_ROWS, s);
+  }
+  if ((rc = launch_jacob<M, true>(D, Lm, n, ld, io.q, s)) != MLB_OK) return rc;
+  MLB_KP((kp_eval_mid<M, NCH><<<g1, cblk, sh_eval, s>>>(D, Lm, n, ld, io.q, io.p)));
+  if ((rc = launch_second_order<M>(D, Lm, n, ld, io.q, s)) != MLB_OK) return rc;
+  for (int step = 0; step < io.n_step; ++step) {
+    const int first = step == 0;
+    // opening half kick + projection, forward retraction start
+    MLB_KP((kp_kick_project<M, NCH><<<g1, cblk, sh_proj, s>>>(Lm, n, ld, io.p, io.q, io.dt,
+                                                             io.dt_pc, first, 1, first, 0, 0.0)));
+    MLB_KP((kp_solve_begin<M, NCH><<<g1, cblk, 0, s>>>(Lm, n, ld, io.q, io.p, io.dt, io.dt_pc, 1.0,
+                                                       o.max_iters)));
+    // forward solve of this step together with the reverse solve of the previous one
+    if ((rc = rounds()) != MLB_OK) return rc;
+    if (step > 0 && (rc = verdict()) != MLB_OK) return rc;
+    MLB_KP((kp_solve_end<M, NCH><<<g1, cblk, 0, s>>>(Lm, n, ld, io.q, io.p, io.dt, io.dt_pc, 1.0, o,
+                                                     1)));
+    // evaluation at the new position, projection of the momentum there
+    if ((rc = launch_jacob<M, true>(D, Lm, n, ld, io.q, s)) != MLB_OK) return rc;
+    MLB_KP((kp_eval_mid<M, NCH><<<g1, cblk, sh_eval, s>>>(D, Lm, n, ld, io.q, io.p)));
+    if ((rc = launch_second_order<M>(D, Lm, n, ld, io.q, s)) != MLB_OK) return rc;
+    MLB_KP((kp_kick_project<M, NCH><<<g1, cblk, sh_proj, s>>>(Lm, n, ld, io.p, io.q, io.dt,
+                                                             io.dt_pc, 1, 0, 0, 0, 0.0)));
+    // hand the check of this step to the twins, then close the step optimistically
+    MLB_KP((kp_twin_copy<NCH><<<g1, cblk, 0, s>>>(Lm, Lt, n, ld, io.q, io.p, tq, tp, Lf.lds,
+                                                  U * U + D.Y, U * D.Y + D.Y)));
+    MLB_KP((kp_solve_begin<M, NCH><<<g1, cblk, 0, s>>>(Lt, n, Lf.lds, tq, tp, io.dt, io.dt_pc, -1.0,
+                                                       o.max_iters)));
+    MLB_KP((kp_kick_project<M, NCH><<<g1, cblk, sh_proj, s>>>(Lm, n, ld, io.p, io.q, io.dt,
+                                                             io.dt_pc, 0, 1, 0, 1, 0.0)));
+  }
+  if ((rc = rounds()) != MLB_OK) return rc;  // the last step's check runs alone
+  if ((rc = verdict()) != MLB_OK) return rc;
+  MLB_KP((kp_merge_twin_counts<M><<<g1, blk, 0, s>>>(Lm, Lt, n)));
+  MLB_KP((kp_finish<M><<<g1, blk, 0, s>>>(Lm, n, io.status, io.n_done, io.iters_fwd,
                                           io.iters_rev, io.h_init, io.h_final)));
 #undef MLB_KP
   return MLB_OK;

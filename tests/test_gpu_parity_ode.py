@@ -400,6 +400,39 @@ def test_fn_host_buffer_entry_point():
 
 
 # ------------------------------------------------- host-driven sub-phase path vs one kernel
+@pytest.mark.parametrize("solver,dt,max_iters", [(co.SOLVER_NEWTON, 0.25, 4),
+                                                 (co.SOLVER_NEWTON, 0.3, 8),
+                                                 (co.SOLVER_QUASI_NEWTON, 0.12, 6)])
+def test_phased_path_with_checks_one_step_behind_handles_failures(solver, dt, max_iters):
+    """Trajectories of two steps or more run the reversibility check of step s on a twin of
+    the chain, in the solver rounds of step s + 1, and commit optimistically
+    (csrc/mlb_stream_phased.cuh, `phased_leapfrog_steps_overlapped`); a failed verdict rolls
+    the chain back and discards the speculative forward solve.  Step size and iteration cap
+    make FitzHugh-Nagumo chains fail in forward solves, reverse solves and checks at
+    different steps: statuses, completed steps, iteration counts and states must be those
+    of the sequential one-kernel path."""
+    mlb, g, cm, gm, gs = fn_case()
+    q = fn_states(cm, 160)
+    p = tangent_momentum(cm, q)
+    outs = []
+    for single in (False, True):
+        integ = mlb.integrators.ConstrainedLeapfrogIntegrator(
+            gs, dt, projection_solver={v: k for k, v in mlb.solvers.SOLVER_IDS.items()}[solver],
+            projection_solver_kwargs=dict(constraint_tol=1e-9, position_tol=1e-8,
+                                          max_iters=max_iters))
+        integ.single_kernel = single
+        outs.append(integ.steps(mlb.states.ChainState(q, p), 5, raise_on_failure=False))
+    a, b = outs
+    sa, sb = cpu(a.status), cpu(b.status)
+    assert (sa != 0).sum() >= 5 and (sa == 0).sum() >= 5, np.bincount(sa)
+    assert len(np.unique(cpu(b.n_done)[sb != 0])) >= 2  # failures at different steps
+    same = (sa == sb) & (cpu(a.n_done) == cpu(b.n_done)) \
+        & (cpu(a.iters_fwd) == cpu(b.iters_fwd)) & (cpu(a.iters_rev) == cpu(b.iters_rev))
+    assert same.mean() > 0.93, (same.mean(), np.bincount(sa), np.bincount(sb))
+    assert scaled_err(cpu(a.pos)[same], cpu(b.pos)[same]) < 1e-10
+    assert scaled_err(cpu(a.mom)[same], cpu(b.mom)[same]) < 1e-6
+
+
 @pytest.mark.parametrize("model", ["fn", "hh"])
 @pytest.mark.parametrize("solver", [co.SOLVER_QUASI_NEWTON, co.SOLVER_NEWTON])
 def test_phased_path_matches_single_kernel(model, solver):
