@@ -729,7 +729,9 @@ struct Launch {
         }();
         // (8,192 chains x 32 eight-schools steps: 0.254 -> 0.161 ms; 16,384: 0.256 -> 0.227;
         // 32,768: 0.327 -> 0.429: profiles/r6r_duo_sweep.txt)
-        const int64_t lim = duo_max >= 0 ? duo_max : sm_count() * 112;
+        // toy model (3 state components, 100 registers): still ahead at 32,768 chains
+        // (0.193 -> 0.163 ms), behind at 65,536 (profiles/r6zz_toy_duo.txt)
+        const int64_t lim = duo_max >= 0 ? duo_max : sm_count() * (M::Q <= 4 ? 256 : 112);
         if ((io.batch_total > n ? io.batch_total : n) <= lim) {
           constexpr int smem = duo_smem_bytes<M>();
           static std::atomic<uint64_t> ready{0};
