@@ -21,8 +21,9 @@
 // speculative work and its iteration counts, so states, statuses, completed steps and
 // iteration counts are those of the sequential integrator.  The chain's critical path per
 // step drops from (forward solve + evaluation + kicks + reverse solve) to the first three.
-// Interior half kicks are not fused here (the closing kick of every step is formed, as in
-// Mici): the candidate state of every step has to exist before its verdict.
+// Interior half kicks are fused as in the one-warp kernels (one kick of dt and one projection
+// at a step boundary); the candidate state of step s, which has to exist before its verdict,
+// takes its momentum as the mean of the momenta before and after that kick.
 #pragma once
 // (included by mlb_launch.cuh after load_vec / store_vec)
 
@@ -43,6 +44,7 @@ __global__ void __launch_bounds__(64, 1)
   using B = typename M::B;
   constexpr int Q = M::Q, Y = M::Y;
   constexpr bool kMuFromDiff = SOLVER == MLB_SOLVER_QUASI_NEWTON || SOLVER == MLB_SOLVER_NEWTON;
+  constexpr bool kFuse = MLB_FUSE_KICKS != 0;  // fused interior half kicks (see back(s))
   extern __shared__ double duo_sm[];
   const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;  // 0 driver, 1 checker
   double* const col = duo_sm + lane;                            // element r at col[r * 32]
@@ -81,9 +83,11 @@ __global__ void __launch_bounds__(64, 1)
       if (s < n_step) {
         int pub = 0;
         if (alive) {  // front(s): everything up to the momentum projected at the new point
+          if (!kFuse || s == 0) {  // (else the opening kick was fused into back(s - 1))
 #pragma unroll
-          for (int k = 0; k < Q; ++k) pw[k] = fma(-0.5 * dti, C.g[k], pw[k]);
-          B::project_cotangent(C.J, C.G, pw);
+            for (int k = 0; k < Q; ++k) pw[k] = fma(-0.5 * dti, C.g[k], pw[k]);
+            B::project_cotangent(C.J, C.G, pw);
+          }
           double qs[Q], mu[Q];
 #pragma unroll
           for (int k = 0; k < Q; ++k) qs[k] = fma(dti, pw[k], qw[k]);
@@ -134,12 +138,28 @@ __global__ void __launch_bounds__(64, 1)
         if (front_st != MLB_ST_OK) {
           st = front_st, alive = false;
         } else {
+          if (kFuse && s + 1 < n_step) {
+            // interior boundary: ONE kick of dt and one projection open step s + 1; the
+            // candidate momentum of step s, P(p - dt/2 g) = p - dt/2 P g (the projection is
+            // linear and p is already tangent), is the mean of p and that
+            double pc[Q];
 #pragma unroll
-          for (int k = 0; k < Q; ++k) pw[k] = fma(-0.5 * dti, C.g[k], pw[k]);
-          B::project_cotangent(C.J, C.G, pw);
+            for (int k = 0; k < Q; ++k) pc[k] = pw[k], pw[k] = fma(-dti, C.g[k], pw[k]);
+            B::project_cotangent(C.J, C.G, pw);
 #pragma unroll
-          for (int k = 0; k < Q; ++k) col[(CQ + k) * 32] = qw[k], col[(CP + k) * 32] = pw[k];
-          h_cand = hamiltonian<M>(C, pw);
+            for (int k = 0; k < Q; ++k) {
+              pc[k] = 0.5 * (pc[k] + pw[k]);
+              col[(CQ + k) * 32] = qw[k], col[(CP + k) * 32] = pc[k];
+            }
+            h_cand = want_h ? hamiltonian<M>(C, pc) : 0.0;
+          } else {
+#pragma unroll
+            for (int k = 0; k < Q; ++k) pw[k] = fma(-0.5 * dti, C.g[k], pw[k]);
+            B::project_cotangent(C.J, C.G, pw);
+#pragma unroll
+            for (int k = 0; k < Q; ++k) col[(CQ + k) * 32] = qw[k], col[(CP + k) * 32] = pw[k];
+            h_cand = hamiltonian<M>(C, pw);
+          }
         }
       }
     } else if (s < n_step && valid && isl[(IPUB + (s & 1)) * 32]) {

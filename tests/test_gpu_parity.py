@@ -406,8 +406,8 @@ def test_small_launch_form_matches_large_batch(kind, solver, dt, max_iters, rev_
     (csrc/mlb_duo.cuh: reversibility check on a second warp, one step behind, speculative
     steps discarded on a failed verdict); larger ones the one-warp forms.  The same chains
     run alone (small launch) and as the head of a 40,000-chain batch must give the same
-    statuses, completed steps, iteration counts and states (not bitwise: the small-launch
-    form does not fuse the interior half kicks), failures included: step sizes and iteration
+    statuses, completed steps, iteration counts and states (to rounding: the candidate
+    momentum of a step is formed differently), failures included: step sizes and iteration
     caps make eight-schools chains fail at different steps in the forward and in the reverse
     solve, and the toy model's chains also fail the reversibility check itself (for 3,000
     chains x 6 steps at dt = 0.15 the oracle counts 104 not converged, 57 non-reversible)."""
