@@ -32,6 +32,7 @@ struct FnOde {
   static constexpr int NG = 6, PAIRS_PER_GROUP = NPAIR / NG;  // second-order pass split
   static constexpr int ROLE_DIRS = 2, N_ROLE = ND / ROLE_DIRS;  // Jacobian sweep split
   static constexpr int ROLE_DIRS_WIDE = MLB_FN_ROLE_DIRS_WIDE, WIDE_MIN_CHAINS = 8192;
+  static constexpr int WIDE_MIN_CHAINS_SO = 8192;
   static constexpr int NG_WIDE = MLB_FN_NG_WIDE;
   static constexpr int GATE_WARPS = 1;  // no cooperative sweep: the RK4 stages are short
   template <int NS1, int NP>

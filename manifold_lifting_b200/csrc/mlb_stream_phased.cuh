@@ -271,6 +271,15 @@ inline int64_t wide_min_chains() {
   return v;
 }
 
+template <class M>
+inline int64_t wide_min_chains_second_order() {
+  static const int64_t v = [] {
+    const char* e = std::getenv("MLB_WIDE_MIN_CHAINS_SO");
+    return e ? (int64_t)std::atoll(e) : (int64_t)M::WIDE_MIN_CHAINS_SO;
+  }();
+  return v;
+}
+
 template <class M, bool EVAL>
 int launch_jacob(const OdeData& D, const PhasedLayout& L, int64_t cnt, int64_t ld,
                  const double* q, cudaStream_t s) {
@@ -453,7 +462,7 @@ __global__ void __launch_bounds__(kStreamBlock)
 template <class M>
 int launch_second_order(const OdeData& D, const PhasedLayout& L, int64_t n, int64_t ld,
                         const double* q, cudaStream_t s) {
-  if (M::NG_WIDE != M::NG && n > wide_min_chains<M>()) {
+  if (M::NG_WIDE != M::NG && n > wide_min_chains_second_order<M>()) {
     kp_second_order<M, M::NG_WIDE><<<dim3(sgrid(n), M::NG_WIDE), kStreamBlock, 0, s>>>(D, L, n, ld, q);
   } else {
     kp_second_order<M, M::NG><<<dim3(sgrid(n), M::NG), kStreamBlock, 0, s>>>(D, L, n, ld, q);
