@@ -553,7 +553,8 @@ def measure(args, ctx, full):
 
     n, total = local_chains(args, world)
     n_step, K, W = args.n_step, args.steps, max(args.warmup, 3)
-    data, q_host, p_host = make_inputs(args, n, rank * n)
+    # (MLB_BENCH_RANK: draw the inputs of another rank's share on a single GPU - diagnostics)
+    data, q_host, p_host = make_inputs(args, n, int(os.environ.get("MLB_BENCH_RANK", rank)) * n)
     y_obs = consts = None
     if args.workload == "hier":
         model = mlb.models.EightSchoolsModel(*data)

@@ -52,11 +52,12 @@ struct HhOde {
   static constexpr int NG = MLB_HH_NG, PAIRS_PER_GROUP = NPAIR / NG;
   static constexpr int ROLE_DIRS = MLB_HH_ROLE_DIRS, N_ROLE = ND / ROLE_DIRS;  // Jacobian sweep split
   // launches of more than WIDE_MIN_CHAINS chains take ROLE_DIRS_WIDE directions per role
-  // (1,536: with the reversibility checks one step behind, the solver rounds of 1,024 chains
-  // carry up to 2,048 virtual chains, which the wide form serves in 107 instead of 143 ms per
-  // 4 steps, while an evaluation sweep of 1,024 chains is better off narrow: 153 ms with the
-  // threshold at 900, profiles/r7b_hh_wide.txt); the second-order sweep switches later
-  static constexpr int ROLE_DIRS_WIDE = MLB_HH_ROLE_DIRS_WIDE, WIDE_MIN_CHAINS = 1536;
+  // (a threshold of 1,536 - the solver rounds carry chains + twins since the reversibility
+  // checks run one step behind - was tried: 107 instead of 143 ms per 4 steps for ONE
+  // 1,024-chain share of the 8-GPU split, but 134 / 125 instead of 116 / 120 ms for two
+  // others and 176 instead of 146 ms on eight GPUs (max over ranks): not kept,
+  // profiles/r7b_hh_wide.txt, r7e_hh_ranks.txt); the second-order sweep has its own threshold
+  static constexpr int ROLE_DIRS_WIDE = MLB_HH_ROLE_DIRS_WIDE, WIDE_MIN_CHAINS = 3072;
   static constexpr int WIDE_MIN_CHAINS_SO = 3072;
   // second-order sweep of a full GPU: all 21 pairs per thread.  At 8,192 chains that is 256
   // warps on 592 schedulers (11.1 ms, 1.7 warps active per SM,
