@@ -37,3 +37,20 @@ def test_cuda_arm_refuses_to_run_without_a_gpu():
                          capture_output=True, text=True, timeout=600, cwd=ROOT)  # fmt: skip
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
     assert not [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+
+
+def test_reference_arm_under_two_ranks_prints_once():
+    """The driver launches `--impl reference` like the CUDA arm (torchrun, one process per
+    GPU): rank 0 alone runs and prints the line - `n_gpus` = 2, the strong-scaling config of
+    the 2-GPU run -, the other rank exits 0 without work."""
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+         "--master-addr", "127.0.0.1", "--master-port", "29617", os.path.join(ROOT, "bench.py"),
+         "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0",
+         "--cpu-sample-chains", "256"], capture_output=True, text=True, timeout=900, cwd=ROOT)  # fmt: skip
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert KEYS <= set(d) and d["impl"] == "reference" and d["n_gpus"] == 2
+    assert d["config"]["chains_total"] == 65536 and d["config"]["chains_per_gpu"] == 32768
